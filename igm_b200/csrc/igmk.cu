@@ -1,0 +1,422 @@
+// igmk.cu - libigmk.so: C ABI (include/igmk.h) + host-side launch logic.
+//
+// Build (see __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -shared -Xcompiler -fPIC -o igm_b200/libigmk.so igm_b200/csrc/igmk.cu
+// -fmad=false: float32 d2 and float64 p/o arithmetic must not be contracted
+// (bit-exact parity with NumPy / CPython).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/igmk.h"
+#include "igmk_actdist.cuh"
+#include "igmk_contact.cuh"
+
+using namespace igmk;
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess)                                                      \
+            return fail(IGMK_ECUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    } while (0)
+
+struct igmk_ctx {
+    int device = 0;
+    int nbead = 0, nstruct = 0, npad = 0, nchunks = 0, n_hap = 0;
+    int sm_count = 0;
+    float* d_coords = nullptr;       // [nbead][3][npad]
+    float* d_radii = nullptr;        // [nbead]
+    HapEntry* d_hap = nullptr;       // [n_hap]
+    std::vector<HapEntry> h_hap;
+    bool have_coords = false, have_index = false;
+    // staging for the *_host entry points
+    void* d_stage = nullptr; size_t stage_bytes = 0;
+    void* d_pairs = nullptr; size_t pairs_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_kernel_ms = 0.f;
+    int block_v_override = 0;
+};
+
+static int ensure(void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return IGMK_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    CUDA_TRY(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return IGMK_OK;
+}
+
+extern "C" int igmk_version(void) { return IGMK_VERSION; }
+extern "C" const char* igmk_last_error(void) { return g_err.c_str(); }
+extern "C" int64_t igmk_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
+    if (!out) return fail(IGMK_EINVAL, "igmk_create: out is NULL");
+    *out = nullptr;
+    if (nbead <= 0 || nstruct <= 0) return fail(IGMK_EINVAL, "igmk_create: nbead and nstruct must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(IGMK_ECUDA, "igmk_create: no CUDA device (%s); there is no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(IGMK_EINVAL, "igmk_create: device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    igmk_ctx* c = new igmk_ctx();
+    c->device = device;
+    c->nbead = nbead;
+    c->nstruct = nstruct;
+    c->npad = (nstruct + 31) / 32 * 32;
+    c->nchunks = (nstruct + 3) / 4;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    const size_t bytes = (size_t)nbead * 3 * c->npad * sizeof(float);
+    e = cudaMalloc(&c->d_coords, bytes);
+    if (e != cudaSuccess) { delete c; return fail(IGMK_ECUDA, "igmk_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    cudaMemset(c->d_coords, 0, bytes);
+    cudaMalloc(&c->d_radii, (size_t)nbead * sizeof(float));
+    cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    const char* ov = getenv("IGMK_BLOCK_V");
+    if (ov) c->block_v_override = atoi(ov);
+    *out = c;
+    return IGMK_OK;
+}
+
+extern "C" int igmk_destroy(igmk_ctx* c) {
+    if (!c) return IGMK_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_coords);
+    cudaFree(c->d_radii);
+    cudaFree(c->d_hap);
+    cudaFree(c->d_stage);
+    cudaFree(c->d_pairs);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return IGMK_OK;
+}
+
+// (nb, nstruct, 3) bead-major AoS  ->  [bead][xyz][npad] SoA
+__global__ void stage_coords_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                    int nstruct, int npad) {
+    const size_t bead = blockIdx.x;
+    const float* s = src + bead * (size_t)nstruct * 3;
+    float* d = dst + bead * (size_t)npad * 3;
+    for (int t = threadIdx.x; t < 3 * nstruct; t += blockDim.x) {
+        const int st = t / 3, c = t - 3 * st;
+        d[(size_t)c * npad + st] = s[t];
+    }
+}
+
+extern "C" int igmk_upload_coords_range(igmk_ctx* c, const float* xyz, int bead0, int nb, int on_device) {
+    if (!c || !xyz) return fail(IGMK_EINVAL, "igmk_upload_coords: NULL argument");
+    if (bead0 < 0 || nb < 0 || bead0 + nb > c->nbead) return fail(IGMK_EINVAL, "igmk_upload_coords: bead range out of bounds");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t per_bead = (size_t)c->nstruct * 3 * sizeof(float);
+    // stage at most 256 MiB at a time
+    int step = (int)((256ull << 20) / per_bead);
+    if (step < 1) step = 1;
+    for (int b = 0; b < nb; b += step) {
+        const int n = (nb - b < step) ? nb - b : step;
+        const float* src = xyz + (size_t)b * c->nstruct * 3;
+        const float* dsrc = src;
+        if (!on_device) {
+            int rc = ensure(&c->d_stage, &c->stage_bytes, (size_t)n * per_bead);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemcpyAsync(c->d_stage, src, (size_t)n * per_bead, cudaMemcpyHostToDevice, c->stream));
+            dsrc = (const float*)c->d_stage;
+        }
+        stage_coords_kernel<<<n, 256, 0, c->stream>>>(dsrc, c->d_coords + (size_t)(bead0 + b) * 3 * c->npad,
+                                                     c->nstruct, c->npad);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    c->have_coords = true;
+    return IGMK_OK;
+}
+
+extern "C" int igmk_upload_coords(igmk_ctx* c, const float* xyz, int on_device) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_upload_coords: NULL context");
+    return igmk_upload_coords_range(c, xyz, 0, c->nbead, on_device);
+}
+
+extern "C" int igmk_set_index(igmk_ctx* c, int n_hap, const int32_t* copy_ptr,
+                              const int32_t* copy_beads, const int32_t* chrom_hap,
+                              const float* radii) {
+    if (!c || !copy_ptr || !copy_beads || !chrom_hap || !radii) return fail(IGMK_EINVAL, "igmk_set_index: NULL argument");
+    if (n_hap <= 0) return fail(IGMK_EINVAL, "igmk_set_index: n_hap must be positive");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<HapEntry> h(n_hap);
+    for (int i = 0; i < n_hap; ++i) {
+        const int nc = copy_ptr[i + 1] - copy_ptr[i];
+        if (nc < 1) return fail(IGMK_EINVAL, "igmk_set_index: bin %d has no copy", i);
+        if (nc > 2) return fail(IGMK_ELIMIT, "igmk_set_index: bin %d has %d copies; at most 2 are supported", i, nc);
+        const int b0 = copy_beads[copy_ptr[i]];
+        const int b1 = (nc == 2) ? copy_beads[copy_ptr[i] + 1] : -1;
+        if (b0 < 0 || b0 >= c->nbead || b1 >= c->nbead) return fail(IGMK_EINVAL, "igmk_set_index: bead id out of range in bin %d", i);
+        h[i].b0 = b0; h[i].b1 = b1; h[i].chrom = chrom_hap[i]; h[i].radius = radii[b0];
+    }
+    if (c->d_hap) { cudaFree(c->d_hap); c->d_hap = nullptr; }
+    CUDA_TRY(cudaMalloc(&c->d_hap, (size_t)n_hap * sizeof(HapEntry)));
+    CUDA_TRY(cudaMemcpy(c->d_hap, h.data(), (size_t)n_hap * sizeof(HapEntry), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_radii, radii, (size_t)c->nbead * sizeof(float), cudaMemcpyHostToDevice));
+    c->h_hap.swap(h);
+    c->n_hap = n_hap;
+    c->have_index = true;
+    return IGMK_OK;
+}
+
+// ------------------------------------------------------------- K1 launches
+template <int V>
+static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel<V>,
+                                                           32 * kWarpsPerBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    long long want = (P.n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long cap = (long long)c->sm_count * per_sm;
+    const int grid = (int)((want < cap) ? want : cap);
+    actdist_warp_kernel<V><<<grid, 32 * kWarpsPerBlock, 0, st>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+template <int V, int MAXT>
+static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, cudaStream_t st) {
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<V, MAXT>, threads, 0));
+    if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_block_kernel<%d> cannot run with %d threads", V, threads);
+    long long cap = (long long)c->sm_count * per_sm;
+    const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
+    actdist_block_kernel<V, MAXT><<<grid, threads, 0, st>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
+    const size_t smem = (size_t)4 * P.nstruct * sizeof(uint32_t);
+    if (smem > 227 * 1024) return fail(IGMK_ELIMIT, "IGMK_ALGO_SIMPLE supports nstruct <= %d", 227 * 1024 / 16);
+    CUDA_TRY(cudaFuncSetAttribute(actdist_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_simple_kernel, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long cap = (long long)c->sm_count * per_sm;
+    const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
+    actdist_simple_kernel<<<grid, 256, smem, st>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+// block-mode shapes: V chunks per thread, at most kBlockMaxThreads[V] threads
+static int block_max_threads(int V) {
+    switch (V) { case 3: return 1024; case 4: return 768; case 6: return 512; case 8: return 384; default: return 0; }
+}
+
+extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
+                                   const int32_t* d_i, const int32_t* d_j,
+                                   const double* d_pwish, const double* d_plast,
+                                   float contact_range, int it_corr, int mode, int algo,
+                                   igmk_pair_result* d_out, void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_actdist: NULL context");
+    if (!c->have_coords || !c->have_index) return fail(IGMK_ESTATE, "igmk_actdist: upload coordinates and index first");
+    if (n_pairs < 0) return fail(IGMK_EINVAL, "igmk_actdist: negative n_pairs");
+    if (mode != IGMK_MODE_LB && mode != IGMK_MODE_GP) return fail(IGMK_EINVAL, "igmk_actdist: bad mode %d", mode);
+    if (n_pairs == 0) return IGMK_OK;
+    if (!d_i || !d_j || !d_pwish || !d_plast || !d_out) return fail(IGMK_EINVAL, "igmk_actdist: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ActdistParams P;
+    P.coords = c->d_coords; P.hap = c->d_hap;
+    P.pi = d_i; P.pj = d_j; P.pwish = d_pwish; P.plast = d_plast; P.out = d_out;
+    P.n_pairs = n_pairs; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
+    P.n_hap = c->n_hap; P.contact_range = contact_range; P.it_corr = it_corr; P.mode = mode;
+
+    if (algo == IGMK_ALGO_SIMPLE) return launch_simple(c, P, st);
+    if (algo != IGMK_ALGO_FAST) return fail(IGMK_EINVAL, "igmk_actdist: bad algo %d", algo);
+
+    if (c->nchunks <= 32 * 8 && c->block_v_override == 0) {
+        const int V = (c->nchunks + 31) / 32;
+        switch (V) {
+            case 1: return launch_warp<1>(c, P, st);
+            case 2: return launch_warp<2>(c, P, st);
+            case 3: return launch_warp<3>(c, P, st);
+            case 4: return launch_warp<4>(c, P, st);
+            case 5: return launch_warp<5>(c, P, st);
+            case 6: return launch_warp<6>(c, P, st);
+            case 7: return launch_warp<7>(c, P, st);
+            default: return launch_warp<8>(c, P, st);
+        }
+    }
+    // larger populations: one pair per CTA
+    static const int prefer[4] = {4, 8, 3, 6};
+    int bestV = 0, bestT = 0;
+    double best_util = -1.0;
+    for (int k = 0; k < 4; ++k) {
+        const int V = prefer[k];
+        if (c->block_v_override && V != c->block_v_override) continue;
+        int T = ((c->nchunks + V - 1) / V + 31) / 32 * 32;
+        if (T < 64) T = 64;
+        if (T > block_max_threads(V)) continue;
+        const double util = (double)c->nchunks / ((double)T * V);
+        if (util > best_util + 0.02) { best_util = util; bestV = V; bestT = T; }
+    }
+    if (!bestV) return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 12288", c->nstruct);
+    switch (bestV) {
+        case 3: return launch_block<3, 1024>(c, P, bestT, st);
+        case 4: return launch_block<4, 768>(c, P, bestT, st);
+        case 6: return launch_block<6, 512>(c, P, bestT, st);
+        default: return launch_block<8, 384>(c, P, bestT, st);
+    }
+}
+
+extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
+                                 const int32_t* i, const int32_t* j,
+                                 const double* pwish, const double* plast,
+                                 float contact_range, int it_corr, int mode, int algo,
+                                 igmk_pair_result* out) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_actdist_host: NULL context");
+    if (n_pairs == 0) return IGMK_OK;
+    if (n_pairs < 0 || !i || !j || !pwish || !plast || !out) return fail(IGMK_EINVAL, "igmk_actdist_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)n_pairs;
+    const size_t off_j = n * 4, off_pw = (n * 8 + 7) / 8 * 8, off_pl = off_pw + n * 8;
+    const size_t off_out = off_pl + n * 8;
+    const size_t total = off_out + n * sizeof(igmk_pair_result);
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, i, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_j, j, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_pw, pwish, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_pl, plast, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = igmk_actdist_device(c, n_pairs, (const int32_t*)base, (const int32_t*)(base + off_j),
+                             (const double*)(base + off_pw), (const double*)(base + off_pl),
+                             contact_range, it_corr, mode, algo,
+                             (igmk_pair_result*)(base + off_out), c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, base + off_out, n * sizeof(igmk_pair_result), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
+    return IGMK_OK;
+}
+
+extern "C" float igmk_last_kernel_ms(igmk_ctx* c) { return c ? c->last_kernel_ms : 0.f; }
+
+// Record expansion, host side: task() flattening + get_actdist's result lists
+// (ActivationDistanceStep.py:221-222, 476-483).
+extern "C" int igmk_expand_records(igmk_ctx* c, int64_t n_pairs,
+                                   const int32_t* pi, const int32_t* pj,
+                                   const igmk_pair_result* res,
+                                   int32_t* row, int32_t* col, float* dist, float* prob,
+                                   int64_t capacity, int64_t* n_records) {
+    if (!c || !c->have_index) return fail(IGMK_ESTATE, "igmk_expand_records: index not set");
+    if (n_pairs < 0 || (n_pairs > 0 && (!pi || !pj || !res))) return fail(IGMK_EINVAL, "igmk_expand_records: bad argument");
+    int64_t k = 0;
+    for (int64_t t = 0; t < n_pairs; ++t) {
+        const igmk_pair_result& r = res[t];
+        if (r.nrec <= 0) continue;
+        const int i = pi[t], j = pj[t];
+        if (i < 0 || j < 0 || i >= c->n_hap || j >= c->n_hap) return fail(IGMK_EINVAL, "igmk_expand_records: pair %lld out of range", (long long)t);
+        const HapEntry& a = c->h_hap[i];
+        const HapEntry& b = c->h_hap[j];
+        if (k + r.nrec > capacity) return fail(IGMK_EINVAL, "igmk_expand_records: capacity %lld too small", (long long)capacity);
+        const int ab[2] = {a.b0, a.b1}, bb[2] = {b.b0, b.b1};
+        const int na = a.b1 >= 0 ? 2 : 1, nb = b.b1 >= 0 ? 2 : 1;
+        if (a.chrom == b.chrom) {
+            const int m = na < nb ? na : nb;                    // zip(ii, jj)
+            for (int u = 0; u < m; ++u) { row[k] = ab[u]; col[k] = bb[u]; dist[k] = r.dist; prob[k] = r.prob; ++k; }
+        } else {
+            for (int u = 0; u < na; ++u)                        // for i0 in ii for i1 in jj
+                for (int w = 0; w < nb; ++w) { row[k] = ab[u]; col[k] = bb[w]; dist[k] = r.dist; prob[k] = r.prob; ++k; }
+        }
+    }
+    if (n_records) *n_records = k;
+    return IGMK_OK;
+}
+
+// ------------------------------------------------------------- K2 launches
+extern "C" int igmk_contact_counts_device(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
+                                          float contact_range, int strict,
+                                          uint32_t* d_counts, void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_contact_counts: NULL context");
+    if (!c->have_coords || !c->have_index) return fail(IGMK_ESTATE, "igmk_contact_counts: upload coordinates and index first");
+    if (row0 < 0 || col0 < 0 || nrows < 0 || ncols < 0 || row0 + nrows > c->nbead || col0 + ncols > c->nbead)
+        return fail(IGMK_EINVAL, "igmk_contact_counts: tile out of range");
+    if (nrows == 0 || ncols == 0) return IGMK_OK;
+    if (!d_counts) return fail(IGMK_EINVAL, "igmk_contact_counts: NULL output");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ContactParams P;
+    P.coords = c->d_coords; P.radii = c->d_radii; P.counts = d_counts;
+    P.nstruct = c->nstruct; P.npad = c->npad; P.nbead = c->nbead;
+    P.row0 = row0; P.nrows = nrows; P.col0 = col0; P.ncols = ncols;
+    P.contact_range = contact_range; P.strict = strict;
+    dim3 grid((ncols + kCtTile - 1) / kCtTile, (nrows + kCtTile - 1) / kCtTile);
+    contact_tile_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+extern "C" int igmk_contact_counts_host(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
+                                        float contact_range, int strict, uint32_t* counts) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_contact_counts_host: NULL context");
+    if (nrows == 0 || ncols == 0) return IGMK_OK;
+    if (nrows < 0 || ncols < 0 || !counts) return fail(IGMK_EINVAL, "igmk_contact_counts_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)nrows * ncols * sizeof(uint32_t);
+    int rc = ensure(&c->d_stage, &c->stage_bytes, bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = igmk_contact_counts_device(c, row0, nrows, col0, ncols, contact_range, strict,
+                                    (uint32_t*)c->d_stage, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(counts, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
+    return IGMK_OK;
+}
+
+extern "C" int igmk_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return fail(IGMK_EINVAL, "igmk_host_alloc: bad argument");
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+    return IGMK_OK;
+}
+
+extern "C" int igmk_host_free(void* ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return IGMK_OK;
+}

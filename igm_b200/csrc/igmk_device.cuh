@@ -1,0 +1,257 @@
+// igmk_device.cuh - device-side building blocks shared by the A-step kernels.
+//
+// Arithmetic contract (pinned by tests against the reference's
+// own get_actdist):
+//   d2 = fl32(fl32(fl32(dx*dx) + fl32(dy*dy)) + fl32(dz*dz)), dx = fl32(xi - xj)
+//   strictly sequential, no FMA  (np.sum(np.square(x - y), axis=1),
+//   igm/steps/ActivationDistanceStep.py:418,435)
+//   p / o arithmetic in float64 exactly as CPython evaluates :445-470.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/igmk.h"
+
+namespace igmk {
+
+// One haploid bin: bead ids of its (<= 2) copies, chromosome, radius of copy 0.
+struct __align__(16) HapEntry {
+    int   b0;
+    int   b1;      // -1 when the bin has a single copy (male X / Y)
+    int   chrom;
+    float radius;  // radii[ii[0]]  (ActivationDistanceStep.py:393)
+};
+
+struct ActdistParams {
+    const float*    coords;   // [nbead][3][npad] float32
+    const HapEntry* hap;      // [n_hap]
+    const int32_t*  pi;
+    const int32_t*  pj;
+    const double*   pwish;
+    const double*   plast;
+    igmk_pair_result* out;
+    long long n_pairs;
+    int   nstruct;
+    int   npad;               // row stride in floats, multiple of 32
+    int   nchunks;            // ceil(nstruct / 4)
+    int   n_hap;
+    float contact_range;      // already float32 (NEP-50: python float * f32 -> f32)
+    int   it_corr;
+    int   mode;
+};
+
+// Combination shapes of one pair (which of the four copy combinations
+// d0=(a0,b0) d1=(a0,b1) d2=(a1,b0) d3=(a1,b1) exist, in reference order).
+enum : int { CM_D0 = 1, CM_D1 = 2, CM_D2 = 4, CM_D3 = 8 };
+
+struct PairDesc {
+    int   a0, a1, b0, b1;   // bead ids (-1: absent)
+    int   cmask;            // combinations that are computed
+    int   keep;             // n_possible_contacts: values kept per structure
+    int   nrec;             // records the pair expands to when p > 0
+    int   valid;            // 0: i == j / out of range -> empty result
+    float rcutsq;
+};
+
+__device__ __forceinline__ float d2_nofma(float xi, float yi, float zi,
+                                          float xj, float yj, float zj) {
+    const float dx = __fsub_rn(xi, xj);
+    const float dy = __fsub_rn(yi, yj);
+    const float dz = __fsub_rn(zi, zj);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Pair metadata, uniform over the group (ActivationDistanceStep.py:379-424,
+// GP_activation.py:355-366).
+__device__ __forceinline__ PairDesc make_pair_desc(const ActdistParams& P, int i, int j) {
+    PairDesc d;
+    d.valid = (i != j) && i >= 0 && j >= 0 && i < P.n_hap && j < P.n_hap;
+    d.a0 = d.a1 = d.b0 = d.b1 = -1;
+    d.cmask = 0; d.keep = 0; d.nrec = 0; d.rcutsq = 0.f;
+    if (!d.valid) return d;
+    const int4 ha = __ldg(reinterpret_cast<const int4*>(P.hap + i));
+    const int4 hb = __ldg(reinterpret_cast<const int4*>(P.hap + j));
+    d.a0 = ha.x; d.a1 = ha.y; d.b0 = hb.x; d.b1 = hb.y;
+    const int na = (d.a1 >= 0) ? 2 : 1;
+    const int nb = (d.b1 >= 0) ? 2 : 1;
+    const bool intra = (ha.z == hb.z);
+    const float ri = __int_as_float(ha.w), rj = __int_as_float(hb.w);
+    const float rc = __fmul_rn(P.contact_range, __fadd_rn(ri, rj));
+    d.rcutsq = __fmul_rn(rc, rc);
+    const int all = CM_D0 | (nb == 2 ? CM_D1 : 0) | (na == 2 ? CM_D2 : 0) |
+                    ((na == 2 && nb == 2) ? CM_D3 : 0);
+    if (P.mode == IGMK_MODE_LB && intra) {
+        // zip(ii, jj): (a0,b0),(a1,b1); the reference needs len(ii) == len(jj) here
+        // (quirk q5) - the host rejects other inputs before launch.
+        d.cmask = CM_D0 | ((na == 2 && nb == 2) ? CM_D3 : 0);
+        d.keep = (na < nb) ? na : nb;
+    } else if (P.mode == IGMK_MODE_LB) {
+        d.cmask = all;
+        d.keep = na * nb;
+    } else {
+        d.cmask = all;
+        d.keep = (na < nb) ? na : nb;
+    }
+    d.nrec = intra ? ((na < nb) ? na : nb) : na * nb;
+    return d;
+}
+
+// Four copy-combination values of one structure -> the `keep` kept values in
+// slots s[0..3]; unused slots are NaN (never counted, never selected).
+__device__ __forceinline__ void pack_slots(const PairDesc& d, int mode, float d0, float d1,
+                                           float d2, float d3, float (&s)[4]) {
+    const float qnan = __int_as_float(0x7fffffff);
+    if (mode == IGMK_MODE_GP) {
+        // keep the `keep` smallest of the existing combinations (d_sq.sort(axis=0)
+        // then rows 0:npc, GP_activation.py:389-395).  fminf/fmaxf ignore NaN.
+        if (d.keep == 2) {
+            const float lo1 = fminf(d0, d1), hi1 = fmaxf(d0, d1);
+            const float lo2 = fminf(d2, d3), hi2 = fmaxf(d2, d3);
+            s[0] = fminf(lo1, lo2);
+            s[1] = fminf(fmaxf(lo1, lo2), fminf(hi1, hi2));
+        } else {
+            s[0] = fminf(fminf(d0, d1), fminf(d2, d3));
+            s[1] = qnan;
+        }
+        s[2] = qnan; s[3] = qnan;
+    } else {
+        // LB: every computed combination is kept, in enumeration order.
+        const int cm = d.cmask;
+        s[0] = d0;
+        s[1] = (cm == (CM_D0 | CM_D3)) ? d3 : ((cm == (CM_D0 | CM_D2)) ? d2 : d1);
+        s[2] = (cm == 15) ? d2 : qnan;
+        s[3] = (cm == 15) ? d3 : qnan;
+    }
+}
+
+// All kept values of structure `st` from scalar loads (slow path: candidate
+// re-materialisation, simple kernel).
+__device__ __forceinline__ void struct_slots(const ActdistParams& P, const PairDesc& d, int st,
+                                             float (&s)[4]) {
+    const float qnan = __int_as_float(0x7fffffff);
+    const size_t row = (size_t)3 * P.npad;
+    float ax[2] = {0, 0}, ay[2] = {0, 0}, az[2] = {0, 0};
+    float bx[2] = {0, 0}, by[2] = {0, 0}, bz[2] = {0, 0};
+    const float* pa0 = P.coords + (size_t)d.a0 * row + st;
+    ax[0] = __ldg(pa0); ay[0] = __ldg(pa0 + P.npad); az[0] = __ldg(pa0 + 2 * P.npad);
+    const float* pb0 = P.coords + (size_t)d.b0 * row + st;
+    bx[0] = __ldg(pb0); by[0] = __ldg(pb0 + P.npad); bz[0] = __ldg(pb0 + 2 * P.npad);
+    if (d.a1 >= 0) {
+        const float* pa1 = P.coords + (size_t)d.a1 * row + st;
+        ax[1] = __ldg(pa1); ay[1] = __ldg(pa1 + P.npad); az[1] = __ldg(pa1 + 2 * P.npad);
+    }
+    if (d.b1 >= 0) {
+        const float* pb1 = P.coords + (size_t)d.b1 * row + st;
+        bx[1] = __ldg(pb1); by[1] = __ldg(pb1 + P.npad); bz[1] = __ldg(pb1 + 2 * P.npad);
+    }
+    const float d0 = d2_nofma(ax[0], ay[0], az[0], bx[0], by[0], bz[0]);
+    const float d1 = (d.cmask & CM_D1) ? d2_nofma(ax[0], ay[0], az[0], bx[1], by[1], bz[1]) : qnan;
+    const float d2 = (d.cmask & CM_D2) ? d2_nofma(ax[1], ay[1], az[1], bx[0], by[0], bz[0]) : qnan;
+    const float d3 = (d.cmask & CM_D3) ? d2_nofma(ax[1], ay[1], az[1], bx[1], by[1], bz[1]) : qnan;
+    pack_slots(d, P.mode, d0, d1, d2, d3, s);
+}
+
+// cleanProbability, igm/steps/ActivationDistanceStep.py:314-332 (float64).
+__device__ __forceinline__ double clean_probability(double pij, double pexist) {
+    double pclean = pij;
+    if (pexist < 1.0) pclean = __ddiv_rn(__dsub_rn(pij, pexist), __dsub_rn(1.0, pexist));
+    return (pclean > 0.0) ? pclean : 0.0;      // python max(0, x): NaN and -0.0 -> 0
+}
+
+// p and the order-statistic index o, :445-470.  o = -1 when p <= 0.
+__device__ __forceinline__ void compute_p_o(int contact_count, int npc, int nstruct,
+                                            double pwish, double plast, int it_corr,
+                                            double& p, int& o) {
+    const int total = npc * nstruct;
+    if (it_corr == 1) {
+        const double pnow = __ddiv_rn((double)contact_count, (double)total);
+        const double t = clean_probability(pnow, plast);
+        p = clean_probability(pwish, t);
+    } else {
+        p = pwish;
+    }
+    o = -1;
+    if (p > 0.0) {
+        // int(round(npc * p * N)): left to right, round-half-even (np.float64.__round__)
+        const double x = __dmul_rn(__dmul_rn((double)npc, p), (double)nstruct);
+        const double r = rint(x);
+        o = (r >= (double)(total - 1)) ? (total - 1) : (int)r;
+        if (o < 0) o = 0;
+    } else {
+        p = 0.0;
+    }
+}
+
+// float32(float("%.4f" % x)) for x >= 0: the text round trip of task()/reduce()
+// (:38, :230, :249).  Exact: x * 1e4 is split into hi + lo with an FMA, so the
+// decimal rounding (half-even on exact ties, as CPython's dtoa does) is decided
+// on the true product.
+__device__ __forceinline__ float round4_to_f32(double x) {
+    const double hi = __dmul_rn(x, 1e4);
+    if (!(hi < 4.0e15)) return __double2float_rn(x);   // already integral at 1e-4
+    const double lo = __fma_rn(x, 1e4, -hi);
+    double r = rint(hi);
+    const double e = __dsub_rn(hi, r);                 // exact, |e| <= 0.5
+    if (e == 0.5 && lo > 0.0) r += 1.0;
+    else if (e == -0.5 && lo < 0.0) r -= 1.0;
+    return __double2float_rn(__ddiv_rn(r, 1e4));
+}
+
+__device__ __forceinline__ void write_result(igmk_pair_result* out, const PairDesc& d,
+                                             uint32_t d2_bits, int count, int o, double p) {
+    const int nrec = (o >= 0) ? d.nrec : 0;
+    const float dist = (o >= 0) ? round4_to_f32(sqrt((double)__uint_as_float(d2_bits))) : 0.f;
+    const float prob = (o >= 0) ? round4_to_f32(p) : 0.f;
+    const long long pb = __double_as_longlong(p);
+    // two 16-byte stores (layout of igmk_pair_result)
+    uint4* dst = reinterpret_cast<uint4*>(out);
+    dst[0] = make_uint4(d2_bits, (uint32_t)count, (uint32_t)o, (uint32_t)nrec);
+    dst[1] = make_uint4((uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32),
+                        __float_as_uint(dist), __float_as_uint(prob));
+}
+
+__device__ __forceinline__ void write_empty(igmk_pair_result* out) {
+    uint4 z = make_uint4(0, 0, 0xffffffffu, 0);   // o = -1
+    uint4* dst = reinterpret_cast<uint4*>(out);
+    dst[0] = z;
+    dst[1] = make_uint4(0, 0, 0, 0);
+}
+
+// ---- packed bf16x2 primitives (sm_90+ PTX; keys are the high 16 bits of the
+// non-negative float32 d2, so bf16 order == unsigned order == float order) ----
+__device__ __forceinline__ uint32_t bf2_le(uint32_t a, uint32_t b) {   // 1.0 / 0.0 per half
+    uint32_t r;
+    asm("set.le.bf16x2.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_le_mask(uint32_t a, uint32_t b) {  // 0xffff / 0 per half
+    uint32_t r;
+    asm("set.le.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_ge_mask(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_min(uint32_t a, uint32_t b) {  // NaN operand ignored
+    uint32_t r;
+    asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// small non-negative integer counts held as bf16 (exact up to 256) -> int
+__device__ __forceinline__ int bf2_count_sum(uint32_t acc) {
+    return (int)(__uint_as_float(acc << 16) + __uint_as_float(acc & 0xffff0000u));
+}
+
+}  // namespace igmk

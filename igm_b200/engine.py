@@ -1,0 +1,171 @@
+"""Host-side driver of the CUDA library for one population on one GPU.
+
+``ActdistEngine`` is what the Step drop-in (igm_b200/steps) and bench.py call;
+it owns one ``igmk_ctx`` (coordinates resident in HBM, bead-major,
+structure-contiguous) and exposes the hot path of the reference's
+``ActivationDistanceStep.task`` loop (igm/steps/ActivationDistanceStep.py:
+215-222) plus the contact-frequency tiles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (ALGO_FAST, ALGO_SIMPLE, MODE_GP, MODE_LB, PAIR_RESULT_DTYPE, IgmkError,
+                   check, ptr)
+from .population import Population
+
+_MODES = {"LB": MODE_LB, "GP": MODE_GP, MODE_LB: MODE_LB, MODE_GP: MODE_GP, "lb": MODE_LB, "gp": MODE_GP}
+
+
+class ActdistEngine:
+    def __init__(self, pop: Optional[Population] = None, device: int = 0, *,
+                 nbead: Optional[int] = None, nstruct: Optional[int] = None):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        if pop is not None:
+            nbead, nstruct = pop.nbead, pop.nstruct
+        check(self._lib.igmk_create(int(device), int(nbead), int(nstruct), C.byref(self._ctx)))
+        self.device = int(device)
+        self.nbead, self.nstruct = int(nbead), int(nstruct)
+        self.n_hap = 0
+        self._ncopies = None
+        self._chrom_hap = None
+        if pop is not None:
+            self.upload_coordinates(pop.coordinates)
+            self.set_index(pop.copy_index.ptr, pop.copy_index.beads, pop.chrom_hap(), pop.radii)
+
+    # -- lifetime --------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.igmk_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- staging ---------------------------------------------------------
+    def upload_coordinates(self, xyz, bead0: int = 0) -> None:
+        """xyz: (nb, nstruct, 3) float32, bead-major - NumPy array (host) or a
+        CUDA torch tensor on this engine's device."""
+        on_device = 0
+        if isinstance(xyz, np.ndarray):
+            xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+            shape = xyz.shape
+        else:
+            if not xyz.is_cuda:
+                xyz = xyz.contiguous().numpy()
+                return self.upload_coordinates(xyz, bead0)
+            if str(xyz.dtype) != "torch.float32":
+                raise TypeError("coordinates must be float32")
+            xyz = xyz.contiguous()
+            shape = tuple(xyz.shape)
+            on_device = 1
+        if len(shape) != 3 or shape[1] != self.nstruct or shape[2] != 3:
+            raise ValueError("coordinates must be (nbead, %d, 3), got %r" % (self.nstruct, shape))
+        check(self._lib.igmk_upload_coords_range(self._ctx, ptr(xyz), int(bead0), int(shape[0]), on_device))
+
+    def set_index(self, copy_ptr, copy_beads, chrom_hap, radii) -> None:
+        copy_ptr = np.ascontiguousarray(copy_ptr, dtype=np.int32)
+        copy_beads = np.ascontiguousarray(copy_beads, dtype=np.int32)
+        chrom_hap = np.ascontiguousarray(chrom_hap, dtype=np.int32)
+        radii = np.ascontiguousarray(radii, dtype=np.float32)
+        n_hap = len(copy_ptr) - 1
+        if len(chrom_hap) != n_hap or len(radii) != self.nbead:
+            raise ValueError("index arrays have inconsistent lengths")
+        check(self._lib.igmk_set_index(self._ctx, n_hap, ptr(copy_ptr), ptr(copy_beads),
+                                       ptr(chrom_hap), ptr(radii)))
+        self.n_hap = n_hap
+        self._ncopies = np.diff(copy_ptr)
+        self._chrom_hap = chrom_hap
+
+    # -- A-step ----------------------------------------------------------
+    def _validate_pairs(self, i, j, mode):
+        if len(i) == 0:
+            return
+        if i.min() < 0 or j.min() < 0 or i.max() >= self.n_hap or j.max() >= self.n_hap:
+            raise ValueError("pair index out of range [0, %d)" % self.n_hap)
+        if mode == MODE_LB:
+            # quirk q5: the reference's intra branch reads uninitialised
+            # memory when the two loci have different copy counts - refuse instead.
+            bad = (self._chrom_hap[i] == self._chrom_hap[j]) & (self._ncopies[i] != self._ncopies[j]) & (i != j)
+            if bad.any():
+                k = int(np.nonzero(bad)[0][0])
+                raise ValueError("intra-chromosomal pair (%d, %d) has unequal copy counts" % (i[k], j[k]))
+
+    def actdist(self, i, j, pwish, plast=None, contact_range: float = 2.0, it_corr: int = 0,
+                mode="LB", algo: int = ALGO_FAST) -> np.ndarray:
+        """Host arrays in, structured result array (PAIR_RESULT_DTYPE) out.
+        One entry per pair, input order.  Copies are inside the call."""
+        mode = _MODES[mode]
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        pwish = np.ascontiguousarray(pwish, dtype=np.float64)
+        plast = np.zeros(len(i), np.float64) if plast is None else np.ascontiguousarray(plast, dtype=np.float64)
+        if not (len(i) == len(j) == len(pwish) == len(plast)):
+            raise ValueError("pair arrays must have equal length")
+        self._validate_pairs(i, j, mode)
+        out = np.zeros(len(i), dtype=PAIR_RESULT_DTYPE)
+        check(self._lib.igmk_actdist_host(self._ctx, len(i), ptr(i), ptr(j), ptr(pwish), ptr(plast),
+                                          float(np.float32(contact_range)), int(it_corr), mode, int(algo),
+                                          ptr(out)))
+        return out
+
+    def actdist_device(self, d_i, d_j, d_pwish, d_plast, d_out, n_pairs: Optional[int] = None,
+                       contact_range: float = 2.0, it_corr: int = 0, mode="LB",
+                       algo: int = ALGO_FAST, stream: int = 0) -> None:
+        """Device buffers (torch CUDA tensors or raw addresses); asynchronous."""
+        n = int(n_pairs if n_pairs is not None else d_i.numel())
+        check(self._lib.igmk_actdist_device(self._ctx, n, ptr(d_i), ptr(d_j), ptr(d_pwish),
+                                            ptr(d_plast), float(np.float32(contact_range)), int(it_corr),
+                                            _MODES[mode], int(algo), ptr(d_out), stream or None))
+
+    def expand_records(self, i, j, res) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Pair results -> (row, col, dist, prob), the four actdist.hdf5 columns."""
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        res = np.ascontiguousarray(res, dtype=PAIR_RESULT_DTYPE)
+        cap = int(res["nrec"].sum())
+        row = np.empty(cap, np.int32)
+        col = np.empty(cap, np.int32)
+        dist = np.empty(cap, np.float32)
+        prob = np.empty(cap, np.float32)
+        n = C.c_int64(0)
+        check(self._lib.igmk_expand_records(self._ctx, len(i), ptr(i), ptr(j), ptr(res), ptr(row),
+                                            ptr(col), ptr(dist), ptr(prob), cap, C.byref(n)))
+        assert n.value == cap
+        return row, col, dist, prob
+
+    # -- contact frequency -------------------------------------------------
+    def contact_counts(self, row0: int, nrows: int, col0: int, ncols: int,
+                       contact_range: float = 2.0, strict: bool = False) -> np.ndarray:
+        out = np.zeros((nrows, ncols), dtype=np.uint32)
+        check(self._lib.igmk_contact_counts_host(self._ctx, int(row0), int(nrows), int(col0),
+                                                 int(ncols), float(np.float32(contact_range)),
+                                                 1 if strict else 0, ptr(out)))
+        return out
+
+    def contact_counts_device(self, row0, nrows, col0, ncols, d_counts, contact_range=2.0,
+                              strict=False, stream: int = 0) -> None:
+        check(self._lib.igmk_contact_counts_device(self._ctx, int(row0), int(nrows), int(col0),
+                                                   int(ncols), float(np.float32(contact_range)),
+                                                   1 if strict else 0, ptr(d_counts), stream or None))
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.igmk_last_kernel_ms(self._ctx))
+
+
+def launch_count() -> int:
+    return int(_lib.load().igmk_launch_count())

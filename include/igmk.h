@@ -1,0 +1,139 @@
+/*
+ * igmk.h - C ABI of libigmk.so: the B200 (sm_100a) kernels behind IGM's Hi-C
+ * A-step and population contact-frequency map.
+ *
+ * The reference (bonimba87/igm) is pure Python on this path and has no FFI of
+ * its own (its only native code is the SPRITE helper,
+ * igm/cython_compiled/sprite.pyx:21-31).  The entry points below are what a
+ * ctypes binding inside the reference's Step would call instead of the NumPy
+ * loops they replace; each one cites the reference lines it stands in for
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * stub.
+ *
+ * Conventions: plain pointers and sizes only; the caller allocates every
+ * buffer; every function returns 0 on success and a negative IGMK_E* code on
+ * failure (igmk_last_error() gives the message); no exception crosses the
+ * ABI; one context per GPU; a context is not thread-safe, distinct contexts
+ * are independent.  There is no CPU fallback: without a CUDA device every
+ * call fails with IGMK_ECUDA.
+ */
+#ifndef IGMK_H_
+#define IGMK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGMK_VERSION 100
+
+#define IGMK_OK        0
+#define IGMK_EINVAL   -1   /* bad argument */
+#define IGMK_ECUDA    -2   /* CUDA runtime error (no device, launch failure, OOM) */
+#define IGMK_ESTATE   -3   /* call order: coordinates / index not set */
+#define IGMK_ELIMIT   -4   /* outside supported range (ploidy > 2, nstruct > 32768) */
+
+/* A-step flavours.  LB = igm/steps/ActivationDistanceStep.py:336-485 (what
+ * igm-run executes); GP = igm/steps/GP_activation.py:317-445 and
+ * igm/utils/actdist.py:15-96 (keep the min(len(ii),len(jj)) smallest copy
+ * combinations per structure). */
+#define IGMK_MODE_LB 0
+#define IGMK_MODE_GP 1
+
+/* Kernel selection for igmk_actdist_*: 0 = production kernel (register-resident
+ * packed-key select), 1 = straightforward shared-memory bitwise select kept as
+ * an on-device cross-check. */
+#define IGMK_ALGO_FAST   0
+#define IGMK_ALGO_SIMPLE 1
+
+/* Per-pair result, 32 bytes.  One per candidate pair, in input order. */
+typedef struct igmk_pair_result {
+    uint32_t d2_sel_bits;   /* float32 bit pattern of sortdist_sq[o]           (:448,:473) */
+    int32_t  contact_count; /* #{d_sq[0:npc] <= rcutsq}                         (:442)     */
+    int32_t  o;             /* order-statistic index, -1 when p <= 0 or i == j  (:469-470) */
+    int32_t  nrec;          /* records this pair expands to: 0,1,2 or 4         (:476-483) */
+    double   p;             /* corrected probability (float64)                  (:452-462) */
+    float    dist;          /* float32("%10.4f" % sqrt_f64(d2_sel))             (:38,:230,:249) */
+    float    prob;          /* float32("%.4f" % p)                              (:38,:230,:249) */
+} igmk_pair_result;
+
+typedef struct igmk_ctx igmk_ctx;
+
+int         igmk_version(void);
+const char* igmk_last_error(void);
+/* Number of kernel launches issued by this library in the calling process
+ * (bench.py's gpu_launches claim). */
+int64_t     igmk_launch_count(void);
+
+/* Context for a population of nbead beads x nstruct structures on `device`. */
+int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out);
+int igmk_destroy(igmk_ctx* ctx);
+
+/* Stage coordinates once per A-step.  `xyz` is the .hss layout
+ * (nbead, nstruct, 3) float32, bead-major (igm/core/step.py:373,
+ * igm/_preprocess.py:102-105); replaces the per-pair hss.get_bead_crd(k) reads
+ * (ActivationDistanceStep.py:415-416,431-432).  Stored in HBM as
+ * [bead][xyz][nstruct padded to 32] so one bead's row over all structures is
+ * contiguous.  `on_device` != 0: xyz is a device pointer. */
+int igmk_upload_coords(igmk_ctx* ctx, const float* xyz, int on_device);
+/* Partial upload of beads [bead0, bead0 + nb): lets a loader stream HDF5
+ * chunks (pack_beads x nstruct x 3, igm/steps/ModelingStep.py:753-760). */
+int igmk_upload_coords_range(igmk_ctx* ctx, const float* xyz, int bead0, int nb, int on_device);
+
+/* Index tables (host pointers): copy_ptr[n_hap+1] / copy_beads = CSR of
+ * hss.index.copy_index; chrom_hap[n_hap] = hss.index.chrom indexed by haploid
+ * bin; radii[nbead]  (ActivationDistanceStep.py:383-393). */
+int igmk_set_index(igmk_ctx* ctx, int n_hap, const int32_t* copy_ptr,
+                   const int32_t* copy_beads, const int32_t* chrom_hap,
+                   const float* radii);
+
+/* get_actdist for n_pairs candidate pairs (ActivationDistanceStep.py:336-485;
+ * loop at :215-219).  *_device: every pointer is device memory, asynchronous
+ * on `stream` (a cudaStream_t, NULL = default stream).  *_host: host pointers;
+ * copies in, runs, copies out and synchronises before returning. */
+int igmk_actdist_device(igmk_ctx* ctx, int64_t n_pairs,
+                        const int32_t* d_i, const int32_t* d_j,
+                        const double* d_pwish, const double* d_plast,
+                        float contact_range, int it_corr, int mode, int algo,
+                        igmk_pair_result* d_out, void* stream);
+int igmk_actdist_host(igmk_ctx* ctx, int64_t n_pairs,
+                      const int32_t* i, const int32_t* j,
+                      const double* pwish, const double* plast,
+                      float contact_range, int it_corr, int mode, int algo,
+                      igmk_pair_result* out);
+
+/* Record expansion of task()/reduce() (ActivationDistanceStep.py:221-222,
+ * 476-483, 249-257): pair results -> the four actdist.hdf5 columns, reference
+ * order.  Host pointers; row/col/dist/prob must hold sum(nrec) entries;
+ * *n_records receives that sum. */
+int igmk_expand_records(igmk_ctx* ctx, int64_t n_pairs,
+                        const int32_t* i, const int32_t* j,
+                        const igmk_pair_result* res,
+                        int32_t* row, int32_t* col, float* dist, float* prob,
+                        int64_t capacity, int64_t* n_records);
+
+/* Population contact-frequency counts for a tile of bead pairs
+ * (HssFile.buildContactMap as used by igm/steps/HicEvaluationStep.py:107-112
+ * and igm/report/hic.py:51; in-tree statement of the formula:
+ * HicEvaluationStep.py:73-93).  counts[(a - row0) * ncols + (b - col0)] =
+ * #{s : d2_s(a,b) <= (cr*(r_a+r_b))^2}  (strict '<' when strict != 0) for
+ * a in [row0,row0+nrows), b in [col0,col0+ncols).  d_counts is device memory. */
+int igmk_contact_counts_device(igmk_ctx* ctx, int row0, int nrows, int col0, int ncols,
+                               float contact_range, int strict,
+                               uint32_t* d_counts, void* stream);
+int igmk_contact_counts_host(igmk_ctx* ctx, int row0, int nrows, int col0, int ncols,
+                             float contact_range, int strict, uint32_t* counts);
+
+/* Pinned host memory for zero-staging transfers (optional). */
+int igmk_host_alloc(void** ptr, int64_t bytes);
+int igmk_host_free(void* ptr);
+
+/* Device-time of the last igmk_actdist_host / igmk_contact_counts_host call:
+ * kernel only, in milliseconds (CUDA events on the library's stream). */
+float igmk_last_kernel_ms(igmk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGMK_H_ */

@@ -1,0 +1,250 @@
+"""GPU parity tests of K1 (activation distance) through the C ABI.
+
+The CUDA path is compared with (a) the committed golden vectors produced by
+the reference's own get_actdist and (b) the NumPy oracle on seeded inputs.
+Bar: bit-exact d2 / count / o / p, identical record text (sha256).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import actdist_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"lb": orc.MODE_LB, "gp": orc.MODE_GP}
+
+
+def _engine(pop):
+    from igm_b200.engine import ActdistEngine
+    return ActdistEngine(pop, device=0)
+
+
+def _records_text(eng, ii, jj, res):
+    row, col, dist, prob = eng.expand_records(ii, jj, res)
+    return row, col, dist, prob
+
+
+def _check_against_details(res, dets):
+    exp = orc.details_to_arrays(dets)
+    assert np.array_equal(res["contact_count"], exp["contact_count"])
+    assert np.array_equal(res["o"], exp["o"])
+    assert np.array_equal(res["p"].view(np.uint64), exp["p"].view(np.uint64))
+    sel = exp["o"] >= 0
+    assert np.array_equal(res["d2_sel_bits"][sel], exp["d2_sel_bits"][sel])
+    assert np.array_equal(res["nrec"], exp["nrec"])
+
+
+@pytest.mark.parametrize("case", [c[0] for c in H.all_small_cases()])
+@pytest.mark.parametrize("algo", [0, 1])
+def test_golden_small(case, algo):
+    name, npz, prefix = [c for c in H.all_small_cases() if c[0] == case][0]
+    pop, ii, jj, pw, pl = H.load_case(npz, prefix)
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            for it_corr in (0, 1):
+                g = H.golden_out(npz, prefix, mode, it_corr)
+                res = eng.actdist(ii, jj, pw, pl, 2.0, it_corr, mode, algo)
+                assert np.array_equal(res["nrec"], g["nrec"]), (mode, it_corr)
+                row, col, dist, prob = eng.expand_records(ii, jj, res)
+                assert np.array_equal(row, g["row"]) and np.array_equal(col, g["col"])
+                # activation distance: float64 sqrt of the selected float32 d2 (bit-exact)
+                first = np.concatenate([[0], np.cumsum(g["nrec"])[:-1]])[g["nrec"] > 0]
+                ad = np.sqrt(res["d2_sel_bits"][g["nrec"] > 0].view(np.float32).astype(np.float64))
+                assert np.array_equal(ad.view(np.uint64), g["ad"][first].view(np.uint64))
+                assert np.array_equal(res["p"][g["nrec"] > 0].view(np.uint64), g["p"][first].view(np.uint64))
+                # stored columns = 4-decimal text round trip of the reference output
+                assert np.array_equal(dist.view(np.uint32), orc.text_roundtrip(g["ad"]).view(np.uint32))
+                assert np.array_equal(prob.view(np.uint32), orc.text_roundtrip(g["p"]).view(np.uint32))
+                # and the '%d.out.tmp' text itself
+                recs = list(zip(row.tolist(), col.tolist(), np.repeat(ad, g["nrec"][g["nrec"] > 0]).tolist(),
+                                np.repeat(res["p"][g["nrec"] > 0], g["nrec"][g["nrec"] > 0]).tolist()))
+                assert hashlib.sha256(orc.task_text(recs).encode()).hexdigest() == g["sha"]
+
+
+def test_contact_range_variant():
+    s = np.load(os.path.join(H.GOLDEN, "synth_small.npz"))
+    pop, ii, jj, pw, pl = H.load_case(s, "n100")
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            g = H.golden_out(s, "n100cr35", mode, 1)
+            res = eng.actdist(ii, jj, pw, pl, 3.5, 1, mode)
+            row, col, dist, prob = eng.expand_records(ii, jj, res)
+            assert np.array_equal(dist.view(np.uint32), orc.text_roundtrip(g["ad"]).view(np.uint32))
+            assert np.array_equal(prob.view(np.uint32), orc.text_roundtrip(g["p"]).view(np.uint32))
+
+
+@pytest.mark.parametrize("nstruct", [5, 64, 129, 500, 1000, 1024])
+@pytest.mark.parametrize("mode", ["lb", "gp"])
+def test_oracle_synthetic_warp_mode(nstruct, mode):
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, nstruct, seed=100 + nstruct, genome_scale=0.02)
+    rng = np.random.default_rng(nstruct)
+    nh = pop.n_hap
+    ii = rng.integers(0, nh, 300)
+    jj = rng.integers(0, nh, 300)
+    k = ii < jj
+    ii, jj = ii[k].astype(np.int32), jj[k].astype(np.int32)
+    pw = rng.uniform(0.001, 1.0, len(ii)).astype(np.float32).astype(np.float64)
+    pw[::9] = 1.0
+    pl = np.where(rng.random(len(ii)) < 0.5, 0.0, orc.text_roundtrip(rng.uniform(0, 0.8, len(ii))).astype(np.float64))
+    with _engine(pop) as eng:
+        for it_corr in (0, 1):
+            _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, it_corr, 2.0, MODES[mode])
+            for algo in (0, 1):
+                res = eng.actdist(ii, jj, pw, pl, 2.0, it_corr, mode, algo)
+                _check_against_details(res, dets)
+
+
+@pytest.mark.parametrize("nstruct,block_v", [(1500, 0), (2600, 0), (4100, 3), (4100, 4), (4100, 6), (4100, 8), (10000, 0)])
+def test_oracle_synthetic_block_mode(nstruct, block_v, monkeypatch):
+    from igm_b200 import synthetic
+    if block_v:
+        monkeypatch.setenv("IGMK_BLOCK_V", str(block_v))
+    pop = synthetic.make_population(2_000_000, nstruct, seed=7 + nstruct, genome_scale=0.004)
+    rng = np.random.default_rng(nstruct)
+    nh = pop.n_hap
+    ii = rng.integers(0, nh, 120)
+    jj = rng.integers(0, nh, 120)
+    k = ii < jj
+    ii, jj = ii[k].astype(np.int32), jj[k].astype(np.int32)
+    pw = rng.uniform(0.001, 1.0, len(ii)).astype(np.float32).astype(np.float64)
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, 1, 2.0, MODES[mode])
+            res = eng.actdist(ii, jj, pw, pl, 2.0, 1, mode, 0)
+            _check_against_details(res, dets)
+
+
+def test_degenerate_inputs():
+    """Identical coordinates (all distances equal), empty and i == j inputs."""
+    from igm_b200.population import CopyIndex, Population
+    from igm_b200 import synthetic
+    nstruct = 300
+    bins = np.array([6, 5, 3])
+    chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins, n_diploid_chroms=2)
+    nbead = len(chrom_bead)
+    crd = np.zeros((nbead, nstruct, 3), np.float32)
+    crd[:, :, 0] = np.arange(nbead, dtype=np.float32)[:, None] * 100.0   # same in every structure
+    pop = Population(crd, np.full(nbead, 50.0, np.float32), chrom_bead, ci, copy_bead)
+    ii = np.array([0, 0, 1, 2, 7, 3, 3], np.int32)
+    jj = np.array([1, 7, 12, 13, 12, 3, 9], np.int32)    # (3,3): i == j
+    pw = np.array([1.0, 0.3, 0.2, 0.01, 0.5, 0.5, 0.999], np.float64)
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, 0, 2.0, MODES[mode])
+            for algo in (0, 1):
+                res = eng.actdist(ii, jj, pw, pl, 2.0, 0, mode, algo)
+                _check_against_details(res, dets)
+        # empty input
+        res = eng.actdist(np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0), np.zeros(0))
+        assert len(res) == 0
+        row, col, dist, prob = eng.expand_records(np.zeros(0, np.int32), np.zeros(0, np.int32), res)
+        assert len(row) == 0
+
+
+def test_tiny_and_denormal_distances():
+    """Keys in the bf16-denormal range and exact zeros."""
+    from igm_b200.population import CopyIndex, Population
+    from igm_b200 import synthetic
+    nstruct = 200
+    bins = np.array([4, 4])
+    chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins, n_diploid_chroms=2)
+    nbead = len(chrom_bead)
+    rng = np.random.default_rng(5)
+    crd = (rng.standard_normal((nbead, nstruct, 3)) * 1e-20).astype(np.float32)
+    crd[:, ::7, :] = 0.0
+    pop = Population(crd, np.full(nbead, 1e-21, np.float32), chrom_bead, ci, copy_bead)
+    ii, jj = np.triu_indices(8, 1)
+    ii, jj = ii.astype(np.int32), jj.astype(np.int32)
+    pw = rng.uniform(0.01, 1.0, len(ii))
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                pop.copy_index, 1, 2.0, orc.MODE_LB)
+        res = eng.actdist(ii, jj, pw, pl, 2.0, 1, "lb", 0)
+        _check_against_details(res, dets)
+
+
+@pytest.mark.skipif(not H.have_demo(), reason="oracle/_ref/demo not present")
+@pytest.mark.parametrize("sigma", ["1", "0.2", "0.1", "0.05", "0.02", "0.01"])
+def test_full_demo_sha(sigma):
+    """Config 1: the shipped demo population, every sigma of the demo config;
+    the '%d.out.tmp' text must hash to what the reference's get_actdist gave."""
+    from igm_b200.population import Population, ProbMatrix
+    pop = Population.from_hss(H.DEMO_HSS)
+    pm = ProbMatrix.from_hcs(H.DEMO_HCS)
+    s = H.demo_full_summary()["sigmas"][sigma]
+    ci, cj, cp = orc.select_candidates(pm.indptr, pm.indices, pm.data, pm.chrom,
+                                       float(sigma), float(sigma), "float64")
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            if mode not in s:
+                continue
+            res = eng.actdist(ci, cj, cp, None, 2.0, 0, mode)
+            row, col, dist, prob = eng.expand_records(ci, cj, res)
+            assert len(row) == s[mode]["records"]
+            ad = np.sqrt(res["d2_sel_bits"].view(np.float32).astype(np.float64))
+            ad_r = np.repeat(ad, res["nrec"])
+            p_r = np.repeat(res["p"], res["nrec"])
+            text = "\n".join(["%6d %6d %10.4f %.4f" % x for x in zip(row.tolist(), col.tolist(), ad_r.tolist(), p_r.tolist())])
+            assert hashlib.sha256(text.encode()).hexdigest() == s[mode]["sha256"]
+            # the device-side 4-decimal rounding equals the text round trip
+            if sigma != "0.01":
+                assert np.array_equal(dist.view(np.uint32), orc.text_roundtrip(ad_r).view(np.uint32))
+                assert np.array_equal(prob.view(np.uint32), orc.text_roundtrip(p_r).view(np.uint32))
+
+
+def test_round4_random():
+    """round4_to_f32 on device == float32(float('%.4f' % x)) incl. exact ties."""
+    from igm_b200.population import Population
+    from igm_b200 import synthetic
+    # drive it through prob: p = pwish (it_corr = 0), any positive float64
+    pop = synthetic.make_population(2_000_000, 16, seed=3, genome_scale=0.004)
+    rng = np.random.default_rng(11)
+    n = 4000
+    pw = np.concatenate([rng.uniform(0, 1, n), np.arange(1, 400, 2) / 32.0 / 16.0,
+                         np.array([0.00005, 0.00015, 0.03125, 0.5 + 1 / 32.0, 1e-9, 0.99995, 1.0])])
+    ii = np.zeros(len(pw), np.int32)
+    jj = np.ones(len(pw), np.int32)
+    with _engine(pop) as eng:
+        res = eng.actdist(ii, jj, pw, None, 2.0, 0, "lb")
+    assert np.array_equal(res["prob"].view(np.uint32), orc.text_roundtrip(pw).view(np.uint32))
+    ad = np.sqrt(res["d2_sel_bits"].view(np.float32).astype(np.float64))
+    assert np.array_equal(res["dist"].view(np.uint32), orc.text_roundtrip(ad).view(np.uint32))
+
+
+def test_device_entry_point_and_errors():
+    import torch
+    from igm_b200 import synthetic, _lib
+    from igm_b200.engine import ActdistEngine
+    pop = synthetic.make_population(2_000_000, 100, seed=21, genome_scale=0.01)
+    rng = np.random.default_rng(2)
+    ii = rng.integers(0, pop.n_hap - 1, 500).astype(np.int32)
+    jj = (ii + 1 + rng.integers(0, 3, 500)).clip(max=pop.n_hap - 1).astype(np.int32)
+    pw = rng.uniform(0.01, 1, 500)
+    with ActdistEngine(pop, 0) as eng:
+        host = eng.actdist(ii, jj, pw)
+        dev = torch.device("cuda:0")
+        d_i, d_j = torch.from_numpy(ii).to(dev), torch.from_numpy(jj).to(dev)
+        d_pw, d_pl = torch.from_numpy(pw).to(dev), torch.zeros(500, dtype=torch.float64, device=dev)
+        d_out = torch.zeros(500 * 32, dtype=torch.uint8, device=dev)
+        eng.actdist_device(d_i, d_j, d_pw, d_pl, d_out, 500)
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(_lib.PAIR_RESULT_DTYPE)
+        assert got.tobytes() == host.tobytes()
+        # coordinates staged from a CUDA tensor give the same answer
+        eng.upload_coordinates(torch.from_numpy(pop.coordinates).to(dev))
+        assert eng.actdist(ii, jj, pw).tobytes() == host.tobytes()
+        with pytest.raises(ValueError):
+            eng.actdist(np.array([0], np.int32), np.array([pop.n_hap], np.int32), np.array([0.5]))
+    with pytest.raises(_lib.IgmkError):
+        ActdistEngine(nbead=10, nstruct=10, device=99)
