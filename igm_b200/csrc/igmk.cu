@@ -310,8 +310,9 @@ extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
     if (n_pairs < 0 || !i || !j || !pwish || !plast || !out) return fail(IGMK_EINVAL, "igmk_actdist_host: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t n = (size_t)n_pairs;
-    const size_t off_j = n * 4, off_pw = (n * 8 + 7) / 8 * 8, off_pl = off_pw + n * 8;
-    const size_t off_out = off_pl + n * 8;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t off_j = up(n * 4), off_pw = off_j + up(n * 4), off_pl = off_pw + up(n * 8);
+    const size_t off_out = off_pl + up(n * 8);
     const size_t total = off_out + n * sizeof(igmk_pair_result);
     int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
     if (rc) return rc;

@@ -128,7 +128,9 @@ def make_prob_matrix(chrom_hap: np.ndarray, seed: int = 20261018,
     rr = np.repeat(i, cnt)
     u = rng.random(cnt.sum())
     cc = np.repeat(chrom_end, cnt) + np.floor(u * np.repeat(n_after, cnt)).astype(np.int64)
-    key = np.unique(rr * n + cc)
+    key = rr * n + cc
+    key.sort()
+    key = key[np.concatenate([[True], np.diff(key) != 0])]
     rr, cc = key // n, key % n
     pv = np.exp(rng.uniform(np.log(inter_lo), np.log(inter_hi), size=len(rr)))
     rows_l.append(rr)
@@ -139,8 +141,41 @@ def make_prob_matrix(chrom_hap: np.ndarray, seed: int = 20261018,
     vals = np.concatenate(vals_l).astype(np.float32)
     order = np.lexsort((cols, rows))
     rows, cols, vals = rows[order], cols[order], vals[order]
-    indptr = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(indptr, rows + 1, 1)
-    indptr = np.cumsum(indptr)
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int64)
     return ProbMatrix(indptr, cols.astype(np.int32), vals, chrom_hap,
                       np.ones(n, dtype=np.float32))
+
+
+def random_walk_coordinates_torch(chrom_bead: np.ndarray, copy_bead: np.ndarray, nstruct: int,
+                                  radius: float, seed: int, device, chunk: int = 1024):
+    """Same construction as random_walk_coordinates, generated on the GPU with
+    torch (benchmark-sized populations: 29 838 x 10 000 x 3 floats take minutes
+    on the host).  Different random stream than the NumPy generator; parity
+    checks always compare against what is actually resident on the device."""
+    import torch
+    nbead = len(chrom_bead)
+    half = NUCLEUS_RADIUS / float(np.sqrt(3.0))
+    key = chrom_bead.astype(np.int64) * 2 + copy_bead
+    first = np.concatenate([[True], np.diff(key) != 0])
+    first_t = torch.from_numpy(first).to(device)
+    seg_id = torch.from_numpy(np.cumsum(first) - 1).to(device)
+    nseg = int(first.sum())
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    out = torch.empty((nbead, nstruct, 3), dtype=torch.float32, device=device)
+    step = 2.0 * float(radius) / float(np.sqrt(3.0))
+    period = 4.0 * half
+    for s0 in range(0, nstruct, chunk):
+        ns = min(chunk, nstruct - s0)
+        steps = torch.randn((nbead, ns, 3), generator=gen, device=device, dtype=torch.float32) * step
+        steps[first_t] = 0.0
+        walk = torch.cumsum(steps, dim=0)
+        # subtract the cumulative value at each segment start, add a random origin
+        seg_start = walk[first_t]                       # (nseg, ns, 3)
+        origin = (torch.rand((nseg, ns, 3), generator=gen, device=device) * 2.0 - 1.0) * half
+        walk = walk - seg_start[seg_id] + origin[seg_id]
+        y = torch.remainder(walk + half, period)
+        y = torch.where(y > 2.0 * half, period - y, y) - half
+        out[:, s0:s0 + ns] = y
+        del steps, walk, y
+    return out
