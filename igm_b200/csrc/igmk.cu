@@ -210,14 +210,14 @@ static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t s
     return IGMK_OK;
 }
 
-template <int V, int MAXT>
+template <int V, int MAXT, int MINB>
 static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, cudaStream_t st) {
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<V, MAXT>, threads, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<V, MAXT, MINB>, threads, 0));
     if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_block_kernel<%d> cannot run with %d threads", V, threads);
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
-    actdist_block_kernel<V, MAXT><<<grid, threads, 0, st>>>(P);
+    actdist_block_kernel<V, MAXT, MINB><<<grid, threads, 0, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return IGMK_OK;
@@ -236,11 +236,6 @@ static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return IGMK_OK;
-}
-
-// block-mode shapes: V chunks per thread, at most kBlockMaxThreads[V] threads
-static int block_max_threads(int V) {
-    switch (V) { case 3: return 1024; case 4: return 768; case 6: return 512; case 8: return 384; default: return 0; }
 }
 
 extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
@@ -265,39 +260,24 @@ extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
     if (algo == IGMK_ALGO_SIMPLE) return launch_simple(c, P, st);
     if (algo != IGMK_ALGO_FAST) return fail(IGMK_EINVAL, "igmk_actdist: bad algo %d", algo);
 
-    if (c->nchunks <= 32 * 8 && c->block_v_override == 0) {
+    // Thread-group shape: V float4 chunks (16 structures x <= 4 combinations) per thread.
+    //   nstruct <= 512: one warp per pair, V = ceil(nchunks / 32) <= 4
+    //   larger:         one CTA per pair, V = 4, T = ceil(nchunks / 4) rounded up to a warp
+    int force_block = c->block_v_override;
+    if (c->nchunks <= 32 * 4 && !force_block) {
         const int V = (c->nchunks + 31) / 32;
         switch (V) {
             case 1: return launch_warp<1>(c, P, st);
             case 2: return launch_warp<2>(c, P, st);
             case 3: return launch_warp<3>(c, P, st);
-            case 4: return launch_warp<4>(c, P, st);
-            case 5: return launch_warp<5>(c, P, st);
-            case 6: return launch_warp<6>(c, P, st);
-            case 7: return launch_warp<7>(c, P, st);
-            default: return launch_warp<8>(c, P, st);
+            default: return launch_warp<4>(c, P, st);
         }
     }
-    // larger populations: one pair per CTA
-    static const int prefer[4] = {4, 8, 3, 6};
-    int bestV = 0, bestT = 0;
-    double best_util = -1.0;
-    for (int k = 0; k < 4; ++k) {
-        const int V = prefer[k];
-        if (c->block_v_override && V != c->block_v_override) continue;
-        int T = ((c->nchunks + V - 1) / V + 31) / 32 * 32;
-        if (T < 64) T = 64;
-        if (T > block_max_threads(V)) continue;
-        const double util = (double)c->nchunks / ((double)T * V);
-        if (util > best_util + 0.02) { best_util = util; bestV = V; bestT = T; }
-    }
-    if (!bestV) return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 12288", c->nstruct);
-    switch (bestV) {
-        case 3: return launch_block<3, 1024>(c, P, bestT, st);
-        case 4: return launch_block<4, 768>(c, P, bestT, st);
-        case 6: return launch_block<6, 512>(c, P, bestT, st);
-        default: return launch_block<8, 384>(c, P, bestT, st);
-    }
+    int T = ((c->nchunks + 3) / 4 + 31) / 32 * 32;
+    if (T < 32) T = 32;
+    if (T > 768) return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 12288", c->nstruct);
+    if (T <= 128) return launch_block<4, 128, 6>(c, P, T, st);
+    return launch_block<4, 768, 1>(c, P, T, st);
 }
 
 extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,

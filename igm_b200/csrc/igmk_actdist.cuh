@@ -95,80 +95,133 @@ struct BlockGroup {
 // --------------------------------------------------------- stage 1: fill keys
 // keys[v][slot][qh]: low half = structure 4c + 2qh, high half = 4c + 2qh + 1 of
 // chunk c = tid + v * nthr; NaN pattern (0x7fff) for everything not kept.
-template <int V>
+//
+// Pair shapes (uniform over the group) get their own straight-line code:
+//   SH_FULL4   LB, both loci diploid, inter-chromosomal: 4 combinations kept
+//   SH_INTRA2  LB, both loci diploid, intra-chromosomal: (a0,b0),(a1,b1)
+//   SH_GP4     GP, both loci diploid: 2 smallest of the 4 combinations
+//   SH_GENERIC anything with a haploid locus (male X/Y): branch-free selects
+enum : int { SH_FULL4 = 0, SH_INTRA2 = 1, SH_GP4 = 2, SH_GENERIC = 3 };
+
+__device__ __forceinline__ int pair_shape(const PairDesc& d, int mode) {
+    if (d.a1 >= 0 && d.b1 >= 0) {
+        if (mode == IGMK_MODE_GP) return SH_GP4;
+        return (d.cmask == 15) ? SH_FULL4 : SH_INTRA2;
+    }
+    return SH_GENERIC;
+}
+
+struct Row3 { float4 x, y, z; };
+
+__device__ __forceinline__ Row3 load_row3(const float* base, int npad, int off) {
+    Row3 r;
+    r.x = __ldg(reinterpret_cast<const float4*>(base + off));
+    r.y = __ldg(reinterpret_cast<const float4*>(base + npad + off));
+    r.z = __ldg(reinterpret_cast<const float4*>(base + 2 * npad + off));
+    return r;
+}
+
+__device__ __forceinline__ float f4get(const float4& v, int q) {
+    return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
+}
+
+__device__ __forceinline__ float d2q(const Row3& a, const Row3& b, int q) {
+    return d2_nofma(f4get(a.x, q), f4get(a.y, q), f4get(a.z, q),
+                    f4get(b.x, q), f4get(b.y, q), f4get(b.z, q));
+}
+
+template <int V, int SH>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
                                           int tid, int nthr, uint32_t (&keys)[V][4][2],
                                           int& cnt) {
+    constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const size_t row = (size_t)3 * P.npad;
     const float* A0 = P.coords + (size_t)d.a0 * row;
     const float* B0 = P.coords + (size_t)d.b0 * row;
     const float* A1 = P.coords + (size_t)(d.a1 >= 0 ? d.a1 : d.a0) * row;
     const float* B1 = P.coords + (size_t)(d.b1 >= 0 ? d.b1 : d.b0) * row;
-    const bool need_a1 = (d.cmask & (CM_D2 | CM_D3)) != 0;
-    const bool need_b1 = (d.cmask & (CM_D1 | CM_D3)) != 0;
     const float qnan = __int_as_float(0x7fffffff);
     const float rc = d.rcutsq;
     const int npad = P.npad;
     int c_local = 0;
 
-#pragma unroll
+    // The chunk loop is deliberately NOT unrolled (instruction-cache footprint):
+    // every iteration produces the keys of one chunk in nk[][] and shifts the
+    // register-resident key array down by one chunk, so that after V iterations
+    // keys[v] holds chunk v.
+#pragma unroll 1
     for (int v = 0; v < V; ++v) {
         const int c = tid + v * nthr;
-        float s[4][4];   // [q][slot]
+        uint32_t nk[NS][2];
         if (c < P.nchunks) {
             const int off = 4 * c;
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 ax0 = __ldg(reinterpret_cast<const float4*>(A0 + off));
-            const float4 ay0 = __ldg(reinterpret_cast<const float4*>(A0 + npad + off));
-            const float4 az0 = __ldg(reinterpret_cast<const float4*>(A0 + 2 * npad + off));
-            const float4 bx0 = __ldg(reinterpret_cast<const float4*>(B0 + off));
-            const float4 by0 = __ldg(reinterpret_cast<const float4*>(B0 + npad + off));
-            const float4 bz0 = __ldg(reinterpret_cast<const float4*>(B0 + 2 * npad + off));
-            float4 ax1 = zero4, ay1 = zero4, az1 = zero4, bx1 = zero4, by1 = zero4, bz1 = zero4;
-            if (need_a1) {
-                ax1 = __ldg(reinterpret_cast<const float4*>(A1 + off));
-                ay1 = __ldg(reinterpret_cast<const float4*>(A1 + npad + off));
-                az1 = __ldg(reinterpret_cast<const float4*>(A1 + 2 * npad + off));
-            }
-            if (need_b1) {
-                bx1 = __ldg(reinterpret_cast<const float4*>(B1 + off));
-                by1 = __ldg(reinterpret_cast<const float4*>(B1 + npad + off));
-                bz1 = __ldg(reinterpret_cast<const float4*>(B1 + 2 * npad + off));
-            }
-            const float AX0[4] = {ax0.x, ax0.y, ax0.z, ax0.w}, AY0[4] = {ay0.x, ay0.y, ay0.z, ay0.w},
-                        AZ0[4] = {az0.x, az0.y, az0.z, az0.w};
-            const float AX1[4] = {ax1.x, ax1.y, ax1.z, ax1.w}, AY1[4] = {ay1.x, ay1.y, ay1.z, ay1.w},
-                        AZ1[4] = {az1.x, az1.y, az1.z, az1.w};
-            const float BX0[4] = {bx0.x, bx0.y, bx0.z, bx0.w}, BY0[4] = {by0.x, by0.y, by0.z, by0.w},
-                        BZ0[4] = {bz0.x, bz0.y, bz0.z, bz0.w};
-            const float BX1[4] = {bx1.x, bx1.y, bx1.z, bx1.w}, BY1[4] = {by1.x, by1.y, by1.z, by1.w},
-                        BZ1[4] = {bz1.x, bz1.y, bz1.z, bz1.w};
+            const Row3 a0 = load_row3(A0, npad, off);
+            const Row3 b0 = load_row3(B0, npad, off);
+            const Row3 a1 = load_row3(A1, npad, off);
+            const Row3 b1 = load_row3(B1, npad, off);
+            float s[4][NS];   // [q][slot]
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float d0, d1 = qnan, d2 = qnan, d3 = qnan;
-                d0 = d2_nofma(AX0[q], AY0[q], AZ0[q], BX0[q], BY0[q], BZ0[q]);
-                if (d.cmask & CM_D1) d1 = d2_nofma(AX0[q], AY0[q], AZ0[q], BX1[q], BY1[q], BZ1[q]);
-                if (d.cmask & CM_D2) d2 = d2_nofma(AX1[q], AY1[q], AZ1[q], BX0[q], BY0[q], BZ0[q]);
-                if (d.cmask & CM_D3) d3 = d2_nofma(AX1[q], AY1[q], AZ1[q], BX1[q], BY1[q], BZ1[q]);
-                pack_slots(d, P.mode, d0, d1, d2, d3, s[q]);
-                if (off + q >= P.nstruct) { s[q][0] = s[q][1] = s[q][2] = s[q][3] = qnan; }
+                if (SH == SH_FULL4) {
+                    s[q][0] = d2q(a0, b0, q);
+                    s[q][1] = d2q(a0, b1, q);
+                    s[q][2] = d2q(a1, b0, q);
+                    s[q][3] = d2q(a1, b1, q);
+                } else if (SH == SH_INTRA2) {
+                    s[q][0] = d2q(a0, b0, q);
+                    s[q][1] = d2q(a1, b1, q);
+                } else if (SH == SH_GP4) {
+                    const float e0 = d2q(a0, b0, q), e1 = d2q(a0, b1, q);
+                    const float e2 = d2q(a1, b0, q), e3 = d2q(a1, b1, q);
+                    const float lo1 = fminf(e0, e1), hi1 = fmaxf(e0, e1);
+                    const float lo2 = fminf(e2, e3), hi2 = fmaxf(e2, e3);
+                    s[q][0] = fminf(lo1, lo2);
+                    s[q][1] = fminf(fmaxf(lo1, lo2), fminf(hi1, hi2));
+                } else {
+                    const float e0 = d2q(a0, b0, q);
+                    const float e1 = (d.cmask & CM_D1) ? d2q(a0, b1, q) : qnan;
+                    const float e2 = (d.cmask & CM_D2) ? d2q(a1, b0, q) : qnan;
+                    const float e3 = (d.cmask & CM_D3) ? d2q(a1, b1, q) : qnan;
+                    float t[4];
+                    pack_slots(d, P.mode, e0, e1, e2, e3, t);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) c_local += (s[q][k] <= rc) ? 1 : 0;   // NaN: false
+                    for (int k = 0; k < NS; ++k) s[q][k] = t[k];
+                }
             }
-        } else {
+            if (off + 4 > P.nstruct) {          // tail chunk of the population (one thread)
+#pragma unroll
+                for (int q = 1; q < 4; ++q)
+                    if (off + q >= P.nstruct) {
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) s[q][k] = qnan;
+                    }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) s[q][k] = qnan;
+                for (int k = 0; k < NS; ++k) c_local += (s[q][k] <= rc) ? 1 : 0;   // NaN: false
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+#pragma unroll
+                for (int qh = 0; qh < 2; ++qh) {
+                    // {hi16(s[2qh]), hi16(s[2qh+1])}: bytes 2,3 of each -> one PRMT
+                    nk[k][qh] = __byte_perm(__float_as_uint(s[2 * qh][k]),
+                                            __float_as_uint(s[2 * qh + 1][k]), 0x7632);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { nk[k][0] = 0x7fff7fffu; nk[k][1] = 0x7fff7fffu; }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NS; ++k) {
 #pragma unroll
-            for (int qh = 0; qh < 2; ++qh) {
-                // {hi16(s[2qh]), hi16(s[2qh+1])}: bytes 2,3 of each -> PRMT
-                keys[v][k][qh] = __byte_perm(__float_as_uint(s[2 * qh][k]),
-                                             __float_as_uint(s[2 * qh + 1][k]), 0x7632);
+            for (int u = 0; u + 1 < V; ++u) {
+                keys[u][k][0] = keys[u + 1][k][0];
+                keys[u][k][1] = keys[u + 1][k][1];
             }
+            keys[V - 1][k][0] = nk[k][0];
+            keys[V - 1][k][1] = nk[k][1];
         }
     }
     cnt = c_local;
@@ -213,17 +266,31 @@ __device__ __forceinline__ void scan_range(const uint32_t (&keys)[V][4][2], int 
         }
 }
 
-// full float32 bit pattern of the element behind bit `bit` of word `w`
-__device__ __forceinline__ uint32_t element_bits(const ActdistParams& P, const PairDesc& d,
+// full float32 bit pattern of kept slot `slot` of structure `st`, re-materialised
+// from the coordinates (candidate gathering; deliberately out of line)
+__device__ __noinline__ uint32_t recompute_slot(const float* coords, const HapEntry* hap,
+                                                int nstruct, int npad, int nchunks, int n_hap,
+                                                float contact_range, int mode,
+                                                int i, int j, int st, int slot) {
+    ActdistParams P;
+    P.coords = coords; P.hap = hap; P.nstruct = nstruct; P.npad = npad; P.nchunks = nchunks;
+    P.n_hap = n_hap; P.contact_range = contact_range; P.mode = mode; P.it_corr = 0;
+    const PairDesc d = make_pair_desc(P, i, j);
+    float s[4];
+    struct_slots(P, d, st, s);
+    const float val = (slot == 0) ? s[0] : (slot == 1) ? s[1] : (slot == 2) ? s[2] : s[3];
+    return __float_as_uint(val);
+}
+
+// element behind bit `bit` of word `w` of a scan_range bitmap
+__device__ __forceinline__ uint32_t element_bits(const ActdistParams& P, int i, int j,
                                                  int tid, int nthr, int w, int bit) {
     const int R = (w << 4) | (bit & 15);
     const int half = bit >> 4;
     const int v = R >> 3, slot = (R >> 1) & 3, qh = R & 1;
     const int st = 4 * (tid + v * nthr) + 2 * qh + half;
-    float s[4];
-    struct_slots(P, d, st, s);
-    const float val = (slot == 0) ? s[0] : (slot == 1) ? s[1] : (slot == 2) ? s[2] : s[3];
-    return __float_as_uint(val);
+    return recompute_slot(P.coords, P.hap, P.nstruct, P.npad, P.nchunks, P.n_hap,
+                          P.contact_range, P.mode, i, j, st, slot);
 }
 
 // ------------------------------------------------------------- one pair
@@ -239,8 +306,17 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
     const double pwish = __ldg(P.pwish + pair), plast = __ldg(P.plast + pair);
 
     uint32_t keys[V][4][2];
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { keys[v][k][0] = 0x7fff7fffu; keys[v][k][1] = 0x7fff7fffu; }
     int cnt;
-    fill_keys<V>(P, d, g.tid, g.nthr, keys, cnt);
+    switch (pair_shape(d, P.mode)) {       // uniform over the group
+        case SH_FULL4:  fill_keys<V, SH_FULL4>(P, d, g.tid, g.nthr, keys, cnt); break;
+        case SH_INTRA2: fill_keys<V, SH_INTRA2>(P, d, g.tid, g.nthr, keys, cnt); break;
+        case SH_GP4:    fill_keys<V, SH_GP4>(P, d, g.tid, g.nthr, keys, cnt); break;
+        default:        fill_keys<V, SH_GENERIC>(P, d, g.tid, g.nthr, keys, cnt); break;
+    }
 
     // per-thread key range (NaN halves are ignored by min/max.bf16x2)
     uint32_t mn2 = 0x7fff7fffu, mx2 = 0x7fff7fffu;
@@ -299,7 +375,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
                 while (b) {
                     const int bit = __ffs(b) - 1;
                     b &= b - 1;
-                    const uint32_t x = element_bits(P, d, g.tid, g.nthr, w, bit);
+                    const uint32_t x = element_bits(P, i, j, g.tid, g.nthr, w, bit);
                     c_loc += ((x & 0xffffu) <= m2) ? 1 : 0;
                 }
             }
@@ -323,7 +399,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
         while (b) {
             const int bit = __ffs(b) - 1;
             b &= b - 1;
-            const uint32_t x = element_bits(P, d, g.tid, g.nthr, w, bit);
+            const uint32_t x = element_bits(P, i, j, g.tid, g.nthr, w, bit);
             if (x >= vlo && x <= vhi) {
                 const int slot = atomicAdd(g.cand_cnt, 1);
                 if (slot < kCandCap) g.cand[slot] = x;
@@ -357,7 +433,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
 constexpr int kWarpsPerBlock = 8;
 
 template <int V>
-__global__ void __launch_bounds__(32 * kWarpsPerBlock, 2)
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
 actdist_warp_kernel(const ActdistParams P) {
     __shared__ uint32_t s_cand[kWarpsPerBlock][kCandCap];
     __shared__ int s_cnt[kWarpsPerBlock];
@@ -376,8 +452,8 @@ actdist_warp_kernel(const ActdistParams P) {
 }
 
 // G = blockDim.x (multiple of 32, <= 1024): one pair per CTA.
-template <int V, int MAXT>
-__global__ void __launch_bounds__(MAXT)
+template <int V, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 actdist_block_kernel(const ActdistParams P) {
     __shared__ uint32_t s_cand[kCandCap];
     __shared__ int s_cnt;
