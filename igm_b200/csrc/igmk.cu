@@ -89,7 +89,7 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     c->device = device;
     c->nbead = nbead;
     c->nstruct = nstruct;
-    c->npad = (nstruct + 31) / 32 * 32;
+    c->npad = (nstruct + kSeg - 1) / kSeg * kSeg;
     c->nchunks = (nstruct + 3) / 4;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -123,7 +123,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     return IGMK_OK;
 }
 
-// (nb, nstruct, 3) bead-major AoS  ->  [bead][xyz][npad] SoA
+// (nb, nstruct, 3) bead-major AoS  ->  [bead][segment of 128 structures][xyz][128]
 __global__ void stage_coords_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                     int nstruct, int npad) {
     const size_t bead = blockIdx.x;
@@ -131,7 +131,7 @@ __global__ void stage_coords_kernel(const float* __restrict__ src, float* __rest
     float* d = dst + bead * (size_t)npad * 3;
     for (int t = threadIdx.x; t < 3 * nstruct; t += blockDim.x) {
         const int st = t / 3, c = t - 3 * st;
-        d[(size_t)c * npad + st] = s[t];
+        d[coord_off(st) + (size_t)c * kSeg] = s[t];
     }
 }
 
@@ -195,6 +195,14 @@ extern "C" int igmk_set_index(igmk_ctx* c, int n_hap, const int32_t* copy_ptr,
 }
 
 // ------------------------------------------------------------- K1 launches
+static int launch_finish(const ActdistParams& P, cudaStream_t st) {
+    const long long blocks = (P.n_pairs + 255) / 256;
+    finish_results_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.out, P.n_pairs);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
 template <int V>
 static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
     int per_sm = 0;
@@ -207,7 +215,7 @@ static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t s
     actdist_warp_kernel<V><<<grid, 32 * kWarpsPerBlock, 0, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    return IGMK_OK;
+    return launch_finish(P, st);
 }
 
 template <int V, int MAXT, int MINB>
@@ -220,7 +228,7 @@ static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, 
     actdist_block_kernel<V, MAXT, MINB><<<grid, threads, 0, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    return IGMK_OK;
+    return launch_finish(P, st);
 }
 
 static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
@@ -235,7 +243,7 @@ static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t
     actdist_simple_kernel<<<grid, 256, smem, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
-    return IGMK_OK;
+    return launch_finish(P, st);
 }
 
 extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,

@@ -5,11 +5,11 @@
 // igm/steps/GP_activation.py:367-424).
 //
 // Fast kernel, per candidate pair handled by a group of G threads
-// (G = 32: one warp per pair for nstruct <= 1024; G = blockDim for larger
-// populations):
-//   1. every thread streams V float4 chunks (4 structures each) of the <= 4
-//      bead rows with 128-bit loads, computes the copy-combination d2 values
-//      in registers (non-FMA float32, bit-identical to NumPy), counts
+// (G = 32: one warp per pair for nstruct <= 512; G = blockDim for larger
+// populations, 64 threads at nstruct = 1000, 640 at 10 000):
+//   1. every thread streams V <= 4 float4 chunks (4 structures each) of the
+//      <= 4 bead rows with 128-bit loads, computes the copy-combination d2
+//      values in registers (non-FMA float32, bit-identical to NumPy), counts
 //      d2 <= rcutsq, and keeps only the HIGH 16 BITS of each kept d2, two per
 //      register (bf16x2).  d2 >= 0, so bf16 order == float order.
 //   2. p and the order-statistic index o are evaluated in float64.
@@ -28,11 +28,12 @@ namespace igmk {
 constexpr int kCandCap = 32;
 
 // ------------------------------------------------------------------ groups
+// Shared scratch is addressed through 32-bit shared-window addresses.
 struct WarpGroup {
     int tid;            // lane
     int nthr;           // 32
-    uint32_t* cand;     // shared, kCandCap entries (per warp)
-    int* cand_cnt;      // shared (per warp)
+    uint32_t cand;      // shared address of kCandCap words (per warp)
+    uint32_t cand_cnt;  // shared address of the candidate counter (per warp)
 
     __device__ __forceinline__ int sum(int x) { return __reduce_add_sync(0xffffffffu, x); }
     __device__ __forceinline__ void sum_min_max(int& s, uint32_t& mn, uint32_t& mx) {
@@ -42,54 +43,49 @@ struct WarpGroup {
     }
     __device__ __forceinline__ void sync() { __syncwarp(); }
     __device__ __forceinline__ bool leader_warp() const { return true; }
-    __device__ __forceinline__ uint32_t bcast(uint32_t v) { return v; }  // already warp-uniform
 };
 
 struct BlockGroup {
     int tid;
     int nthr;
-    uint32_t* cand;
-    int* cand_cnt;
-    int* red;           // shared [2][3][32]
-    uint32_t* bc;       // shared broadcast slot
+    uint32_t cand;
+    uint32_t cand_cnt;
+    uint32_t red;       // shared address of [2][3][32] words
     int parity;
 
     __device__ __forceinline__ int sum(int x) {
         const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
-        int* r = red + parity * 96;
-        const int w = __reduce_add_sync(0xffffffffu, x);
-        if (lane == 0) r[warp] = w;
-        __syncthreads();
-        const int v = (lane < nw) ? r[lane] : 0;
+        const uint32_t r = red + parity * 384;
         parity ^= 1;
+        const int w = __reduce_add_sync(0xffffffffu, x);
+        if (lane == 0) sts32(r + warp * 4, (uint32_t)w);
+        __syncthreads();
+        if (nw == 2) return w + (int)lds32(r + (warp ^ 1) * 4);
+        const int v = (lane < nw) ? (int)lds32(r + lane * 4) : 0;
         return __reduce_add_sync(0xffffffffu, v);
     }
     __device__ __forceinline__ void sum_min_max(int& s, uint32_t& mn, uint32_t& mx) {
         const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
-        int* r = red + parity * 96;
+        const uint32_t r = red + parity * 384;
+        parity ^= 1;
         const int ws = __reduce_add_sync(0xffffffffu, s);
         const uint32_t wmn = __reduce_min_sync(0xffffffffu, mn);
         const uint32_t wmx = __reduce_max_sync(0xffffffffu, mx);
-        if (lane == 0) { r[warp] = ws; r[32 + warp] = (int)wmn; r[64 + warp] = (int)wmx; }
+        if (lane == 0) {
+            sts32(r + warp * 4, (uint32_t)ws);
+            sts32(r + 128 + warp * 4, wmn);
+            sts32(r + 256 + warp * 4, wmx);
+        }
         __syncthreads();
-        const int vs = (lane < nw) ? r[lane] : 0;
-        const uint32_t vmn = (lane < nw) ? (uint32_t)r[32 + lane] : 0xffffffffu;
-        const uint32_t vmx = (lane < nw) ? (uint32_t)r[64 + lane] : 0u;
-        parity ^= 1;
+        const int vs = (lane < nw) ? (int)lds32(r + lane * 4) : 0;
+        const uint32_t vmn = (lane < nw) ? lds32(r + 128 + lane * 4) : 0xffffffffu;
+        const uint32_t vmx = (lane < nw) ? lds32(r + 256 + lane * 4) : 0u;
         s = __reduce_add_sync(0xffffffffu, vs);
         mn = __reduce_min_sync(0xffffffffu, vmn);
         mx = __reduce_max_sync(0xffffffffu, vmx);
     }
     __device__ __forceinline__ void sync() { __syncthreads(); }
     __device__ __forceinline__ bool leader_warp() const { return tid < 32; }
-    // value known to warp 0 only -> everybody
-    __device__ __forceinline__ uint32_t bcast(uint32_t v) {
-        if (tid == 0) *bc = v;
-        __syncthreads();
-        const uint32_t r = *bc;
-        __syncthreads();
-        return r;
-    }
 };
 
 // --------------------------------------------------------- stage 1: fill keys
@@ -113,11 +109,12 @@ __device__ __forceinline__ int pair_shape(const PairDesc& d, int mode) {
 
 struct Row3 { float4 x, y, z; };
 
-__device__ __forceinline__ Row3 load_row3(const float* base, int npad, int off) {
+// x / y / z of 4 consecutive structures: three 128-bit loads at constant offsets
+__device__ __forceinline__ Row3 load_row3(const float* p) {
     Row3 r;
-    r.x = __ldg(reinterpret_cast<const float4*>(base + off));
-    r.y = __ldg(reinterpret_cast<const float4*>(base + npad + off));
-    r.z = __ldg(reinterpret_cast<const float4*>(base + 2 * npad + off));
+    r.x = __ldg(reinterpret_cast<const float4*>(p));
+    r.y = __ldg(reinterpret_cast<const float4*>(p + kSeg));
+    r.z = __ldg(reinterpret_cast<const float4*>(p + 2 * kSeg));
     return r;
 }
 
@@ -130,19 +127,33 @@ __device__ __forceinline__ float d2q(const Row3& a, const Row3& b, int q) {
                     f4get(b.x, q), f4get(b.y, q), f4get(b.z, q));
 }
 
+struct PairPtrs { const float *A0, *A1, *B0, *B1; };
+
+__device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const PairDesc& d) {
+    const size_t row = (size_t)3 * P.npad;
+    PairPtrs pp;
+    pp.A0 = P.coords + (size_t)d.a0 * row;
+    pp.B0 = P.coords + (size_t)d.b0 * row;
+    pp.A1 = P.coords + (size_t)(d.a1 >= 0 ? d.a1 : d.a0) * row;
+    pp.B1 = P.coords + (size_t)(d.b1 >= 0 ? d.b1 : d.b0) * row;
+    return pp;
+}
+
 template <int V, int SH>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
-                                          int tid, int nthr, uint32_t (&keys)[V][4][2],
-                                          int& cnt) {
+                                          const PairPtrs& pp, int tid, int nthr,
+                                          uint32_t (&keys)[V][4][2], int& cnt) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
-    const size_t row = (size_t)3 * P.npad;
-    const float* A0 = P.coords + (size_t)d.a0 * row;
-    const float* B0 = P.coords + (size_t)d.b0 * row;
-    const float* A1 = P.coords + (size_t)(d.a1 >= 0 ? d.a1 : d.a0) * row;
-    const float* B1 = P.coords + (size_t)(d.b1 >= 0 ? d.b1 : d.b0) * row;
     const float qnan = __int_as_float(0x7fffffff);
     const float rc = d.rcutsq;
-    const int npad = P.npad;
+    // chunk c = tid + v * nthr lives in segment c >> 5 at lane offset (c & 31) * 4;
+    // nthr is a multiple of 32, so only the segment advances with v.
+    const size_t off0 = (size_t)(tid >> 5) * kSegFloats + (size_t)(tid & 31) * 4;
+    const size_t vstride = (size_t)(nthr >> 5) * kSegFloats;
+    const float* pa0 = pp.A0 + off0;
+    const float* pb0 = pp.B0 + off0;
+    const float* pa1 = pp.A1 + off0;
+    const float* pb1 = pp.B1 + off0;
     int c_local = 0;
 
     // The chunk loop is deliberately NOT unrolled (instruction-cache footprint):
@@ -154,11 +165,10 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
         const int c = tid + v * nthr;
         uint32_t nk[NS][2];
         if (c < P.nchunks) {
-            const int off = 4 * c;
-            const Row3 a0 = load_row3(A0, npad, off);
-            const Row3 b0 = load_row3(B0, npad, off);
-            const Row3 a1 = load_row3(A1, npad, off);
-            const Row3 b1 = load_row3(B1, npad, off);
+            const Row3 a0 = load_row3(pa0);
+            const Row3 b0 = load_row3(pb0);
+            const Row3 a1 = load_row3(pa1);
+            const Row3 b1 = load_row3(pb1);
             float s[4][NS];   // [q][slot]
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -188,10 +198,10 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
                     for (int k = 0; k < NS; ++k) s[q][k] = t[k];
                 }
             }
-            if (off + 4 > P.nstruct) {          // tail chunk of the population (one thread)
+            if (4 * c + 4 > P.nstruct) {        // tail chunk of the population (one thread)
 #pragma unroll
                 for (int q = 1; q < 4; ++q)
-                    if (off + q >= P.nstruct) {
+                    if (4 * c + q >= P.nstruct) {
 #pragma unroll
                         for (int k = 0; k < NS; ++k) s[q][k] = qnan;
                     }
@@ -223,6 +233,7 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
             keys[V - 1][k][0] = nk[k][0];
             keys[V - 1][k][1] = nk[k][1];
         }
+        pa0 += vstride; pb0 += vstride; pa1 += vstride; pb1 += vstride;
     }
     cnt = c_local;
 }
@@ -266,31 +277,41 @@ __device__ __forceinline__ void scan_range(const uint32_t (&keys)[V][4][2], int 
         }
 }
 
-// full float32 bit pattern of kept slot `slot` of structure `st`, re-materialised
-// from the coordinates (candidate gathering; deliberately out of line)
-__device__ __noinline__ uint32_t recompute_slot(const float* coords, const HapEntry* hap,
-                                                int nstruct, int npad, int nchunks, int n_hap,
-                                                float contact_range, int mode,
-                                                int i, int j, int st, int slot) {
-    ActdistParams P;
-    P.coords = coords; P.hap = hap; P.nstruct = nstruct; P.npad = npad; P.nchunks = nchunks;
-    P.n_hap = n_hap; P.contact_range = contact_range; P.mode = mode; P.it_corr = 0;
-    const PairDesc d = make_pair_desc(P, i, j);
+// Full float32 pattern of one kept value, re-materialised from the coordinates
+// (candidate gathering; deliberately out of line).  LB: slot -> one combination.
+__device__ __noinline__ uint32_t recompute_lb(const float* pa, const float* pb, int st) {
+    return __float_as_uint(d2_scalar(pa, pb, st));
+}
+// GP: all combinations of the structure, then the kept slot.
+__device__ __noinline__ uint32_t recompute_gp(const float* A0, const float* A1, const float* B0,
+                                              const float* B1, int cmask, int keep, int st,
+                                              int slot) {
+    const float qnan = __int_as_float(0x7fffffff);
+    PairDesc d;
+    d.cmask = cmask; d.keep = keep;
+    const float d0 = d2_scalar(A0, B0, st);
+    const float d1 = (cmask & CM_D1) ? d2_scalar(A0, B1, st) : qnan;
+    const float d2 = (cmask & CM_D2) ? d2_scalar(A1, B0, st) : qnan;
+    const float d3 = (cmask & CM_D3) ? d2_scalar(A1, B1, st) : qnan;
     float s[4];
-    struct_slots(P, d, st, s);
-    const float val = (slot == 0) ? s[0] : (slot == 1) ? s[1] : (slot == 2) ? s[2] : s[3];
-    return __float_as_uint(val);
+    pack_slots(d, IGMK_MODE_GP, d0, d1, d2, d3, s);
+    return __float_as_uint(slot == 0 ? s[0] : s[1]);
 }
 
 // element behind bit `bit` of word `w` of a scan_range bitmap
-__device__ __forceinline__ uint32_t element_bits(const ActdistParams& P, int i, int j,
+__device__ __forceinline__ uint32_t element_bits(const PairPtrs& pp, const PairDesc& d, int mode,
                                                  int tid, int nthr, int w, int bit) {
     const int R = (w << 4) | (bit & 15);
     const int half = bit >> 4;
     const int v = R >> 3, slot = (R >> 1) & 3, qh = R & 1;
     const int st = 4 * (tid + v * nthr) + 2 * qh + half;
-    return recompute_slot(P.coords, P.hap, P.nstruct, P.npad, P.nchunks, P.n_hap,
-                          P.contact_range, P.mode, i, j, st, slot);
+    if (mode == IGMK_MODE_GP)
+        return recompute_gp(pp.A0, pp.A1, pp.B0, pp.B1, d.cmask, d.keep, st, slot);
+    // LB: the slot-th existing combination (enumeration order d0..d3)
+    int cm = d.cmask;
+    for (int t = 0; t < slot; ++t) cm &= cm - 1;
+    const int comb = __ffs(cm) - 1;
+    return recompute_lb((comb & 2) ? pp.A1 : pp.A0, (comb & 1) ? pp.B1 : pp.B0, st);
 }
 
 // ------------------------------------------------------------- one pair
@@ -304,6 +325,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
         return;
     }
     const double pwish = __ldg(P.pwish + pair), plast = __ldg(P.plast + pair);
+    const PairPtrs pp = pair_ptrs(P, d);
 
     uint32_t keys[V][4][2];
 #pragma unroll
@@ -312,10 +334,10 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
         for (int k = 0; k < 4; ++k) { keys[v][k][0] = 0x7fff7fffu; keys[v][k][1] = 0x7fff7fffu; }
     int cnt;
     switch (pair_shape(d, P.mode)) {       // uniform over the group
-        case SH_FULL4:  fill_keys<V, SH_FULL4>(P, d, g.tid, g.nthr, keys, cnt); break;
-        case SH_INTRA2: fill_keys<V, SH_INTRA2>(P, d, g.tid, g.nthr, keys, cnt); break;
-        case SH_GP4:    fill_keys<V, SH_GP4>(P, d, g.tid, g.nthr, keys, cnt); break;
-        default:        fill_keys<V, SH_GENERIC>(P, d, g.tid, g.nthr, keys, cnt); break;
+        case SH_FULL4:  fill_keys<V, SH_FULL4>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
+        case SH_INTRA2: fill_keys<V, SH_INTRA2>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
+        case SH_GP4:    fill_keys<V, SH_GP4>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
+        default:        fill_keys<V, SH_GENERIC>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
     }
 
     // per-thread key range (NaN halves are ignored by min/max.bf16x2)
@@ -335,7 +357,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
     mxl = (mxl > 0x7f80u) ? 0u : mxl;
     mxh = (mxh > 0x7f80u) ? 0u : mxh;
     uint32_t kmax = max(mxl, mxh);
-    if (g.tid == 0) *g.cand_cnt = 0;
+    if (g.tid == 0) sts32(g.cand_cnt, 0u);
     g.sum_min_max(cnt, kmin, kmax);
 
     double p;
@@ -375,7 +397,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
                 while (b) {
                     const int bit = __ffs(b) - 1;
                     b &= b - 1;
-                    const uint32_t x = element_bits(P, i, j, g.tid, g.nthr, w, bit);
+                    const uint32_t x = element_bits(pp, d, P.mode, g.tid, g.nthr, w, bit);
                     c_loc += ((x & 0xffffu) <= m2) ? 1 : 0;
                 }
             }
@@ -399,10 +421,10 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
         while (b) {
             const int bit = __ffs(b) - 1;
             b &= b - 1;
-            const uint32_t x = element_bits(P, i, j, g.tid, g.nthr, w, bit);
+            const uint32_t x = element_bits(pp, d, P.mode, g.tid, g.nthr, w, bit);
             if (x >= vlo && x <= vhi) {
-                const int slot = atomicAdd(g.cand_cnt, 1);
-                if (slot < kCandCap) g.cand[slot] = x;
+                const uint32_t slot = atoms_inc(g.cand_cnt);
+                if (slot < (uint32_t)kCandCap) sts32(g.cand + slot * 4, x);
             }
         }
     }
@@ -411,12 +433,11 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
     // ---- exact rank inside one warp: the (o - cb)-th smallest candidate
     if (g.leader_warp()) {
         const int lane = g.tid & 31;
-        const int n = min(*g.cand_cnt, kCandCap);
+        const int n = min((int)lds32(g.cand_cnt), kCandCap);
         const int r = o - cb;
-        const uint32_t x = (lane < n) ? g.cand[lane] : 0xffffffffu;
+        const uint32_t x = (lane < n) ? lds32(g.cand + lane * 4) : 0xffffffffu;
         int rank = 0;
-#pragma unroll 8
-        for (int t = 0; t < kCandCap; ++t) {
+        for (int t = 0; t < n; ++t) {
             const uint32_t y = __shfl_sync(0xffffffffu, x, t);
             rank += (y < x || (y == x && t < lane)) ? 1 : 0;
         }
@@ -436,13 +457,13 @@ template <int V>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 actdist_warp_kernel(const ActdistParams P) {
     __shared__ uint32_t s_cand[kWarpsPerBlock][kCandCap];
-    __shared__ int s_cnt[kWarpsPerBlock];
+    __shared__ uint32_t s_cnt[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5;
     WarpGroup g;
     g.tid = threadIdx.x & 31;
     g.nthr = 32;
-    g.cand = s_cand[warp];
-    g.cand_cnt = &s_cnt[warp];
+    g.cand = smem_addr(&s_cand[warp][0]);
+    g.cand_cnt = smem_addr(&s_cnt[warp]);
     const long long stride = (long long)gridDim.x * kWarpsPerBlock;
     for (long long pair = (long long)blockIdx.x * kWarpsPerBlock + warp; pair < P.n_pairs;
          pair += stride) {
@@ -451,21 +472,19 @@ actdist_warp_kernel(const ActdistParams P) {
     }
 }
 
-// G = blockDim.x (multiple of 32, <= 1024): one pair per CTA.
+// G = blockDim.x (multiple of 32, <= 768): one pair per CTA.
 template <int V, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 actdist_block_kernel(const ActdistParams P) {
     __shared__ uint32_t s_cand[kCandCap];
-    __shared__ int s_cnt;
-    __shared__ int s_red[2 * 96];
-    __shared__ uint32_t s_bc;
+    __shared__ uint32_t s_cnt;
+    __shared__ uint32_t s_red[2 * 96];
     BlockGroup g;
     g.tid = threadIdx.x;
     g.nthr = blockDim.x;
-    g.cand = s_cand;
-    g.cand_cnt = &s_cnt;
-    g.red = s_red;
-    g.bc = &s_bc;
+    g.cand = smem_addr(s_cand);
+    g.cand_cnt = smem_addr(&s_cnt);
+    g.red = smem_addr(s_red);
     g.parity = 0;
     for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
         process_pair<V, BlockGroup>(P, g, pair);

@@ -121,10 +121,11 @@ contact_tile_kernel(const ContactParams P) {
             const int comp = rem >> 3, v4 = rem & 7;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const int a = a_base + bead, b = b_base + bead;
+            const size_t so = coord_off(s0 + 4 * v4) + (size_t)comp * kSeg;
             const float4 va = (a < a_end)
-                ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)a * row + (size_t)comp * P.npad + s0 + 4 * v4)) : z;
+                ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)a * row + so)) : z;
             const float4 vb = (b < b_end)
-                ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)b * row + (size_t)comp * P.npad + s0 + 4 * v4)) : z;
+                ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)b * row + so)) : z;
             *reinterpret_cast<float4*>(s_a + bead * kCtRow + comp * kCtStruct + 4 * v4) = va;
             *reinterpret_cast<float4*>(s_b + bead * kCtRow + comp * kCtStruct + 4 * v4) = vb;
         }

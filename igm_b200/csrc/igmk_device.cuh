@@ -6,6 +6,13 @@
 //   strictly sequential, no FMA  (np.sum(np.square(x - y), axis=1),
 //   igm/steps/ActivationDistanceStep.py:418,435)
 //   p / o arithmetic in float64 exactly as CPython evaluates :445-470.
+//
+// Coordinate layout in HBM (one block of 3 * npad floats per bead, npad a
+// multiple of 128):
+//   [bead][segment of 128 structures][x | y | z][128]
+// so one bead's coordinates over all structures are contiguous (12 * npad
+// bytes), a warp's 128-bit loads of one component are one 512-byte run, and
+// the x / y / z loads of a chunk differ by the constants 512 / 1024 bytes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -13,6 +20,14 @@
 #include "../../include/igmk.h"
 
 namespace igmk {
+
+constexpr int kSeg = 128;              // structures per row segment
+constexpr int kSegFloats = 3 * kSeg;   // floats per segment (x, y, z rows)
+
+// float offset of (component 0, structure s) inside one bead's block
+__host__ __device__ __forceinline__ size_t coord_off(int s) {
+    return (size_t)(s >> 7) * kSegFloats + (size_t)(s & (kSeg - 1));
+}
 
 // One haploid bin: bead ids of its (<= 2) copies, chromosome, radius of copy 0.
 struct __align__(16) HapEntry {
@@ -23,7 +38,7 @@ struct __align__(16) HapEntry {
 };
 
 struct ActdistParams {
-    const float*    coords;   // [nbead][3][npad] float32
+    const float*    coords;   // see layout above
     const HapEntry* hap;      // [n_hap]
     const int32_t*  pi;
     const int32_t*  pj;
@@ -32,7 +47,7 @@ struct ActdistParams {
     igmk_pair_result* out;
     long long n_pairs;
     int   nstruct;
-    int   npad;               // row stride in floats, multiple of 32
+    int   npad;               // padded structure count, multiple of 128
     int   nchunks;            // ceil(nstruct / 4)
     int   n_hap;
     float contact_range;      // already float32 (NEP-50: python float * f32 -> f32)
@@ -124,30 +139,27 @@ __device__ __forceinline__ void pack_slots(const PairDesc& d, int mode, float d0
     }
 }
 
+// d2 of structure st between the beads whose blocks start at pa / pb (scalar loads)
+__device__ __forceinline__ float d2_scalar(const float* pa, const float* pb, int st) {
+    const size_t o = coord_off(st);
+    return d2_nofma(__ldg(pa + o), __ldg(pa + o + kSeg), __ldg(pa + o + 2 * kSeg),
+                    __ldg(pb + o), __ldg(pb + o + kSeg), __ldg(pb + o + 2 * kSeg));
+}
+
 // All kept values of structure `st` from scalar loads (slow path: candidate
-// re-materialisation, simple kernel).
+// re-materialisation in GP mode, cross-check kernel).
 __device__ __forceinline__ void struct_slots(const ActdistParams& P, const PairDesc& d, int st,
                                              float (&s)[4]) {
     const float qnan = __int_as_float(0x7fffffff);
     const size_t row = (size_t)3 * P.npad;
-    float ax[2] = {0, 0}, ay[2] = {0, 0}, az[2] = {0, 0};
-    float bx[2] = {0, 0}, by[2] = {0, 0}, bz[2] = {0, 0};
-    const float* pa0 = P.coords + (size_t)d.a0 * row + st;
-    ax[0] = __ldg(pa0); ay[0] = __ldg(pa0 + P.npad); az[0] = __ldg(pa0 + 2 * P.npad);
-    const float* pb0 = P.coords + (size_t)d.b0 * row + st;
-    bx[0] = __ldg(pb0); by[0] = __ldg(pb0 + P.npad); bz[0] = __ldg(pb0 + 2 * P.npad);
-    if (d.a1 >= 0) {
-        const float* pa1 = P.coords + (size_t)d.a1 * row + st;
-        ax[1] = __ldg(pa1); ay[1] = __ldg(pa1 + P.npad); az[1] = __ldg(pa1 + 2 * P.npad);
-    }
-    if (d.b1 >= 0) {
-        const float* pb1 = P.coords + (size_t)d.b1 * row + st;
-        bx[1] = __ldg(pb1); by[1] = __ldg(pb1 + P.npad); bz[1] = __ldg(pb1 + 2 * P.npad);
-    }
-    const float d0 = d2_nofma(ax[0], ay[0], az[0], bx[0], by[0], bz[0]);
-    const float d1 = (d.cmask & CM_D1) ? d2_nofma(ax[0], ay[0], az[0], bx[1], by[1], bz[1]) : qnan;
-    const float d2 = (d.cmask & CM_D2) ? d2_nofma(ax[1], ay[1], az[1], bx[0], by[0], bz[0]) : qnan;
-    const float d3 = (d.cmask & CM_D3) ? d2_nofma(ax[1], ay[1], az[1], bx[1], by[1], bz[1]) : qnan;
+    const float* A0 = P.coords + (size_t)d.a0 * row;
+    const float* B0 = P.coords + (size_t)d.b0 * row;
+    const float* A1 = P.coords + (size_t)(d.a1 >= 0 ? d.a1 : d.a0) * row;
+    const float* B1 = P.coords + (size_t)(d.b1 >= 0 ? d.b1 : d.b0) * row;
+    const float d0 = d2_scalar(A0, B0, st);
+    const float d1 = (d.cmask & CM_D1) ? d2_scalar(A0, B1, st) : qnan;
+    const float d2 = (d.cmask & CM_D2) ? d2_scalar(A1, B0, st) : qnan;
+    const float d3 = (d.cmask & CM_D3) ? d2_scalar(A1, B1, st) : qnan;
     pack_slots(d, P.mode, d0, d1, d2, d3, s);
 }
 
@@ -197,24 +209,36 @@ __device__ __forceinline__ float round4_to_f32(double x) {
     return __double2float_rn(__ddiv_rn(r, 1e4));
 }
 
+// Raw per-pair result; dist / prob (the 4-decimal text round trip) are filled in
+// by finish_results_kernel, one thread per pair.
 __device__ __forceinline__ void write_result(igmk_pair_result* out, const PairDesc& d,
                                              uint32_t d2_bits, int count, int o, double p) {
     const int nrec = (o >= 0) ? d.nrec : 0;
-    const float dist = (o >= 0) ? round4_to_f32(sqrt((double)__uint_as_float(d2_bits))) : 0.f;
-    const float prob = (o >= 0) ? round4_to_f32(p) : 0.f;
     const long long pb = __double_as_longlong(p);
-    // two 16-byte stores (layout of igmk_pair_result)
     uint4* dst = reinterpret_cast<uint4*>(out);
     dst[0] = make_uint4(d2_bits, (uint32_t)count, (uint32_t)o, (uint32_t)nrec);
-    dst[1] = make_uint4((uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32),
-                        __float_as_uint(dist), __float_as_uint(prob));
+    dst[1] = make_uint4((uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32), 0u, 0u);
 }
 
 __device__ __forceinline__ void write_empty(igmk_pair_result* out) {
-    uint4 z = make_uint4(0, 0, 0xffffffffu, 0);   // o = -1
     uint4* dst = reinterpret_cast<uint4*>(out);
-    dst[0] = z;
+    dst[0] = make_uint4(0, 0, 0xffffffffu, 0);   // o = -1
     dst[1] = make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(256)
+finish_results_kernel(igmk_pair_result* out, long long n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4 a = reinterpret_cast<const uint4*>(out + t)[0];
+    const int o = (int)a.z;
+    float dist = 0.f, prob = 0.f;
+    if (o >= 0) {
+        const double p = out[t].p;
+        dist = round4_to_f32(sqrt((double)__uint_as_float(a.x)));   // float64 sqrt (:473)
+        prob = round4_to_f32(p);
+    }
+    reinterpret_cast<float2*>(out + t)[3] = make_float2(dist, prob);
 }
 
 // ---- packed bf16x2 primitives (sm_90+ PTX; keys are the high 16 bits of the
@@ -252,6 +276,24 @@ __device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
 // small non-negative integer counts held as bf16 (exact up to 256) -> int
 __device__ __forceinline__ int bf2_count_sum(uint32_t acc) {
     return (int)(__uint_as_float(acc << 16) + __uint_as_float(acc & 0xffff0000u));
+}
+
+// ---- shared memory through 32-bit window addresses (no generic-pointer math)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t atoms_inc(uint32_t addr) {
+    uint32_t v;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 }  // namespace igmk

@@ -74,7 +74,7 @@ int igmk_destroy(igmk_ctx* ctx);
  * (nbead, nstruct, 3) float32, bead-major (igm/core/step.py:373,
  * igm/_preprocess.py:102-105); replaces the per-pair hss.get_bead_crd(k) reads
  * (ActivationDistanceStep.py:415-416,431-432).  Stored in HBM as
- * [bead][xyz][nstruct padded to 32] so one bead's row over all structures is
+ * [bead][segment of 128 structures][xyz][128] so one bead's row over all structures is
  * contiguous.  `on_device` != 0: xyz is a device pointer. */
 int igmk_upload_coords(igmk_ctx* ctx, const float* xyz, int on_device);
 /* Partial upload of beads [bead0, bead0 + nb): lets a loader stream HDF5
