@@ -206,13 +206,15 @@ static int launch_finish(const ActdistParams& P, cudaStream_t st) {
 template <int V>
 static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
     int per_sm = 0;
+    const size_t smem = (size_t)kWarpsPerBlock * 2 * V * 32 * 16;
+    CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel<V>,
-                                                           32 * kWarpsPerBlock, 0));
+                                                           32 * kWarpsPerBlock, smem));
     if (per_sm < 1) per_sm = 1;
     long long want = (P.n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((want < cap) ? want : cap);
-    actdist_warp_kernel<V><<<grid, 32 * kWarpsPerBlock, 0, st>>>(P);
+    actdist_warp_kernel<V><<<grid, 32 * kWarpsPerBlock, smem, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
@@ -221,11 +223,13 @@ static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t s
 template <int V, int MAXT, int MINB>
 static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, cudaStream_t st) {
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<V, MAXT, MINB>, threads, 0));
+    const size_t smem = (size_t)2 * V * threads * 16;
+    CUDA_TRY(cudaFuncSetAttribute(actdist_block_kernel<V, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<V, MAXT, MINB>, threads, smem));
     if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_block_kernel<%d> cannot run with %d threads", V, threads);
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
-    actdist_block_kernel<V, MAXT, MINB><<<grid, threads, 0, st>>>(P);
+    actdist_block_kernel<V, MAXT, MINB><<<grid, threads, smem, st>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
@@ -271,20 +275,30 @@ extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
     // Thread-group shape: V float4 chunks (16 structures x <= 4 combinations) per thread.
     //   nstruct <= 512: one warp per pair, V = ceil(nchunks / 32) <= 4
     //   larger:         one CTA per pair, V = 4, T = ceil(nchunks / 4) rounded up to a warp
-    int force_block = c->block_v_override;
-    if (c->nchunks <= 32 * 4 && !force_block) {
+    // IGMK_BLOCK_V (tuning knob): 0 = default, 1 = force one warp per pair,
+    // 3 = CTA-per-pair compiled for <= 85 registers instead of <= 64.
+    const int knob = c->block_v_override;
+    const bool warp_ok = c->nchunks <= 32 * 8;
+    if (warp_ok && (knob == 1 || (knob == 0 && c->nchunks <= 32 * 4))) {
         const int V = (c->nchunks + 31) / 32;
         switch (V) {
             case 1: return launch_warp<1>(c, P, st);
             case 2: return launch_warp<2>(c, P, st);
             case 3: return launch_warp<3>(c, P, st);
-            default: return launch_warp<4>(c, P, st);
+            case 4: return launch_warp<4>(c, P, st);
+            case 5: return launch_warp<5>(c, P, st);
+            case 6: return launch_warp<6>(c, P, st);
+            case 7: return launch_warp<7>(c, P, st);
+            default: return launch_warp<8>(c, P, st);
         }
     }
     int T = ((c->nchunks + 3) / 4 + 31) / 32 * 32;
     if (T < 32) T = 32;
     if (T > 768) return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 12288", c->nstruct);
-    if (T <= 128) return launch_block<4, 128, 6>(c, P, T, st);
+    if (T <= 128) {
+        if (knob == 3) return launch_block<4, 128, 6>(c, P, T, st);
+        return launch_block<4, 128, 8>(c, P, T, st);      // 64 registers: 16 CTAs x 2 warps per SM
+    }
     return launch_block<4, 768, 1>(c, P, T, st);
 }
 

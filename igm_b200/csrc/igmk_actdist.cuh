@@ -34,6 +34,8 @@ struct WarpGroup {
     int nthr;           // 32
     uint32_t cand;      // shared address of kCandCap words (per warp)
     uint32_t cand_cnt;  // shared address of the candidate counter (per warp)
+    uint32_t kscr;      // shared address of this thread's key scratch column
+    uint32_t kstride;   // bytes between consecutive key quads of one thread
 
     __device__ __forceinline__ int sum(int x) { return __reduce_add_sync(0xffffffffu, x); }
     __device__ __forceinline__ void sum_min_max(int& s, uint32_t& mn, uint32_t& mx) {
@@ -50,6 +52,8 @@ struct BlockGroup {
     int nthr;
     uint32_t cand;
     uint32_t cand_cnt;
+    uint32_t kscr;
+    uint32_t kstride;
     uint32_t red;       // shared address of [2][3][32] words
     int parity;
 
@@ -142,7 +146,7 @@ __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const Pair
 template <int V, int SH>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
                                           const PairPtrs& pp, int tid, int nthr,
-                                          uint32_t (&keys)[V][4][2], int& cnt) {
+                                          uint32_t kscr, uint32_t kstride, int& cnt) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
     const float rc = d.rcutsq;
@@ -156,10 +160,11 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
     const float* pb1 = pp.B1 + off0;
     int c_local = 0;
 
-    // The chunk loop is deliberately NOT unrolled (instruction-cache footprint):
-    // every iteration produces the keys of one chunk in nk[][] and shifts the
-    // register-resident key array down by one chunk, so that after V iterations
-    // keys[v] holds chunk v.
+    // The chunk loop is deliberately NOT unrolled (instruction-cache footprint and
+    // register pressure: 48 registers of loaded coordinates are live here).  The
+    // packed keys of each chunk are parked in this thread's private column of
+    // shared memory (indexable, unlike registers) and pulled back into registers
+    // once after the loop, for the bisection passes.
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
         const int c = tid + v * nthr;
@@ -223,15 +228,10 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
 #pragma unroll
             for (int k = 0; k < NS; ++k) { nk[k][0] = 0x7fff7fffu; nk[k][1] = 0x7fff7fffu; }
         }
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-#pragma unroll
-            for (int u = 0; u + 1 < V; ++u) {
-                keys[u][k][0] = keys[u + 1][k][0];
-                keys[u][k][1] = keys[u + 1][k][1];
-            }
-            keys[V - 1][k][0] = nk[k][0];
-            keys[V - 1][k][1] = nk[k][1];
+        {
+            const uint32_t dst = kscr + (uint32_t)(2 * v) * kstride;
+            sts128(dst, nk[0][0], nk[0][1], nk[1][0], nk[1][1]);
+            if (NS == 4) sts128(dst + kstride, nk[2][0], nk[2][1], nk[3][0], nk[3][1]);
         }
         pa0 += vstride; pb0 += vstride; pa1 += vstride; pb1 += vstride;
     }
@@ -327,17 +327,21 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
     const double pwish = __ldg(P.pwish + pair), plast = __ldg(P.plast + pair);
     const PairPtrs pp = pair_ptrs(P, d);
 
-    uint32_t keys[V][4][2];
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { keys[v][k][0] = 0x7fff7fffu; keys[v][k][1] = 0x7fff7fffu; }
     int cnt;
     switch (pair_shape(d, P.mode)) {       // uniform over the group
-        case SH_FULL4:  fill_keys<V, SH_FULL4>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
-        case SH_INTRA2: fill_keys<V, SH_INTRA2>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
-        case SH_GP4:    fill_keys<V, SH_GP4>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
-        default:        fill_keys<V, SH_GENERIC>(P, d, pp, g.tid, g.nthr, keys, cnt); break;
+        case SH_FULL4:  fill_keys<V, SH_FULL4>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
+        case SH_INTRA2: fill_keys<V, SH_INTRA2>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
+        case SH_GP4:    fill_keys<V, SH_GP4>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
+        default:        fill_keys<V, SH_GENERIC>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
+    }
+    // keys back into registers (each thread reads only what it wrote itself)
+    uint32_t keys[V][4][2];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        lds128(g.kscr + (uint32_t)(2 * v) * g.kstride, keys[v][0][0], keys[v][0][1], keys[v][1][0], keys[v][1][1]);
+        if (d.keep > 2)
+            lds128(g.kscr + (uint32_t)(2 * v + 1) * g.kstride, keys[v][2][0], keys[v][2][1], keys[v][3][0], keys[v][3][1]);
+        else { keys[v][2][0] = keys[v][2][1] = keys[v][3][0] = keys[v][3][1] = 0x7fff7fffu; }
     }
 
     // per-thread key range (NaN halves are ignored by min/max.bf16x2)
@@ -456,6 +460,7 @@ constexpr int kWarpsPerBlock = 8;
 template <int V>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 actdist_warp_kernel(const ActdistParams P) {
+    extern __shared__ uint4 s_keys[];             // [warp][2 V][32] key quads
     __shared__ uint32_t s_cand[kWarpsPerBlock][kCandCap];
     __shared__ uint32_t s_cnt[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5;
@@ -464,6 +469,8 @@ actdist_warp_kernel(const ActdistParams P) {
     g.nthr = 32;
     g.cand = smem_addr(&s_cand[warp][0]);
     g.cand_cnt = smem_addr(&s_cnt[warp]);
+    g.kscr = smem_addr(s_keys) + (uint32_t)(warp * 2 * V * 32 + g.tid) * 16u;
+    g.kstride = 32u * 16u;
     const long long stride = (long long)gridDim.x * kWarpsPerBlock;
     for (long long pair = (long long)blockIdx.x * kWarpsPerBlock + warp; pair < P.n_pairs;
          pair += stride) {
@@ -476,6 +483,7 @@ actdist_warp_kernel(const ActdistParams P) {
 template <int V, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 actdist_block_kernel(const ActdistParams P) {
+    extern __shared__ uint4 s_keys[];             // [2 V][blockDim] key quads
     __shared__ uint32_t s_cand[kCandCap];
     __shared__ uint32_t s_cnt;
     __shared__ uint32_t s_red[2 * 96];
@@ -484,6 +492,8 @@ actdist_block_kernel(const ActdistParams P) {
     g.nthr = blockDim.x;
     g.cand = smem_addr(s_cand);
     g.cand_cnt = smem_addr(&s_cnt);
+    g.kscr = smem_addr(s_keys) + (uint32_t)threadIdx.x * 16u;
+    g.kstride = (uint32_t)blockDim.x * 16u;
     g.red = smem_addr(s_red);
     g.parity = 0;
     for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
