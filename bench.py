@@ -40,7 +40,7 @@ SEED = 20261018
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nstruct", type=int, default=1000)
@@ -88,7 +88,8 @@ def algorithmic_bytes(ci, ii, jj, nstruct):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed region (one long-lived
+    `nvidia-smi -lms 50` process; B200_PROFILING.md's clocks line)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -97,28 +98,46 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self.stop_flag = threading.Event()
+        self.proc = None
+        self.t_start = None
+        self.t_stop = None
 
     def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+        except Exception:
+            pass
+
+    def mark_start(self):
+        self.t_start = time.perf_counter()
+
+    def mark_stop(self):
+        self.t_stop = time.perf_counter()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=5)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows
+                if (self.t_start is None or t >= self.t_start) and (self.t_stop is None or t <= self.t_stop + 0.06)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names)
-                   if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+                   if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(pw) if pw else None}
 
 
 def measured_peak_gbs():
@@ -233,9 +252,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler.mark_start()
     l0 = launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     ev[0].record()
@@ -248,14 +269,15 @@ def main():
             dist.all_gather_into_tensor(gather.view(world * n_pairs, 32), mine)
     ev[-1].record()
     torch.cuda.synchronize()
+    sampler.mark_stop()
     if world > 1:
         dist.barrier()
     launches = launch_count() - l0
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]
     if rank == 0:
-        sampler.stop_flag.set()
-        sampler.join(timeout=5)
+        time.sleep(0.1)
+        sampler.stop()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

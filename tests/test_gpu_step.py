@@ -1,0 +1,64 @@
+"""End-to-end run of the Step drop-in on the GPU: setup -> task -> reduce over the
+shipped demo population (config 1), compared with the reference's records."""
+import hashlib
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from oracle import actdist_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not H.have_demo(), reason="oracle/_ref/demo not present")
+def test_step_run_demo_two_iterations(tmp_path):
+    from igm_b200 import hdf5
+    from igm_b200.population import Population, ProbMatrix
+    from igm_b200.steps.ActivationDistanceStep import ActivationDistanceStep, filter_candidates
+    from igm_b200.steps._compat import Config
+    hss = str(tmp_path / "igm-model.hss")
+    shutil.copyfile(H.DEMO_HSS, hss)
+    cfg = Config({
+        "restraints": {"Hi-C": {"input_matrix": H.DEMO_HCS, "intra_sigma_list": [0.2, 0.1],
+                                "inter_sigma_list": [0.2, 0.1], "contact_range": 2.0,
+                                "tmp_dir": "actdist", "keep_temporary_files": True,
+                                "gpu_shards": 2, "write_text_tmp": True}},
+        "optimization": {"structure_output": hss, "iter_corr_knob": 1},
+        "parameters": {"workdir": str(tmp_path), "tmp_dir": str(tmp_path / "tmp")},
+        "runtime": {"Hi-C": {}}})
+    pop = Population.from_hss(hss)
+    pm = ProbMatrix.from_hcs(H.DEMO_HCS)
+    plast_file = None
+    for sigma in (0.2, 0.1):
+        step = ActivationDistanceStep(cfg)
+        assert cfg.get("runtime/Hi-C/inter_sigma") == sigma
+        step.run()
+        out = cfg["runtime"]["Hi-C"]["actdist_file"]
+        # oracle for the same iteration (float32 sigma compare, it_corr = 1, plast from the previous file)
+        from igm_b200.steps.ActivationDistanceStep import lookup_plast
+        ii, jj, pw = filter_candidates(pm, sigma, sigma)
+        pl = lookup_plast(plast_file, pm.n, ii, jj) if plast_file else np.zeros(len(ii))
+        recs, _ = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                pop.copy_index, 1, 2.0, orc.MODE_LB)
+        row, col, dist, prob = orc.records_to_arrays(recs)
+        with hdf5.open_h5(out) as f:
+            assert np.array_equal(f["row"][()], row) and np.array_equal(f["col"][()], col)
+            assert np.array_equal(f["dist"][()].view(np.uint32), dist.view(np.uint32))
+            assert np.array_equal(f["prob"][()].view(np.uint32), prob.view(np.uint32))
+        # the reference's text wire format, byte for byte (two shards concatenated)
+        text = "\n".join(open(os.path.join(step.tmp_dir, "%d.out.tmp" % b)).read() for b in range(2))
+        assert hashlib.sha256(text.encode()).hexdigest() == hashlib.sha256(orc.task_text(recs).encode()).hexdigest()
+        # genfromtxt on that text gives the stored columns (what the reference's reduce would store)
+        g = np.genfromtxt(os.path.join(step.tmp_dir, "0.out.tmp"), dtype=orc.ACTDIST_SHAPE)
+        with hdf5.open_h5(out) as f:
+            assert np.array_equal(g["dist"], f["dist"][()][:len(g)])
+            assert np.array_equal(g["prob"], f["prob"][()][:len(g)])
+        # keep a copy as "previous iteration" (reduce moves the old file to the swap name)
+        plast_file = str(tmp_path / ("prev_%g.hdf5" % sigma))
+        shutil.copyfile(out, plast_file)
+        # next A-step: the runtime sigma is consumed by the driver (bin/igm-run:175-305)
+        del cfg["runtime"]["Hi-C"]["inter_sigma"], cfg["runtime"]["Hi-C"]["intra_sigma"]
+        cfg["runtime"].pop("current_iteration_name", None)

@@ -1,0 +1,150 @@
+"""Host logic of the ActivationDistanceStep drop-in (no GPU): candidate filter,
+plast lookup, file formats and naming, against restatements of the reference
+lines (igm/steps/ActivationDistanceStep.py:111-194, 234-309)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+from igm_b200 import hdf5, synthetic
+from igm_b200.population import ProbMatrix
+from igm_b200.steps import ActivationDistanceStep as S
+from igm_b200.steps._compat import Config
+from oracle import actdist_oracle as orc
+from tests import helpers as H
+
+
+def _small_matrix(seed=0):
+    bins = synthetic.genome_bins(2_000_000, 0.05)
+    chrom_hap, _, _, _ = synthetic.build_index(bins)
+    return synthetic.make_prob_matrix(chrom_hap, seed=seed, inter_per_row=20.0)
+
+
+def test_filter_candidates_matches_reference_loop():
+    pm = _small_matrix()
+    # literal restatement of the setup loop, :166-178
+    rows = pm.rows()
+    keep_i, keep_j, keep_p = [], [], []
+    intra_sigma, inter_sigma = 0.05, 0.02
+    for i, j, pwish in zip(rows, pm.indices, pm.data):        # coo_generator order
+        keep1 = (intra_sigma is not False) and (pm.chrom[i] == pm.chrom[j]) and (pwish >= intra_sigma)
+        keep2 = (inter_sigma is not False) and (pm.chrom[i] != pm.chrom[j]) and (pwish >= inter_sigma)
+        if keep1 or keep2:
+            keep_i.append(i); keep_j.append(j); keep_p.append(pwish)
+    ii, jj, pw = S.filter_candidates(pm, intra_sigma, inter_sigma)
+    assert np.array_equal(ii, np.array(keep_i, np.int32))
+    assert np.array_equal(jj, np.array(keep_j, np.int32))
+    assert np.array_equal(pw, np.array(keep_p, np.float64))
+    # and the oracle's vectorised form
+    oi, oj, op = orc.select_candidates(pm.indptr, pm.indices, pm.data, pm.chrom, intra_sigma, inter_sigma)
+    assert np.array_equal(ii, oi) and np.array_equal(jj, oj) and np.array_equal(pw, op)
+    # one of the two lists switched off
+    ii2, jj2, _ = S.filter_candidates(pm, 0.05, False)
+    assert len(ii2) and np.all(pm.chrom[ii2] == pm.chrom[jj2])
+
+
+@pytest.mark.skipif(not H.have_demo(), reason="oracle/_ref/demo not present")
+def test_filter_on_demo_matrix_float32_edge():
+    pm = ProbMatrix.from_hcs(H.DEMO_HCS)
+    s = H.demo_full_summary()["sigmas"]
+    for sig in ("1", "0.2", "0.1", "0.05", "0.02", "0.01"):
+        ii, jj, pw = S.filter_candidates(pm, float(sig), float(sig))          # float32 compare
+        assert len(ii) == s[sig]["pairs_f32_compare"]
+        ii, jj, pw = S.filter_candidates(pm, float(sig), float(sig), np.float64)
+        assert len(ii) == s[sig]["pairs_f64_compare"]
+
+
+def test_lookup_plast_matches_coo_lil(tmp_path):
+    rng = np.random.default_rng(3)
+    n = 50
+    # a previous actdist file: bead-index records, some with row/col >= n
+    row = rng.integers(0, 2 * n, 400).astype(np.int32)
+    col = rng.integers(0, 2 * n, 400).astype(np.int32)
+    key = row.astype(np.int64) * 4 * n + col
+    _, first = np.unique(key, return_index=True)
+    row, col = row[first], col[first]
+    prob = orc.text_roundtrip(rng.uniform(0, 1, len(row)))
+    f = str(tmp_path / "actdist.hdf5")
+    hdf5.write_h5(f, {"row": row, "col": col, "dist": np.zeros(len(row), np.float32), "prob": prob})
+    # reference lines :145-156
+    m = np.logical_and(row < n, col < n)
+    plast = scipy.sparse.coo_matrix((prob[m], (row[m], col[m])), shape=(n, n)).tolil()
+    ii = rng.integers(0, n, 300).astype(np.int32)
+    jj = rng.integers(0, n, 300).astype(np.int32)
+    exp = np.array([plast[a, b] for a, b in zip(ii, jj)], dtype=np.float64)
+    got = S.lookup_plast(f, n, ii, jj)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(S.lookup_plast(None, n, ii, jj), np.zeros(300))
+
+
+def _cfg(tmp_path, hcs, hss, **hic):
+    d = {"restraints": {"Hi-C": dict({"input_matrix": hcs, "intra_sigma_list": [0.2, 0.05],
+                                      "inter_sigma_list": [0.2, 0.05], "contact_range": 2.0,
+                                      "tmp_dir": "actdist", "keep_temporary_files": False}, **hic)},
+         "optimization": {"structure_output": hss, "iter_corr_knob": 0},
+         "parameters": {"workdir": str(tmp_path), "tmp_dir": str(tmp_path / "tmp")},
+         "runtime": {"Hi-C": {}}}
+    return Config(d)
+
+
+def test_step_bookkeeping_name_setup_reduce_skip(tmp_path):
+    pm = _small_matrix(1)
+    hcs = str(tmp_path / "m.hcs")
+    pm.save_hcs(hcs)
+    cfg = _cfg(tmp_path, hcs, "unused.hss", gpu_shards=3)
+    cfg["runtime"]["opt_iter"] = 2
+    step = S.ActivationDistanceStep(cfg)
+    # sigma lists are consumed exactly as the reference does (:69-98)
+    assert cfg.get("runtime/Hi-C/inter_sigma") == 0.2 and cfg.get("runtime/Hi-C/inter_sigma_list") == [0.05]
+    assert step.name() == "ActivationDistanceStep (INTER sigma=20.00%, INTRA sigma=20.00%, iter=2)"
+    step.setup()
+    assert list(step.argument_list) == [0, 1, 2]
+    assert step.tmp_extensions == [".npy", ".tmp"]
+    parts = [np.load(os.path.join(step.tmp_dir, "%d.in.npy" % b)) for b in range(3)]
+    allp = np.concatenate(parts)
+    ii, jj, pw = S.filter_candidates(pm, 0.2, 0.2)
+    assert allp.dtype == np.float64 and allp.shape == (len(ii), 4)     # (i, j, pwish, plast) as float64
+    assert np.array_equal(allp[:, 0], ii) and np.array_equal(allp[:, 2], pw)
+    # reduce: concatenation, dtypes, swap-file naming (:260-298)
+    rng = np.random.default_rng(0)
+    exp = []
+    for b in range(3):
+        rec = np.zeros(5 + b, dtype=S.actdist_shape)
+        rec["row"] = rng.integers(0, 99, len(rec)); rec["col"] = rng.integers(0, 99, len(rec))
+        rec["dist"] = rng.random(len(rec)); rec["prob"] = rng.random(len(rec))
+        np.save(os.path.join(step.tmp_dir, "%d.out.npy" % b), rec)
+        exp.append(rec)
+    exp = np.concatenate(exp)
+    old = os.path.join(step.tmp_dir, "actdist.hdf5")
+    hdf5.write_h5(old, {"row": np.zeros(1, np.int32), "col": np.zeros(1, np.int32),
+                        "dist": np.zeros(1, np.float32), "prob": np.zeros(1, np.float32)})
+    cfg["runtime"]["Hi-C"]["actdist_file"] = old
+    step.reduce()
+    assert cfg["runtime"]["Hi-C"]["actdist_file"] == old
+    assert os.path.exists(old + ".INTERsigma_0.2000.INTRAsigma_0.2000.iter_1")
+    with hdf5.open_h5(old) as f:
+        assert f["row"].dtype == np.int32 and f["dist"].dtype == np.float32
+        for k in ("row", "col", "dist", "prob"):
+            assert np.array_equal(f[k][()], exp[k])
+    step.cleanup()
+    assert not [x for x in os.listdir(step.tmp_dir) if x.endswith(".npy")]
+    cfg2 = _cfg(tmp_path, hcs, "unused.hss")
+    s2 = S.ActivationDistanceStep(cfg2)
+    s2.skip()
+    assert cfg2["runtime"]["Hi-C"]["actdist_file"] == old
+
+
+def test_hdf5_writer_roundtrip_and_layout(tmp_path):
+    f = str(tmp_path / "t.h5")
+    a = {"row": np.arange(10, dtype=np.int32), "g/x": np.linspace(0, 1, 7).astype(np.float32),
+         "g/y": np.arange(6, dtype=np.int64).reshape(2, 3), "empty": np.zeros(0, np.float32)}
+    hdf5.write_h5(f, a, attrs={"nbead": np.int64(3), "version": np.int32(2)})
+    with hdf5.open_h5(f) as h:
+        assert set(h.keys()) == {"row", "g", "empty"}
+        assert np.array_equal(h["row"][()], a["row"])
+        assert np.array_equal(h["g"]["y"][()], a["g/y"]) and h["g"]["x"].dtype == np.float32
+        assert h["empty"][()].shape == (0,)
+        assert h.attrs["nbead"] == 3
+    raw = open(f, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0     # classic superblock v0
