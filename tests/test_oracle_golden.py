@@ -88,3 +88,41 @@ def test_text_roundtrip_quirks():
     assert orc.text_roundtrip([0.00004])[0] == np.float32(0.0)
     assert orc.text_roundtrip([0.03125])[0] == np.float32(0.0312)   # exact tie -> half-even
     assert orc.text_roundtrip([1123.12044])[0] == np.float32(1123.1204)
+
+
+@pytest.mark.parametrize("case", [c[0] for c in H.all_small_cases()])
+def test_c_oracle_matches_numpy_oracle_and_golden(case):
+    """oracle/actdist_oracle.c (plain C restatement) against the NumPy oracle,
+    itself pinned to the reference's golden vectors above."""
+    from oracle import c_oracle
+    if not c_oracle.available():
+        pytest.skip("run `make -C oracle`")
+    name, npz, prefix = [c for c in H.all_small_cases() if c[0] == case][0]
+    pop, ii, jj, pw, pl = H.load_case(npz, prefix)
+    for mode in ("lb", "gp"):
+        for it_corr in (0, 1):
+            _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, it_corr, 2.0, MODES[mode])
+            exp = orc.details_to_arrays(dets)
+            got = c_oracle.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                     pop.copy_index.ptr, pop.copy_index.beads, it_corr, 2.0, MODES[mode])
+            for k in ("contact_count", "o", "nrec"):
+                assert np.array_equal(got[k], exp[k]), (mode, it_corr, k)
+            assert np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))
+            sel = exp["o"] >= 0
+            assert np.array_equal(got["d2_sel_bits"][sel], exp["d2_sel_bits"][sel])
+            g = H.golden_out(npz, prefix, mode, it_corr)
+            assert np.array_equal(got["nrec"], g["nrec"])
+
+
+def test_c_contact_oracle_matches_numpy():
+    from oracle import c_oracle, contact_oracle as co
+    if not c_oracle.available():
+        pytest.skip("run `make -C oracle`")
+    d = np.load(os.path.join(H.GOLDEN, "demo_subset.npz"))
+    pop, *_ = H.load_case(d, "demo")
+    rows, cols = np.arange(0, 40), np.arange(20, 70)
+    for strict in (False, True):
+        a = co.contact_counts_fast(pop.coordinates, pop.radii, rows, cols, 2.0, strict)
+        b = c_oracle.contact_counts(pop.coordinates, pop.radii, rows, cols, 2.0, strict)
+        assert np.array_equal(a, b)
