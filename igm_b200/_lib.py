@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libigmk.so")
+LIB_PATH = os.environ.get("IGMK_LIB_PATH") or os.path.join(HERE, "libigmk.so")
 
 IGMK_OK, IGMK_EINVAL, IGMK_ECUDA, IGMK_ESTATE, IGMK_ELIMIT = 0, -1, -2, -3, -4
 MODE_LB, MODE_GP = 0, 1

@@ -58,7 +58,9 @@ struct igmk_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
-    int block_v_override = 0;
+    int group_threads = 0;       // IGMK_GROUP_THREADS
+    int warps_per_cta = 0;       // IGMK_WARPS_PER_CTA
+    int prefetch = 0;            // IGMK_PREFETCH
 };
 
 static int ensure(void** p, size_t* cap, size_t bytes) {
@@ -102,8 +104,12 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
-    const char* ov = getenv("IGMK_BLOCK_V");
-    if (ov) c->block_v_override = atoi(ov);
+    const char* ov = getenv("IGMK_GROUP_THREADS");
+    if (ov) c->group_threads = atoi(ov);
+    ov = getenv("IGMK_PREFETCH");
+    if (ov) c->prefetch = atoi(ov);
+    ov = getenv("IGMK_WARPS_PER_CTA");
+    if (ov) c->warps_per_cta = atoi(ov);
     *out = c;
     return IGMK_OK;
 }
@@ -203,33 +209,40 @@ static int launch_finish(const ActdistParams& P, cudaStream_t st) {
     return IGMK_OK;
 }
 
-template <int V>
 static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
+    const int V = (c->nchunks + 31) / 32;
+    // one CTA per SM; as many warps as the key arrays (V KiB per warp) leave room for
+    int warps = (int)((200 * 1024) / ((size_t)2 * V * 32 * 16));
+    if (warps > kWarpsPerBlock) warps = kWarpsPerBlock;
+    if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
+    if (warps < 1) return fail(IGMK_ELIMIT, "actdist_warp_kernel: nstruct = %d is too large for one warp per pair", c->nstruct);
     int per_sm = 0;
-    const size_t smem = (size_t)kWarpsPerBlock * 2 * V * 32 * 16;
-    CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel<V>,
-                                                           32 * kWarpsPerBlock, smem));
-    if (per_sm < 1) per_sm = 1;
-    long long want = (P.n_pairs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const size_t smem = (size_t)warps * 2 * V * 32 * 16;
+    CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel, 32 * warps, smem));
+    if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_warp_kernel cannot run with V = %d", V);
+    long long want = (P.n_pairs + warps - 1) / warps;
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((want < cap) ? want : cap);
-    actdist_warp_kernel<V><<<grid, 32 * kWarpsPerBlock, smem, st>>>(P);
+    actdist_warp_kernel<<<grid, 32 * warps, smem, st>>>(P, V);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
 }
 
-template <int V, int MAXT, int MINB>
+template <int MAXT>
 static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, cudaStream_t st) {
+    const int V = (c->nchunks + threads - 1) / threads;
     int per_sm = 0;
     const size_t smem = (size_t)2 * V * threads * 16;
-    CUDA_TRY(cudaFuncSetAttribute(actdist_block_kernel<V, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<V, MAXT, MINB>, threads, smem));
-    if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_block_kernel<%d> cannot run with %d threads", V, threads);
+    if (2 * V > kMaxQuads || smem > 200 * 1024)
+        return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 25600", c->nstruct);
+    CUDA_TRY(cudaFuncSetAttribute(actdist_block_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<MAXT>, threads, smem));
+    if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_block_kernel cannot run with %d threads, V = %d", threads, V);
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
-    actdist_block_kernel<V, MAXT, MINB><<<grid, threads, smem, st>>>(P);
+    actdist_block_kernel<MAXT><<<grid, threads, smem, st>>>(P, V);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
@@ -268,38 +281,34 @@ extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
     P.pi = d_i; P.pj = d_j; P.pwish = d_pwish; P.plast = d_plast; P.out = d_out;
     P.n_pairs = n_pairs; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
     P.n_hap = c->n_hap; P.contact_range = contact_range; P.it_corr = it_corr; P.mode = mode;
+    P.negzero2 = 0x8000000080000000ull;
+    P.prefetch = c->prefetch;
 
     if (algo == IGMK_ALGO_SIMPLE) return launch_simple(c, P, st);
     if (algo != IGMK_ALGO_FAST) return fail(IGMK_EINVAL, "igmk_actdist: bad algo %d", algo);
 
-    // Thread-group shape: V float4 chunks (16 structures x <= 4 combinations) per thread.
-    //   nstruct <= 512: one warp per pair, V = ceil(nchunks / 32) <= 4
-    //   larger:         one CTA per pair, V = 4, T = ceil(nchunks / 4) rounded up to a warp
-    // IGMK_BLOCK_V (tuning knob): 0 = default, 1 = force one warp per pair,
-    // 3 = CTA-per-pair compiled for <= 85 registers instead of <= 64.
-    const int knob = c->block_v_override;
-    const bool warp_ok = c->nchunks <= 32 * 8;
-    if (warp_ok && (knob == 1 || (knob == 0 && c->nchunks <= 32 * 4))) {
-        const int V = (c->nchunks + 31) / 32;
-        switch (V) {
-            case 1: return launch_warp<1>(c, P, st);
-            case 2: return launch_warp<2>(c, P, st);
-            case 3: return launch_warp<3>(c, P, st);
-            case 4: return launch_warp<4>(c, P, st);
-            case 5: return launch_warp<5>(c, P, st);
-            case 6: return launch_warp<6>(c, P, st);
-            case 7: return launch_warp<7>(c, P, st);
-            default: return launch_warp<8>(c, P, st);
+    // Thread-group shape (igmk_actdist.cuh): V float4 chunks (4 structures x <= 4
+    // combinations each) per thread.
+    //   nstruct <= 1024: one warp per pair, V = ceil(nchunks / 32) <= 8
+    //   larger:          one CTA per pair, T <= 320 threads with V = ceil(nchunks / T) about 8
+    //                    (T = 512 beyond nstruct = 15360)
+    // IGMK_GROUP_THREADS (tuning knob): 0 = default, 32 = force one warp per pair
+    // (nstruct <= 4096), otherwise the CTA size to use.
+    int T = c->group_threads;
+    if (T == 0) {
+        if (c->nchunks <= 32 * 8) T = 32;
+        else {
+            T = ((c->nchunks + 7) / 8 + 31) / 32 * 32;          // about 8 chunks per thread
+            if (T < 64) T = 64;
+            if (T > 320) T = ((c->nchunks + 319) / 320 <= 12) ? 320 : 512;
         }
     }
-    int T = ((c->nchunks + 3) / 4 + 31) / 32 * 32;
-    if (T < 32) T = 32;
-    if (T > 768) return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 12288", c->nstruct);
-    if (T <= 128) {
-        if (knob == 3) return launch_block<4, 128, 6>(c, P, T, st);
-        return launch_block<4, 128, 8>(c, P, T, st);      // 64 registers: 16 CTAs x 2 warps per SM
-    }
-    return launch_block<4, 768, 1>(c, P, T, st);
+    if (T == 32 && c->nchunks <= 32 * 32) return launch_warp(c, P, st);
+    if (T < 64) T = 64;
+    if (T > 512) T = 512;
+    T = (T + 31) / 32 * 32;
+    if (T <= 320) return launch_block<320>(c, P, T, st);
+    return launch_block<512>(c, P, T, st);
 }
 
 extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,

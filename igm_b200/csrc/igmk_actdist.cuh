@@ -4,81 +4,136 @@
 // (igm/steps/ActivationDistanceStep.py:405-473; GP flavour
 // igm/steps/GP_activation.py:367-424).
 //
-// Fast kernel, per candidate pair handled by a group of G threads
-// (G = 32: one warp per pair for nstruct <= 512; G = blockDim for larger
-// populations, 64 threads at nstruct = 1000, 640 at 10 000):
-//   1. every thread streams V <= 4 float4 chunks (4 structures each) of the
-//      <= 4 bead rows with 128-bit loads, computes the copy-combination d2
-//      values in registers (non-FMA float32, bit-identical to NumPy), counts
+// Each candidate pair is owned by a group of G threads (G = 32: one warp per
+// pair, no barriers at all, for nstruct <= 1024; G = one CTA of up to 512
+// threads for larger populations, two CTAs resident per SM so that one pair's
+// memory phase overlaps the other's select phase):
+//   1. fill: every thread streams its float4 chunks (4 structures each) of the
+//      <= 4 bead rows with 128-bit loads and computes the copy-combination d2
+//      values with PACKED float32x2 arithmetic (FADD2 / FFMA2: two structures
+//      per instruction, sequentially rounded - bit-identical to NumPy), counts
 //      d2 <= rcutsq, and keeps only the HIGH 16 BITS of each kept d2, two per
-//      register (bf16x2).  d2 >= 0, so bf16 order == float order.
+//      word (bf16x2), parked in the group's shared-memory key array.
+//      d2 >= 0, so bf16 order == float order.
 //   2. p and the order-statistic index o are evaluated in float64.
-//   3. the o-th smallest value is located by bisection on the 16-bit key
-//      interval [kmin, kmax]: one packed compare + one packed add per TWO
-//      elements per pass, one group reduction per pass, until <= 32 candidates
-//      remain (or the interval is a single key).
-//   4. the few candidates are re-materialised in full float32 precision from
-//      the coordinates and ranked exactly inside one warp.
-//   No sort, no shared-memory histogram, no atomics in the main loop.
+//   3. select: bisection on the 16-bit key interval [kmin, kmax]; a pass streams
+//      the keys back from shared memory (LDS.128 = 8 keys) with one packed
+//      compare + one packed add per TWO elements and one group reduction,
+//      until <= 32 candidates remain or the interval is a single key.
+//   4. finish: the locations of the candidates are compacted into a short list,
+//      re-materialised in full float32 from the coordinates by the whole group
+//      in parallel, and ranked exactly by one warp.  The selected value is an
+//      actual element, bit-exact.
+//   No sort, no shared-memory histogram, no atomics in the main loops.
 #pragma once
 #include "igmk_device.cuh"
 
 namespace igmk {
 
-constexpr int kCandCap = 32;
+constexpr int kRankCap = 32;        // bisection stops at <= kRankCap candidates
+constexpr int kWarpListCap = 64;    // candidate list words per warp group
+constexpr int kBlockListCap = 1024; // candidate list words per CTA group
+constexpr int kMaxQuads = 64;       // key quads per thread: bf16 pass counters stay exact
+
+// ----------------------------------------------------------- packed float32x2
+__device__ __forceinline__ u64 f2sub(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 f2add(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// rn(a * a) per half.  Written as fma(a, a, -0.0) with the -0.0 pair coming from
+// a kernel parameter: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even under --fmad=false, which would break the sequential rounding
+// NumPy performs; an FMA whose addend is opaque cannot be contracted further,
+// and x*x + (-0.0) rounds exactly like x*x.
+__device__ __forceinline__ u64 f2sq(u64 a, u64 negzero2) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(negzero2));
+    return r;
+}
+// a <= b ? 1.0f : 0.0f  (FSET.BF; NaN compares false)
+__device__ __forceinline__ float f_le_one(float a, float b) {
+    float r;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ u64 f2pack(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2split(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// x / y / z of 4 consecutive structures as packed pairs (s0,s1) (s2,s3)
+struct Row6 { u64 x01, x23, y01, y23, z01, z23; };
+
+__device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b) {
+#ifdef IGMK_LDG_NOALLOC
+    asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+#else
+    asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+#endif
+}
+__device__ __forceinline__ Row6 load_row6(const float* p) {
+    Row6 r;
+    ldg_v2b64(p, r.x01, r.x23);
+    ldg_v2b64(p + kSeg, r.y01, r.y23);
+    ldg_v2b64(p + 2 * kSeg, r.z01, r.z23);
+    return r;
+}
+// d2 of structures (4c+2h, 4c+2h+1), h = 0 / 1
+template <int H>
+__device__ __forceinline__ u64 d2pair(const Row6& a, const Row6& b, u64 nz) {
+    const u64 dx = f2sub(H ? a.x23 : a.x01, H ? b.x23 : b.x01);
+    const u64 dy = f2sub(H ? a.y23 : a.y01, H ? b.y23 : b.y01);
+    const u64 dz = f2sub(H ? a.z23 : a.z01, H ? b.z23 : b.z01);
+    return f2add(f2add(f2sq(dx, nz), f2sq(dy, nz)), f2sq(dz, nz));
+}
 
 // ------------------------------------------------------------------ groups
 // Shared scratch is addressed through 32-bit shared-window addresses.
-struct WarpGroup {
-    int tid;            // lane
-    int nthr;           // 32
-    uint32_t cand;      // shared address of kCandCap words (per warp)
-    uint32_t cand_cnt;  // shared address of the candidate counter (per warp)
-    uint32_t kscr;      // shared address of this thread's key scratch column
-    uint32_t kstride;   // bytes between consecutive key quads of one thread
-
-    __device__ __forceinline__ int sum(int x) { return __reduce_add_sync(0xffffffffu, x); }
-    __device__ __forceinline__ void sum_min_max(int& s, uint32_t& mn, uint32_t& mx) {
-        s = __reduce_add_sync(0xffffffffu, s);
-        mn = __reduce_min_sync(0xffffffffu, mn);
-        mx = __reduce_max_sync(0xffffffffu, mx);
-    }
-    __device__ __forceinline__ void sync() { __syncwarp(); }
-    __device__ __forceinline__ bool leader_warp() const { return true; }
-};
-
-struct BlockGroup {
-    int tid;
-    int nthr;
-    uint32_t cand;
-    uint32_t cand_cnt;
-    uint32_t kscr;
-    uint32_t kstride;
-    uint32_t red;       // shared address of [2][3][32] words
+template <bool BLOCK>
+struct Group {
+    int tid;            // thread index inside the group
+    int nthr;           // group size (multiple of 32)
+    uint32_t kscr;      // this thread's first key quad
+    uint32_t kstride;   // bytes between consecutive quads of one thread (nthr * 16)
+    uint32_t list;      // candidate list (codes, then values)
+    uint32_t ctl;       // candidate counter
+    int cap;            // list capacity
+    uint32_t red;       // BLOCK: [2][3][32] words
     int parity;
 
     __device__ __forceinline__ int sum(int x) {
+        if (!BLOCK) return __reduce_add_sync(0xffffffffu, x);
         const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
         const uint32_t r = red + parity * 384;
         parity ^= 1;
         const int w = __reduce_add_sync(0xffffffffu, x);
         if (lane == 0) sts32(r + warp * 4, (uint32_t)w);
         __syncthreads();
-        if (nw == 2) return w + (int)lds32(r + (warp ^ 1) * 4);
         const int v = (lane < nw) ? (int)lds32(r + lane * 4) : 0;
         return __reduce_add_sync(0xffffffffu, v);
     }
     __device__ __forceinline__ void sum_min_max(int& s, uint32_t& mn, uint32_t& mx) {
+        s = __reduce_add_sync(0xffffffffu, s);
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (!BLOCK) return;
         const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
         const uint32_t r = red + parity * 384;
         parity ^= 1;
-        const int ws = __reduce_add_sync(0xffffffffu, s);
-        const uint32_t wmn = __reduce_min_sync(0xffffffffu, mn);
-        const uint32_t wmx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) {
-            sts32(r + warp * 4, (uint32_t)ws);
-            sts32(r + 128 + warp * 4, wmn);
-            sts32(r + 256 + warp * 4, wmx);
+            sts32(r + warp * 4, (uint32_t)s);
+            sts32(r + 128 + warp * 4, mn);
+            sts32(r + 256 + warp * 4, mx);
         }
         __syncthreads();
         const int vs = (lane < nw) ? (int)lds32(r + lane * 4) : 0;
@@ -88,13 +143,18 @@ struct BlockGroup {
         mn = __reduce_min_sync(0xffffffffu, vmn);
         mx = __reduce_max_sync(0xffffffffu, vmx);
     }
-    __device__ __forceinline__ void sync() { __syncthreads(); }
-    __device__ __forceinline__ bool leader_warp() const { return tid < 32; }
+    __device__ __forceinline__ void sync() {
+        if (BLOCK) __syncthreads(); else __syncwarp();
+    }
+    __device__ __forceinline__ bool leader_warp() const { return !BLOCK || tid < 32; }
 };
 
 // --------------------------------------------------------- stage 1: fill keys
-// keys[v][slot][qh]: low half = structure 4c + 2qh, high half = 4c + 2qh + 1 of
-// chunk c = tid + v * nthr; NaN pattern (0x7fff) for everything not kept.
+// Key quad q = v * NH + h of a thread (v: chunk index c = tid + v * nthr, h: slot
+// pair) = { key(slot 2h, s0) | key(slot 2h, s1) << 16, (slot 2h: s2, s3),
+//           (slot 2h+1: s0, s1), (slot 2h+1: s2, s3) },  s = structures 4c..4c+3;
+// NaN pattern (0x7fff) for everything not kept.  NH = 2 when 4 values per
+// structure are kept, else 1.
 //
 // Pair shapes (uniform over the group) get their own straight-line code:
 //   SH_FULL4   LB, both loci diploid, inter-chromosomal: 4 combinations kept
@@ -111,26 +171,6 @@ __device__ __forceinline__ int pair_shape(const PairDesc& d, int mode) {
     return SH_GENERIC;
 }
 
-struct Row3 { float4 x, y, z; };
-
-// x / y / z of 4 consecutive structures: three 128-bit loads at constant offsets
-__device__ __forceinline__ Row3 load_row3(const float* p) {
-    Row3 r;
-    r.x = __ldg(reinterpret_cast<const float4*>(p));
-    r.y = __ldg(reinterpret_cast<const float4*>(p + kSeg));
-    r.z = __ldg(reinterpret_cast<const float4*>(p + 2 * kSeg));
-    return r;
-}
-
-__device__ __forceinline__ float f4get(const float4& v, int q) {
-    return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w;
-}
-
-__device__ __forceinline__ float d2q(const Row3& a, const Row3& b, int q) {
-    return d2_nofma(f4get(a.x, q), f4get(a.y, q), f4get(a.z, q),
-                    f4get(b.x, q), f4get(b.y, q), f4get(b.z, q));
-}
-
 struct PairPtrs { const float *A0, *A1, *B0, *B1; };
 
 __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const PairDesc& d) {
@@ -143,13 +183,15 @@ __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const Pair
     return pp;
 }
 
-template <int V, int SH>
+template <int SH>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
-                                          const PairPtrs& pp, int tid, int nthr,
-                                          uint32_t kscr, uint32_t kstride, int& cnt) {
+                                          const PairPtrs& pp, int tid, int nthr, int V,
+                                          uint32_t kscr, uint32_t kstride,
+                                          int& cnt, uint32_t& mn2, uint32_t& mx2) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
     const float rc = d.rcutsq;
+    const u64 nz = P.negzero2;
     // chunk c = tid + v * nthr lives in segment c >> 5 at lane offset (c & 31) * 4;
     // nthr is a multiple of 32, so only the segment advances with v.
     const size_t off0 = (size_t)(tid >> 5) * kSegFloats + (size_t)(tid & 31) * 4;
@@ -158,49 +200,66 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
     const float* pb0 = pp.B0 + off0;
     const float* pa1 = pp.A1 + off0;
     const float* pb1 = pp.B1 + off0;
-    int c_local = 0;
+    u64 c_local = 0ull;            // {count of even, count of odd structures} as floats
+    uint32_t lmn = 0x7fff7fffu, lmx = 0x7fff7fffu;
+    // in generic pairs only NH is not known at compile time
+    const int nh = (NS == 4) ? ((d.keep > 2) ? 2 : 1) : 1;
+    uint32_t dst = kscr;
 
     // The chunk loop is deliberately NOT unrolled (instruction-cache footprint and
-    // register pressure: 48 registers of loaded coordinates are live here).  The
-    // packed keys of each chunk are parked in this thread's private column of
-    // shared memory (indexable, unlike registers) and pulled back into registers
-    // once after the loop, for the bisection passes.
+    // register pressure: 48 registers of loaded coordinates are live here).
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
         const int c = tid + v * nthr;
         uint32_t nk[NS][2];
-        if (c < P.nchunks) {
-            const Row3 a0 = load_row3(pa0);
-            const Row3 b0 = load_row3(pb0);
-            const Row3 a1 = load_row3(pa1);
-            const Row3 b1 = load_row3(pb1);
+        if (c >= P.nchunks) {              // padding chunk: NaN keys, nothing to load
+            sts128(dst, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
+            if (NS == 4) {
+                if (SH == SH_FULL4 || nh == 2) sts128(dst + kstride, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
+            }
+            dst += (uint32_t)nh * kstride;
+            continue;                      // (pointers are not used again: c only grows)
+        }
+        {
             float s[4][NS];   // [q][slot]
+            if (SH == SH_INTRA2) {
+                const Row6 a0 = load_row6(pa0), b0 = load_row6(pb0);
+                const Row6 a1 = load_row6(pa1), b1 = load_row6(pb1);
+                f2split(d2pair<0>(a0, b0, nz), s[0][0], s[1][0]);
+                f2split(d2pair<1>(a0, b0, nz), s[2][0], s[3][0]);
+                f2split(d2pair<0>(a1, b1, nz), s[0][1], s[1][1]);
+                f2split(d2pair<1>(a1, b1, nz), s[2][1], s[3][1]);
+            } else {
+                const Row6 a0 = load_row6(pa0), b0 = load_row6(pb0);
+                const Row6 a1 = load_row6(pa1), b1 = load_row6(pb1);
+                float e[4][4];   // [q][combination d0..d3]
+                f2split(d2pair<0>(a0, b0, nz), e[0][0], e[1][0]);
+                f2split(d2pair<1>(a0, b0, nz), e[2][0], e[3][0]);
+                f2split(d2pair<0>(a0, b1, nz), e[0][1], e[1][1]);
+                f2split(d2pair<1>(a0, b1, nz), e[2][1], e[3][1]);
+                f2split(d2pair<0>(a1, b0, nz), e[0][2], e[1][2]);
+                f2split(d2pair<1>(a1, b0, nz), e[2][2], e[3][2]);
+                f2split(d2pair<0>(a1, b1, nz), e[0][3], e[1][3]);
+                f2split(d2pair<1>(a1, b1, nz), e[2][3], e[3][3]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (SH == SH_FULL4) {
-                    s[q][0] = d2q(a0, b0, q);
-                    s[q][1] = d2q(a0, b1, q);
-                    s[q][2] = d2q(a1, b0, q);
-                    s[q][3] = d2q(a1, b1, q);
-                } else if (SH == SH_INTRA2) {
-                    s[q][0] = d2q(a0, b0, q);
-                    s[q][1] = d2q(a1, b1, q);
-                } else if (SH == SH_GP4) {
-                    const float e0 = d2q(a0, b0, q), e1 = d2q(a0, b1, q);
-                    const float e2 = d2q(a1, b0, q), e3 = d2q(a1, b1, q);
-                    const float lo1 = fminf(e0, e1), hi1 = fmaxf(e0, e1);
-                    const float lo2 = fminf(e2, e3), hi2 = fmaxf(e2, e3);
-                    s[q][0] = fminf(lo1, lo2);
-                    s[q][1] = fminf(fmaxf(lo1, lo2), fminf(hi1, hi2));
-                } else {
-                    const float e0 = d2q(a0, b0, q);
-                    const float e1 = (d.cmask & CM_D1) ? d2q(a0, b1, q) : qnan;
-                    const float e2 = (d.cmask & CM_D2) ? d2q(a1, b0, q) : qnan;
-                    const float e3 = (d.cmask & CM_D3) ? d2q(a1, b1, q) : qnan;
-                    float t[4];
-                    pack_slots(d, P.mode, e0, e1, e2, e3, t);
+                for (int q = 0; q < 4; ++q) {
+                    if (SH == SH_FULL4) {
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) s[q][k] = t[k];
+                        for (int k = 0; k < 4; ++k) s[q][k] = e[q][k];
+                    } else if (SH == SH_GP4) {
+                        const float lo1 = fminf(e[q][0], e[q][1]), hi1 = fmaxf(e[q][0], e[q][1]);
+                        const float lo2 = fminf(e[q][2], e[q][3]), hi2 = fmaxf(e[q][2], e[q][3]);
+                        s[q][0] = fminf(lo1, lo2);
+                        s[q][1] = fminf(fmaxf(lo1, lo2), fminf(hi1, hi2));
+                    } else {
+                        const float e1 = (d.cmask & CM_D1) ? e[q][1] : qnan;
+                        const float e2 = (d.cmask & CM_D2) ? e[q][2] : qnan;
+                        const float e3 = (d.cmask & CM_D3) ? e[q][3] : qnan;
+                        float t[4];
+                        pack_slots(d, P.mode, e[q][0], e1, e2, e3, t);
+#pragma unroll
+                        for (int k = 0; k < NS; ++k) s[q][k] = t[k];
+                    }
                 }
             }
             if (4 * c + 4 > P.nstruct) {        // tail chunk of the population (one thread)
@@ -211,10 +270,12 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
                         for (int k = 0; k < NS; ++k) s[q][k] = qnan;
                     }
             }
+            // contact count: 1.0 / 0.0 flags accumulated two per FADD2 (exact: < 2^24)
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4; q += 2)
 #pragma unroll
-                for (int k = 0; k < NS; ++k) c_local += (s[q][k] <= rc) ? 1 : 0;   // NaN: false
+                for (int k = 0; k < NS; ++k)
+                    c_local = f2add(c_local, f2pack(f_le_one(s[q][k], rc), f_le_one(s[q + 1][k], rc)));
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
 #pragma unroll
@@ -223,62 +284,96 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
                     nk[k][qh] = __byte_perm(__float_as_uint(s[2 * qh][k]),
                                             __float_as_uint(s[2 * qh + 1][k]), 0x7632);
                 }
+                lmn = bf2_min(lmn, bf2_min(nk[k][0], nk[k][1]));   // NaN halves are ignored
+                lmx = bf2_max(lmx, bf2_max(nk[k][0], nk[k][1]));
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NS; ++k) { nk[k][0] = 0x7fff7fffu; nk[k][1] = 0x7fff7fffu; }
         }
-        {
-            const uint32_t dst = kscr + (uint32_t)(2 * v) * kstride;
-            sts128(dst, nk[0][0], nk[0][1], nk[1][0], nk[1][1]);
-            if (NS == 4) sts128(dst + kstride, nk[2][0], nk[2][1], nk[3][0], nk[3][1]);
+        sts128(dst, nk[0][0], nk[0][1], nk[1][0], nk[1][1]);
+        if (NS == 4) {
+            if (SH == SH_FULL4 || nh == 2) sts128(dst + kstride, nk[2][0], nk[2][1], nk[3][0], nk[3][1]);
         }
+        dst += (uint32_t)nh * kstride;
         pa0 += vstride; pb0 += vstride; pa1 += vstride; pb1 += vstride;
     }
-    cnt = c_local;
+    float c_lo, c_hi;
+    f2split(c_local, c_lo, c_hi);
+    cnt = (int)(c_lo + c_hi);
+    mn2 = lmn;
+    mx2 = lmx;
 }
 
-template <int V>
-__device__ __forceinline__ int count_le(const uint32_t (&keys)[V][4][2], int keep, uint32_t piv2) {
-    uint32_t acc0 = 0u, acc1 = 0u;
+// One bisection pass over this thread's nq key quads: #{key <= pivot}.
+// set.le yields 0xffff / 0 per half; subtracting the masks as 32-bit integers
+// (two per IADD3) leaves  acc = (#hi - #lo) * 65536 + #lo.
+template <int NQ>
+__device__ __forceinline__ int count_le_fixed(uint32_t kscr, uint32_t kstride, uint32_t piv2) {
+    uint32_t a0 = 0u, a1 = 0u;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < keep) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                acc0 = bf2_add(acc0, bf2_le(keys[v][k][0], piv2));
-                acc1 = bf2_add(acc1, bf2_le(keys[v][k][1], piv2));
-            }
-        }
+    for (int q = 0; q < NQ; ++q) {
+        uint32_t k0, k1, k2, k3;
+        lds128(kscr + (uint32_t)q * kstride, k0, k1, k2, k3);
+        a0 = a0 - bf2_le_mask(k0, piv2) - bf2_le_mask(k1, piv2);
+        a1 = a1 - bf2_le_mask(k2, piv2) - bf2_le_mask(k3, piv2);
     }
-    return bf2_count_sum(acc0) + bf2_count_sum(acc1);
+    const uint32_t acc = a0 + a1;
+    return ((int)acc >> 16) + 2 * (int)(acc & 0xffffu);
+}
+__device__ __forceinline__ int count_le(uint32_t kscr, uint32_t kstride, int nq, uint32_t piv2) {
+    if (nq == 8) return count_le_fixed<8>(kscr, kstride, piv2);      // nstruct in (896, 1024], 1-2 kept
+    if (nq == 16) return count_le_fixed<16>(kscr, kstride, piv2);    // same, 4 kept
+    uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll 4
+    for (int q = 0; q < nq; ++q) {
+        uint32_t k0, k1, k2, k3;
+        lds128(kscr + (uint32_t)q * kstride, k0, k1, k2, k3);
+        a0 = a0 - bf2_le_mask(k0, piv2) - bf2_le_mask(k1, piv2);
+        a1 = a1 - bf2_le_mask(k2, piv2) - bf2_le_mask(k3, piv2);
+    }
+    const uint32_t acc = a0 + a1;
+    return ((int)acc >> 16) + 2 * (int)(acc & 0xffffu);
 }
 
-// Bit (r) / (16 + r) of word w <-> low / high half of register R = 16 w + r,
-// R = (v * 4 + slot) * 2 + qh.
-template <int V>
-__device__ __forceinline__ void scan_range(const uint32_t (&keys)[V][4][2], int keep,
-                                           uint32_t lo2, uint32_t hi2,
-                                           uint32_t (&bm)[(V + 1) / 2]) {
+// Calls f(e) for every element of this thread whose key lies in [lo, hi];
+// e = q * 8 + r * 2 + half  (quad q, word r, half-word).  Matches of four quads
+// are first collected in one bitmap word (bit w / 16 + w <-> low / high half of
+// word w = 4 (q - q0) + r), so the divergent part costs one trip per match, not
+// one per quad.
+template <bool EQ, class F>
+__device__ __forceinline__ void scan_range(uint32_t kscr, uint32_t kstride, int nq,
+                                           uint32_t lo2, uint32_t hi2, F&& f) {
+#pragma unroll 1
+    for (int q0 = 0; q0 < nq; q0 += 4) {
+        uint32_t bm = 0u;
 #pragma unroll
-    for (int w = 0; w < (V + 1) / 2; ++w) bm[w] = 0u;
+        for (int qq = 0; qq < 4; ++qq) {
+            if (q0 + qq < nq) {            // uniform over the group
+                uint32_t k[4];
+                lds128(kscr + (uint32_t)(q0 + qq) * kstride, k[0], k[1], k[2], k[3]);
 #pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < keep) {
-#pragma unroll
-                for (int qh = 0; qh < 2; ++qh) {
-                    const int R = (v * 4 + k) * 2 + qh;
-                    const uint32_t m = bf2_ge_mask(keys[v][k][qh], lo2) & bf2_le_mask(keys[v][k][qh], hi2);
-                    bm[R >> 4] |= m & (0x00010001u << (R & 15));
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t m = EQ ? bf2_eq_mask(k[r], lo2)
+                                          : (bf2_ge_mask(k[r], lo2) & bf2_le_mask(k[r], hi2));
+                    bm |= m & (0x00010001u << (qq * 4 + r));
                 }
             }
         }
+        while (bm) {
+            const int bit = __ffs(bm) - 1;
+            bm &= bm - 1;
+            const int w = bit & 15;
+            f((q0 + (w >> 2)) * 8 + (w & 3) * 2 + (bit >> 4));
+        }
+    }
+}
+template <class F>
+__device__ __forceinline__ void scan_range(uint32_t kscr, uint32_t kstride, int nq,
+                                           uint32_t lo2, uint32_t hi2, F&& f) {
+    if (lo2 == hi2) scan_range<true>(kscr, kstride, nq, lo2, hi2, f);
+    else            scan_range<false>(kscr, kstride, nq, lo2, hi2, f);
 }
 
 // Full float32 pattern of one kept value, re-materialised from the coordinates
-// (candidate gathering; deliberately out of line).  LB: slot -> one combination.
+// (deliberately out of line).  LB: slot -> one combination.
 __device__ __noinline__ uint32_t recompute_lb(const float* pa, const float* pb, int st) {
     return __float_as_uint(d2_scalar(pa, pb, st));
 }
@@ -298,13 +393,13 @@ __device__ __noinline__ uint32_t recompute_gp(const float* A0, const float* A1, 
     return __float_as_uint(slot == 0 ? s[0] : s[1]);
 }
 
-// element behind bit `bit` of word `w` of a scan_range bitmap
+// element e (scan_range numbering) of thread `owner`
 __device__ __forceinline__ uint32_t element_bits(const PairPtrs& pp, const PairDesc& d, int mode,
-                                                 int tid, int nthr, int w, int bit) {
-    const int R = (w << 4) | (bit & 15);
-    const int half = bit >> 4;
-    const int v = R >> 3, slot = (R >> 1) & 3, qh = R & 1;
-    const int st = 4 * (tid + v * nthr) + 2 * qh + half;
+                                                 int owner, int nthr, int nh, int e) {
+    const int q = e >> 3, r = (e >> 1) & 3, half = e & 1;
+    const int v = (nh == 2) ? (q >> 1) : q, h = (nh == 2) ? (q & 1) : 0;
+    const int slot = 2 * h + (r >> 1), qh = r & 1;
+    const int st = 4 * (owner + v * nthr) + 2 * qh + half;
     if (mode == IGMK_MODE_GP)
         return recompute_gp(pp.A0, pp.A1, pp.B0, pp.B1, d.cmask, d.keep, st, slot);
     // LB: the slot-th existing combination (enumeration order d0..d3)
@@ -314,9 +409,61 @@ __device__ __forceinline__ uint32_t element_bits(const PairPtrs& pp, const PairD
     return recompute_lb((comb & 2) ? pp.A1 : pp.A0, (comb & 1) ? pp.B1 : pp.B0, st);
 }
 
+// r-th smallest (0-based) of the n <= 32 * k list words, by one full warp.
+__device__ __forceinline__ uint32_t warp_select(uint32_t list, int n, int r, int lane) {
+    if (n <= 32) {
+        const uint32_t x = (lane < n) ? lds32(list + lane * 4) : 0xffffffffu;
+        int rank = 0;
+        for (int t = 0; t < n; ++t) {
+            const uint32_t y = __shfl_sync(0xffffffffu, x, t);
+            rank += (y < x || (y == x && t < lane)) ? 1 : 0;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, lane < n && rank == r);
+        // hit is non-empty by construction; the guard keeps a corrupted input from hanging
+        const int src = hit ? (__ffs(hit) - 1) : 0;
+        return __shfl_sync(0xffffffffu, x, src);
+    }
+    // most-significant-bit-first binary radix select over the list
+    uint32_t prefix = 0u, mask = 0u;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t b = 1u << bit;
+        int c0 = 0;
+        for (int t = lane; t < n; t += 32) {
+            const uint32_t x = lds32(list + t * 4);
+            c0 += ((x & mask) == prefix && !(x & b)) ? 1 : 0;
+        }
+        c0 = __reduce_add_sync(0xffffffffu, c0);
+        if (r >= c0) { r -= c0; prefix |= b; }
+        mask |= b;
+    }
+    return prefix;
+}
+
+// Fire-and-forget L2 prefetch of the bead rows the group's NEXT pair will
+// stream (about a third of the row sectors otherwise come from HBM with the full
+// DRAM latency exposed in the fill loop).  One 128-byte line per thread and trip.
+__device__ __forceinline__ void prefetch_rows_l2(const ActdistParams& P, long long next_pair,
+                                                 int tid, int nthr) {
+    if (next_pair >= P.n_pairs) return;
+    const int j = __ldg(P.pj + next_pair);
+    if (j < 0 || j >= P.n_hap) return;
+    const int4 hb = __ldg(reinterpret_cast<const int4*>(P.hap + j));
+    const size_t row_bytes = (size_t)12 * P.npad;
+    const int lines = (int)(row_bytes >> 7);           // npad is a multiple of 128: exact
+    const char* base = reinterpret_cast<const char*>(P.coords);
+    const char* r0 = base + (size_t)hb.x * row_bytes;
+    const char* r1 = base + (size_t)(hb.y >= 0 ? hb.y : hb.x) * row_bytes;
+    for (int l = tid; l < lines; l += nthr) {
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(r0 + ((size_t)l << 7)));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(r1 + ((size_t)l << 7)));
+    }
+}
+
 // ------------------------------------------------------------- one pair
-template <int V, class G>
-__device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long long pair) {
+template <bool BLOCK>
+__device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK>& g, int V,
+                                             long long pair, long long next_pair) {
+    if (P.prefetch) prefetch_rows_l2(P, next_pair, g.tid, g.nthr);
     const int i = __ldg(P.pi + pair), j = __ldg(P.pj + pair);
     const PairDesc d = make_pair_desc(P, i, j);
     igmk_pair_result* out = P.out + pair;
@@ -328,40 +475,22 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
     const PairPtrs pp = pair_ptrs(P, d);
 
     int cnt;
+    uint32_t mn2, mx2;
     switch (pair_shape(d, P.mode)) {       // uniform over the group
-        case SH_FULL4:  fill_keys<V, SH_FULL4>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
-        case SH_INTRA2: fill_keys<V, SH_INTRA2>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
-        case SH_GP4:    fill_keys<V, SH_GP4>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
-        default:        fill_keys<V, SH_GENERIC>(P, d, pp, g.tid, g.nthr, g.kscr, g.kstride, cnt); break;
+        case SH_FULL4:  fill_keys<SH_FULL4>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
+        case SH_INTRA2: fill_keys<SH_INTRA2>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
+        case SH_GP4:    fill_keys<SH_GP4>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
+        default:        fill_keys<SH_GENERIC>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
     }
-    // keys back into registers (each thread reads only what it wrote itself)
-    uint32_t keys[V][4][2];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        lds128(g.kscr + (uint32_t)(2 * v) * g.kstride, keys[v][0][0], keys[v][0][1], keys[v][1][0], keys[v][1][1]);
-        if (d.keep > 2)
-            lds128(g.kscr + (uint32_t)(2 * v + 1) * g.kstride, keys[v][2][0], keys[v][2][1], keys[v][3][0], keys[v][3][1]);
-        else { keys[v][2][0] = keys[v][2][1] = keys[v][3][0] = keys[v][3][1] = 0x7fff7fffu; }
-    }
+    const int nh = (d.keep > 2) ? 2 : 1;
+    const int nq = V * nh;
 
-    // per-thread key range (NaN halves are ignored by min/max.bf16x2)
-    uint32_t mn2 = 0x7fff7fffu, mx2 = 0x7fff7fffu;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (k < d.keep) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                mn2 = bf2_min(mn2, bf2_min(keys[v][k][0], keys[v][k][1]));
-                mx2 = bf2_max(mx2, bf2_max(keys[v][k][0], keys[v][k][1]));
-            }
-        }
-    }
     uint32_t kmin = min(mn2 & 0xffffu, mn2 >> 16);
     uint32_t mxl = mx2 & 0xffffu, mxh = mx2 >> 16;
     mxl = (mxl > 0x7f80u) ? 0u : mxl;
     mxh = (mxh > 0x7f80u) ? 0u : mxh;
     uint32_t kmax = max(mxl, mxh);
-    if (g.tid == 0) sts32(g.cand_cnt, 0u);
+    if (g.tid == 0) sts32(g.ctl, 0u);
     g.sum_min_max(cnt, kmin, kmax);
 
     double p;
@@ -372,140 +501,141 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, G& g, long 
         return;
     }
 
-    // ---- bisection on the 16-bit keys
+    // ---- bisection on the 16-bit keys (each thread reads only its own quads)
     uint32_t lo = kmin, hi = (kmax < kmin) ? kmin : kmax;
     int cb = 0, ch = d.keep * P.nstruct;
-    while (lo < hi && (ch - cb) > kCandCap) {
+    while (lo < hi && (ch - cb) > kRankCap) {
         const uint32_t mid = (lo + hi) >> 1;
-        const int c = g.sum(count_le<V>(keys, d.keep, mid | (mid << 16)));
+        const int c = g.sum(count_le(g.kscr, g.kstride, nq, mid | (mid << 16)));
         if (c > o) { hi = mid; ch = c; } else { lo = mid + 1; cb = c; }
     }
+    const uint32_t lo2 = lo | (lo << 16), hi2 = hi | (hi << 16);
+    int n_list;
 
-    uint32_t bm[(V + 1) / 2];
-    scan_range<V>(keys, d.keep, lo | (lo << 16), hi | (hi << 16), bm);
-    uint32_t vlo = lo << 16, vhi = (hi << 16) | 0xffffu;
-
-    if ((ch - cb) > kCandCap) {
-        // Single fat key h = lo == hi with more than kCandCap elements: bisect the
-        // low 16 bits among the elements of that key, re-materialising them from
-        // the coordinates on every pass (1-2 passes for nstruct ~ 10^4; more only
-        // for degenerate inputs with many identical distances).
+    if ((ch - cb) <= g.cap) {
+        // ---- compact the candidates' locations, then re-materialise them in
+        // full precision with the whole group in parallel
+        g.sync();                               // counter = 0 visible
+        scan_range(g.kscr, g.kstride, nq, lo2, hi2, [&](int e) {
+            const uint32_t slot = atoms_inc(g.ctl);
+            if (slot < (uint32_t)g.cap) sts32(g.list + slot * 4, ((uint32_t)g.tid << 16) | (uint32_t)e);
+        });
+        g.sync();
+        n_list = ch - cb;
+        for (int t = g.tid; t < n_list; t += g.nthr) {
+            const uint32_t code = lds32(g.list + t * 4);
+            sts32(g.list + t * 4, element_bits(pp, d, P.mode, (int)(code >> 16), g.nthr, nh, (int)(code & 0xffffu)));
+        }
+        g.sync();
+    } else {
+        // Single fat key h = lo == hi with more elements than the list holds:
+        // bisect the low 16 bits among the elements of that key, re-materialising
+        // them on every pass (degenerate inputs with very many equal distances).
         const int cb0 = cb;                 // elements with key < h
         uint32_t l2 = 0u, h2 = 0xffffu;
-        while (l2 < h2 && (ch - cb) > kCandCap) {
+        while (l2 < h2 && (ch - cb) > g.cap) {
             const uint32_t m2 = (l2 + h2) >> 1;
             int c_loc = 0;
-#pragma unroll
-            for (int w = 0; w < (V + 1) / 2; ++w) {
-                uint32_t b = bm[w];
-                while (b) {
-                    const int bit = __ffs(b) - 1;
-                    b &= b - 1;
-                    const uint32_t x = element_bits(pp, d, P.mode, g.tid, g.nthr, w, bit);
-                    c_loc += ((x & 0xffffu) <= m2) ? 1 : 0;
-                }
-            }
+            scan_range(g.kscr, g.kstride, nq, lo2, hi2, [&](int e) {
+                const uint32_t x = element_bits(pp, d, P.mode, g.tid, g.nthr, nh, e);
+                c_loc += ((x & 0xffffu) <= m2) ? 1 : 0;
+            });
             const int c = cb0 + g.sum(c_loc);
             if (c > o) { h2 = m2; ch = c; } else { l2 = m2 + 1; cb = c; }
         }
-        vlo = (lo << 16) | l2;
-        vhi = (lo << 16) | h2;
-        if ((ch - cb) > kCandCap) {
+        const uint32_t vlo = (lo << 16) | l2, vhi = (lo << 16) | h2;
+        if ((ch - cb) > g.cap) {
             // l2 == h2: every remaining candidate has the same bit pattern.
             if (g.tid == 0) write_result(out, d, vlo, cnt, o, p);
             return;
         }
-    }
-
-    // ---- gather the <= kCandCap candidates in full precision
-    g.sync();                               // cand_cnt = 0 visible
-#pragma unroll
-    for (int w = 0; w < (V + 1) / 2; ++w) {
-        uint32_t b = bm[w];
-        while (b) {
-            const int bit = __ffs(b) - 1;
-            b &= b - 1;
-            const uint32_t x = element_bits(pp, d, P.mode, g.tid, g.nthr, w, bit);
+        g.sync();
+        scan_range(g.kscr, g.kstride, nq, lo2, hi2, [&](int e) {
+            const uint32_t x = element_bits(pp, d, P.mode, g.tid, g.nthr, nh, e);
             if (x >= vlo && x <= vhi) {
-                const uint32_t slot = atoms_inc(g.cand_cnt);
-                if (slot < (uint32_t)kCandCap) sts32(g.cand + slot * 4, x);
+                const uint32_t slot = atoms_inc(g.ctl);
+                if (slot < (uint32_t)g.cap) sts32(g.list + slot * 4, x);
             }
-        }
+        });
+        g.sync();
+        n_list = ch - cb;
     }
-    g.sync();
 
     // ---- exact rank inside one warp: the (o - cb)-th smallest candidate
     if (g.leader_warp()) {
-        const int lane = g.tid & 31;
-        const int n = min((int)lds32(g.cand_cnt), kCandCap);
-        const int r = o - cb;
-        const uint32_t x = (lane < n) ? lds32(g.cand + lane * 4) : 0xffffffffu;
-        int rank = 0;
-        for (int t = 0; t < n; ++t) {
-            const uint32_t y = __shfl_sync(0xffffffffu, x, t);
-            rank += (y < x || (y == x && t < lane)) ? 1 : 0;
-        }
-        const unsigned hit = __ballot_sync(0xffffffffu, lane < n && rank == r);
-        // hit is non-empty by construction; guard keeps a corrupted input from hanging
-        const int src = hit ? (__ffs(hit) - 1) : 0;
-        const uint32_t ans = __shfl_sync(0xffffffffu, x, src);
-        if (lane == 0) write_result(out, d, ans, cnt, o, p);
+        const uint32_t ans = warp_select(g.list, n_list, o - cb, g.tid & 31);
+        if ((g.tid & 31) == 0) write_result(out, d, ans, cnt, o, p);
     }
 }
 
 // ---------------------------------------------------------------- kernels
-// G = 32: one pair per warp, kWarpsPerBlock independent warps per CTA.
-constexpr int kWarpsPerBlock = 8;
+// G = 32: one pair per warp, kWarpsPerBlock independent warps per CTA, no CTA
+// barrier anywhere.  Consecutive pairs (CSR order: same locus i) go to the warps
+// of one CTA, so the rows of locus i are shared through L1.
+#ifndef IGMK_WPB
+#define IGMK_WPB 20
+#endif
+#ifndef IGMK_MINB
+#define IGMK_MINB 1
+#endif
+constexpr int kWarpsPerBlock = IGMK_WPB;
 
-template <int V>
-__global__ void __launch_bounds__(32 * kWarpsPerBlock)
-actdist_warp_kernel(const ActdistParams P) {
+__global__ void __launch_bounds__(32 * kWarpsPerBlock, IGMK_MINB)
+actdist_warp_kernel(const ActdistParams P, const int V) {
     extern __shared__ uint4 s_keys[];             // [warp][2 V][32] key quads
-    __shared__ uint32_t s_cand[kWarpsPerBlock][kCandCap];
+    __shared__ uint32_t s_list[kWarpsPerBlock][kWarpListCap];
     __shared__ uint32_t s_cnt[kWarpsPerBlock];
     const int warp = threadIdx.x >> 5;
-    WarpGroup g;
+    Group<false> g;
     g.tid = threadIdx.x & 31;
     g.nthr = 32;
-    g.cand = smem_addr(&s_cand[warp][0]);
-    g.cand_cnt = smem_addr(&s_cnt[warp]);
+    g.list = smem_addr(&s_list[warp][0]);
+    g.ctl = smem_addr(&s_cnt[warp]);
+    g.cap = kWarpListCap;
     g.kscr = smem_addr(s_keys) + (uint32_t)(warp * 2 * V * 32 + g.tid) * 16u;
     g.kstride = 32u * 16u;
-    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
-    for (long long pair = (long long)blockIdx.x * kWarpsPerBlock + warp; pair < P.n_pairs;
+    g.red = 0u;
+    g.parity = 0;
+    const int nwarps = blockDim.x >> 5;           // <= kWarpsPerBlock (fewer when V is large)
+    const long long stride = (long long)gridDim.x * nwarps;
+    for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < P.n_pairs;
          pair += stride) {
-        process_pair<V, WarpGroup>(P, g, pair);
+        process_pair<false>(P, g, V, pair, pair + stride);
         __syncwarp();
     }
 }
 
-// G = blockDim.x (multiple of 32, <= 768): one pair per CTA.
-template <int V, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-actdist_block_kernel(const ActdistParams P) {
+// G = blockDim.x (multiple of 32, <= MAXT): one pair per CTA, two CTAs per SM.
+// MAXT = 320 leaves 96 registers per thread (all 12 row loads of a chunk in
+// flight at once); MAXT = 512 (64 registers) is for very large populations.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+actdist_block_kernel(const ActdistParams P, const int V) {
     extern __shared__ uint4 s_keys[];             // [2 V][blockDim] key quads
-    __shared__ uint32_t s_cand[kCandCap];
+    __shared__ uint32_t s_list[kBlockListCap];
     __shared__ uint32_t s_cnt;
     __shared__ uint32_t s_red[2 * 96];
-    BlockGroup g;
+    Group<true> g;
     g.tid = threadIdx.x;
     g.nthr = blockDim.x;
-    g.cand = smem_addr(s_cand);
-    g.cand_cnt = smem_addr(&s_cnt);
+    g.list = smem_addr(s_list);
+    g.ctl = smem_addr(&s_cnt);
+    g.cap = kBlockListCap;
     g.kscr = smem_addr(s_keys) + (uint32_t)threadIdx.x * 16u;
     g.kstride = (uint32_t)blockDim.x * 16u;
     g.red = smem_addr(s_red);
     g.parity = 0;
     for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        process_pair<V, BlockGroup>(P, g, pair);
+        process_pair<true>(P, g, V, pair, pair + gridDim.x);
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------- cross-check kernel
 // Straightforward version kept as an on-device cross-check (IGMK_ALGO_SIMPLE):
-// one CTA per pair, all kept d2 values in shared memory, 32-pass most-
-// significant-bit-first binary radix select on the raw float32 patterns.
+// one CTA per pair, all kept d2 values in shared memory (scalar non-FMA
+// arithmetic), 32-pass most-significant-bit-first binary radix select on the
+// raw float32 patterns.
 __global__ void __launch_bounds__(256)
 actdist_simple_kernel(const ActdistParams P) {
     extern __shared__ uint32_t s_val[];          // keep * nstruct values

@@ -21,6 +21,8 @@
 
 namespace igmk {
 
+typedef unsigned long long u64;
+
 constexpr int kSeg = 128;              // structures per row segment
 constexpr int kSegFloats = 3 * kSeg;   // floats per segment (x, y, z rows)
 
@@ -53,6 +55,8 @@ struct ActdistParams {
     float contact_range;      // already float32 (NEP-50: python float * f32 -> f32)
     int   it_corr;
     int   mode;
+    int   prefetch;           // L2-prefetch the next pair's rows (igmk_actdist.cuh)
+    u64   negzero2;           // {-0.0f, -0.0f}: opaque addend of the packed squares (igmk_actdist.cuh)
 };
 
 // Combination shapes of one pair (which of the four copy combinations
@@ -256,6 +260,11 @@ __device__ __forceinline__ uint32_t bf2_le_mask(uint32_t a, uint32_t b) {  // 0x
 __device__ __forceinline__ uint32_t bf2_ge_mask(uint32_t a, uint32_t b) {
     uint32_t r;
     asm("set.ge.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("set.eq.u32.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
 __device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {

@@ -32,7 +32,7 @@ extern "C" {
 #define IGMK_EINVAL   -1   /* bad argument */
 #define IGMK_ECUDA    -2   /* CUDA runtime error (no device, launch failure, OOM) */
 #define IGMK_ESTATE   -3   /* call order: coordinates / index not set */
-#define IGMK_ELIMIT   -4   /* outside supported range (ploidy > 2, nstruct > 32768) */
+#define IGMK_ELIMIT   -4   /* outside supported range (ploidy > 2, nstruct > 25600) */
 
 /* A-step flavours.  LB = igm/steps/ActivationDistanceStep.py:336-485 (what
  * igm-run executes); GP = igm/steps/GP_activation.py:317-445 and

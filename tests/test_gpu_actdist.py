@@ -100,11 +100,13 @@ def test_oracle_synthetic_warp_mode(nstruct, mode):
                 _check_against_details(res, dets)
 
 
-@pytest.mark.parametrize("nstruct,block_v", [(1500, 0), (2600, 0), (4100, 3), (4100, 4), (4100, 6), (4100, 8), (10000, 0)])
-def test_oracle_synthetic_block_mode(nstruct, block_v, monkeypatch):
+@pytest.mark.parametrize("nstruct,group_threads", [(1000, 64), (1500, 0), (2000, 32), (2600, 0), (4100, 32), (4100, 64),
+                                                   (4100, 160), (4100, 512), (10000, 0), (12288, 0), (20000, 0)])
+def test_oracle_synthetic_block_mode(nstruct, group_threads, monkeypatch):
+    """CTA-per-pair groups (and forced group sizes, incl. one warp for large N)."""
     from igm_b200 import synthetic
-    if block_v:
-        monkeypatch.setenv("IGMK_BLOCK_V", str(block_v))
+    if group_threads:
+        monkeypatch.setenv("IGMK_GROUP_THREADS", str(group_threads))
     pop = synthetic.make_population(2_000_000, nstruct, seed=7 + nstruct, genome_scale=0.004)
     rng = np.random.default_rng(nstruct)
     nh = pop.n_hap
