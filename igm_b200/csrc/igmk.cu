@@ -395,6 +395,7 @@ extern "C" int igmk_contact_counts_device(igmk_ctx* c, int row0, int nrows, int 
     P.nstruct = c->nstruct; P.npad = c->npad; P.nbead = c->nbead;
     P.row0 = row0; P.nrows = nrows; P.col0 = col0; P.ncols = ncols;
     P.contact_range = contact_range; P.strict = strict;
+    P.negzero2 = 0x8000000080000000ull;
     dim3 grid((ncols + kCtTile - 1) / kCtTile, (nrows + kCtTile - 1) / kCtTile);
     contact_tile_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
     g_launches++;

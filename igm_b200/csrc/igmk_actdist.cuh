@@ -35,68 +35,6 @@ constexpr int kWarpListCap = 64;    // candidate list words per warp group
 constexpr int kBlockListCap = 1024; // candidate list words per CTA group
 constexpr int kMaxQuads = 64;       // key quads per thread: bf16 pass counters stay exact
 
-// ----------------------------------------------------------- packed float32x2
-__device__ __forceinline__ u64 f2sub(u64 a, u64 b) {
-    u64 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ u64 f2add(u64 a, u64 b) {
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// rn(a * a) per half.  Written as fma(a, a, -0.0) with the -0.0 pair coming from
-// a kernel parameter: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
-// FFMA2 even under --fmad=false, which would break the sequential rounding
-// NumPy performs; an FMA whose addend is opaque cannot be contracted further,
-// and x*x + (-0.0) rounds exactly like x*x.
-__device__ __forceinline__ u64 f2sq(u64 a, u64 negzero2) {
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(negzero2));
-    return r;
-}
-// a <= b ? 1.0f : 0.0f  (FSET.BF; NaN compares false)
-__device__ __forceinline__ float f_le_one(float a, float b) {
-    float r;
-    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ u64 f2pack(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2split(u64 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-
-// x / y / z of 4 consecutive structures as packed pairs (s0,s1) (s2,s3)
-struct Row6 { u64 x01, x23, y01, y23, z01, z23; };
-
-__device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b) {
-#ifdef IGMK_LDG_NOALLOC
-    asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-#else
-    asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-#endif
-}
-__device__ __forceinline__ Row6 load_row6(const float* p) {
-    Row6 r;
-    ldg_v2b64(p, r.x01, r.x23);
-    ldg_v2b64(p + kSeg, r.y01, r.y23);
-    ldg_v2b64(p + 2 * kSeg, r.z01, r.z23);
-    return r;
-}
-// d2 of structures (4c+2h, 4c+2h+1), h = 0 / 1
-template <int H>
-__device__ __forceinline__ u64 d2pair(const Row6& a, const Row6& b, u64 nz) {
-    const u64 dx = f2sub(H ? a.x23 : a.x01, H ? b.x23 : b.x01);
-    const u64 dy = f2sub(H ? a.y23 : a.y01, H ? b.y23 : b.y01);
-    const u64 dz = f2sub(H ? a.z23 : a.z01, H ? b.z23 : b.z01);
-    return f2add(f2add(f2sq(dx, nz), f2sq(dy, nz)), f2sq(dz, nz));
-}
-
 // ------------------------------------------------------------------ groups
 // Shared scratch is addressed through 32-bit shared-window addresses.
 template <bool BLOCK>
@@ -223,15 +161,15 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
         {
             float s[4][NS];   // [q][slot]
             if (SH == SH_INTRA2) {
-                const Row6 a0 = load_row6(pa0), b0 = load_row6(pb0);
-                const Row6 a1 = load_row6(pa1), b1 = load_row6(pb1);
+                const Row6 a0 = load_row6<LD_KEEP>(pa0), b0 = load_row6<LD_STREAM>(pb0);
+                const Row6 a1 = load_row6<LD_KEEP>(pa1), b1 = load_row6<LD_STREAM>(pb1);
                 f2split(d2pair<0>(a0, b0, nz), s[0][0], s[1][0]);
                 f2split(d2pair<1>(a0, b0, nz), s[2][0], s[3][0]);
                 f2split(d2pair<0>(a1, b1, nz), s[0][1], s[1][1]);
                 f2split(d2pair<1>(a1, b1, nz), s[2][1], s[3][1]);
             } else {
-                const Row6 a0 = load_row6(pa0), b0 = load_row6(pb0);
-                const Row6 a1 = load_row6(pa1), b1 = load_row6(pb1);
+                const Row6 a0 = load_row6<LD_KEEP>(pa0), b0 = load_row6<LD_STREAM>(pb0);
+                const Row6 a1 = load_row6<LD_KEEP>(pa1), b1 = load_row6<LD_STREAM>(pb1);
                 float e[4][4];   // [q][combination d0..d3]
                 f2split(d2pair<0>(a0, b0, nz), e[0][0], e[1][0]);
                 f2split(d2pair<1>(a0, b0, nz), e[2][0], e[3][0]);

@@ -10,8 +10,8 @@
 // in-tree statement (HicEvaluationStep.py:89-92).  PARITY UNPINNED against
 // alabtools.
 //
-// Bound: FP32 CUDA-core issue (about 10 instructions per bead pair per
-// structure), not HBM: every coordinate is read once per tile row/column from
+// Bound: FP32 CUDA-core issue (5.5 instructions per bead pair per structure
+// with packed float32x2 arithmetic; 10 in scalar form), not HBM: every coordinate is read once per tile row/column from
 // L2 and reused 32 times out of shared memory.  Tensor cores do not apply
 // (3-term non-FMA float32 sums that must match NumPy bit for bit).
 //
@@ -27,6 +27,7 @@ constexpr int kCtTile = 32;            // beads per tile side
 constexpr int kCtThreads = 256;
 constexpr int kCtStruct = 32;          // structures staged per step
 constexpr int kCtRow = 3 * kCtStruct + 4;   // floats per bead in smem; /4 is odd -> conflict-free LDS.128
+constexpr int kCtRcRow = kCtTile + 8;       // cut-off tile row: (ta * 40 + tb) % 32 distinct within a warp
 
 struct ContactParams {
     const float* coords;   // [nbead][3][npad]
@@ -36,43 +37,60 @@ struct ContactParams {
     int row0, nrows, col0, ncols;
     float contact_range;
     int strict;
+    u64 negzero2;          // {-0.0f, -0.0f}, see f2sq()
 };
 
-template <bool STRICT, bool TAIL>
-__device__ __forceinline__ void contact_accumulate(const float* sa, const float* sb, int ta, int tb,
-                                                   int slice, int nvalid,
-                                                   const float (&rc)[4][4], int (&cnt)[4][4]) {
+// Full chunks: packed float32x2 arithmetic (two structures per FADD2 / FFMA2,
+// sequentially rounded like the scalar form), contact flags as 1.0 / 0.0
+// (FSET.BF) accumulated two per FADD2 - 5.5 instructions per bead pair and
+// structure instead of 10.
+template <bool STRICT>
+__device__ __forceinline__ void contact_accumulate_packed(const float* sa, const float* sb, int ta, int tb,
+                                                          int slice, u64 nz,
+                                                          const float* s_rc, u64 (&cnt2)[4][4]) {
 #pragma unroll
     for (int gq = 0; gq < 2; ++gq) {
         const int s4 = slice * 8 + gq * 4;       // first of 4 structures within the chunk
-        float4 ax[4], ay[4], az[4];
+        // two row beads at a time (24 registers of row coordinates live)
 #pragma unroll
-        for (int aa = 0; aa < 4; ++aa) {
-            const float* p = sa + (ta + 8 * aa) * kCtRow + s4;
-            ax[aa] = *reinterpret_cast<const float4*>(p);
-            ay[aa] = *reinterpret_cast<const float4*>(p + kCtStruct);
-            az[aa] = *reinterpret_cast<const float4*>(p + 2 * kCtStruct);
-        }
+        for (int ah = 0; ah < 4; ah += 2) {
+            Row6 a[2];
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const float* p = sb + (tb + 8 * bb) * kCtRow + s4;
-            const float4 bx = *reinterpret_cast<const float4*>(p);
-            const float4 by = *reinterpret_cast<const float4*>(p + kCtStruct);
-            const float4 bz = *reinterpret_cast<const float4*>(p + 2 * kCtStruct);
-            const float BX[4] = {bx.x, bx.y, bx.z, bx.w};
-            const float BY[4] = {by.x, by.y, by.z, by.w};
-            const float BZ[4] = {bz.x, bz.y, bz.z, bz.w};
+            for (int a2 = 0; a2 < 2; ++a2) {
+                const float* p = sa + (ta + 8 * (ah + a2)) * kCtRow + s4;
+                lds_v2b64(p, a[a2].x01, a[a2].x23);
+                lds_v2b64(p + kCtStruct, a[a2].y01, a[a2].y23);
+                lds_v2b64(p + 2 * kCtStruct, a[a2].z01, a[a2].z23);
+            }
 #pragma unroll
-            for (int aa = 0; aa < 4; ++aa) {
-                const float AX[4] = {ax[aa].x, ax[aa].y, ax[aa].z, ax[aa].w};
-                const float AY[4] = {ay[aa].x, ay[aa].y, ay[aa].z, ay[aa].w};
-                const float AZ[4] = {az[aa].x, az[aa].y, az[aa].z, az[aa].w};
+            for (int bb = 0; bb < 4; ++bb) {
+                const float* p = sb + (tb + 8 * bb) * kCtRow + s4;
+                Row6 b;
+                lds_v2b64(p, b.x01, b.x23);
+                lds_v2b64(p + kCtStruct, b.y01, b.y23);
+                lds_v2b64(p + 2 * kCtStruct, b.z01, b.z23);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float d2 = d2_nofma(AX[q], AY[q], AZ[q], BX[q], BY[q], BZ[q]);
-                    bool hit = STRICT ? (d2 < rc[aa][bb]) : (d2 <= rc[aa][bb]);
-                    if (TAIL) hit = hit && (s4 + q < nvalid);
-                    cnt[aa][bb] += hit ? 1 : 0;
+                for (int a2 = 0; a2 < 2; ++a2) {
+                    const int aa = ah + a2;
+                    float d0, d1, d2, d3;
+                    f2split(d2pair<0>(a[a2], b, nz), d0, d1);
+                    f2split(d2pair<1>(a[a2], b, nz), d2, d3);
+                    const float r = s_rc[(ta + 8 * aa) * kCtRcRow + tb + 8 * bb];
+#ifndef IGMK_CT_INTCOUNT
+                    if (STRICT) {
+                        cnt2[aa][bb] = f2add(cnt2[aa][bb], f2pack(f_lt_one(d0, r), f_lt_one(d1, r)));
+                        cnt2[aa][bb] = f2add(cnt2[aa][bb], f2pack(f_lt_one(d2, r), f_lt_one(d3, r)));
+                    } else {
+                        cnt2[aa][bb] = f2add(cnt2[aa][bb], f2pack(f_le_one(d0, r), f_le_one(d1, r)));
+                        cnt2[aa][bb] = f2add(cnt2[aa][bb], f2pack(f_le_one(d2, r), f_le_one(d3, r)));
+                    }
+#else
+                    // integer flags on the ALU pipe: the FMA pipes carry only the 8 packed ops
+                    int c = (int)cnt2[aa][bb];
+                    if (STRICT) c += (d0 < r) + (d1 < r) + (d2 < r) + (d3 < r);
+                    else        c += (d0 <= r) + (d1 <= r) + (d2 <= r) + (d3 <= r);
+                    cnt2[aa][bb] = (u64)(unsigned)c;
+#endif
                 }
             }
         }
@@ -84,6 +102,7 @@ contact_tile_kernel(const ContactParams P) {
     __shared__ __align__(16) float s_a[kCtTile * kCtRow];
     __shared__ __align__(16) float s_b[kCtTile * kCtRow];
     __shared__ uint32_t s_cnt[kCtTile * kCtTile];
+    __shared__ float s_rc[kCtTile * kCtRcRow];
 
     const int t = threadIdx.x;
     const int pos = t & 63, slice = t >> 6;
@@ -94,21 +113,19 @@ contact_tile_kernel(const ContactParams P) {
 
     for (int e = t; e < kCtTile * kCtTile; e += kCtThreads) s_cnt[e] = 0u;
 
-    float rc[4][4];
-    int cnt[4][4];
-#pragma unroll
-    for (int aa = 0; aa < 4; ++aa) {
-        const int a = a_base + ta + 8 * aa;
+    // squared cut-offs of the tile (float32, as the A-step computes rcutsq)
+    for (int e = t; e < kCtTile * kCtTile; e += kCtThreads) {
+        const int a = a_base + (e >> 5), b = b_base + (e & 31);
         const float ra = (a < a_end) ? __ldg(P.radii + a) : 0.f;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const int b = b_base + tb + 8 * bb;
-            const float rb = (b < b_end) ? __ldg(P.radii + b) : 0.f;
-            const float r = __fmul_rn(P.contact_range, __fadd_rn(ra, rb));
-            rc[aa][bb] = __fmul_rn(r, r);
-            cnt[aa][bb] = 0;
-        }
+        const float rb = (b < b_end) ? __ldg(P.radii + b) : 0.f;
+        const float r = __fmul_rn(P.contact_range, __fadd_rn(ra, rb));
+        s_rc[(e >> 5) * kCtRcRow + (e & 31)] = __fmul_rn(r, r);
     }
+    u64 cnt2[4][4];        // {even, odd structures} hit counts as floats (exact: < 2^24)
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) cnt2[aa][bb] = 0ull;
 
     const size_t row = (size_t)3 * P.npad;
     for (int s0 = 0; s0 < P.nstruct; s0 += kCtStruct) {
@@ -122,22 +139,26 @@ contact_tile_kernel(const ContactParams P) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const int a = a_base + bead, b = b_base + bead;
             const size_t so = coord_off(s0 + 4 * v4) + (size_t)comp * kSeg;
-            const float4 va = (a < a_end)
+            float4 va = (a < a_end)
                 ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)a * row + so)) : z;
+            // structures past the end of the population: NaN on the row side, so
+            // their d2 is NaN and never counts (the padding in HBM is zero)
+            const int sv = s0 + 4 * v4;
+            if (sv + 3 >= P.nstruct) {
+                const float qn = __int_as_float(0x7fffffff);
+                if (sv >= P.nstruct) va.x = qn;
+                if (sv + 1 >= P.nstruct) va.y = qn;
+                if (sv + 2 >= P.nstruct) va.z = qn;
+                va.w = qn;
+            }
             const float4 vb = (b < b_end)
                 ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)b * row + so)) : z;
             *reinterpret_cast<float4*>(s_a + bead * kCtRow + comp * kCtStruct + 4 * v4) = va;
             *reinterpret_cast<float4*>(s_b + bead * kCtRow + comp * kCtStruct + 4 * v4) = vb;
         }
         __syncthreads();
-        const int nvalid = P.nstruct - s0;      // structures of this chunk that exist
-        if (nvalid >= kCtStruct) {
-            if (P.strict) contact_accumulate<true, false>(s_a, s_b, ta, tb, slice, nvalid, rc, cnt);
-            else          contact_accumulate<false, false>(s_a, s_b, ta, tb, slice, nvalid, rc, cnt);
-        } else {
-            if (P.strict) contact_accumulate<true, true>(s_a, s_b, ta, tb, slice, nvalid, rc, cnt);
-            else          contact_accumulate<false, true>(s_a, s_b, ta, tb, slice, nvalid, rc, cnt);
-        }
+        if (P.strict) contact_accumulate_packed<true>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
+        else          contact_accumulate_packed<false>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
     }
 
     // combine the 4 structure slices
@@ -145,7 +166,15 @@ contact_tile_kernel(const ContactParams P) {
     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb)
-            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)cnt[aa][bb]);
+        {
+#ifndef IGMK_CT_INTCOUNT
+            float c_lo, c_hi;
+            f2split(cnt2[aa][bb], c_lo, c_hi);
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)(int)(c_lo + c_hi));
+#else
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)cnt2[aa][bb]);
+#endif
+        }
     __syncthreads();
     for (int e = t; e < kCtTile * kCtTile; e += kCtThreads) {
         const int a = a_base + (e >> 5), b = b_base + (e & 31);

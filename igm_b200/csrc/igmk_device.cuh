@@ -245,6 +245,88 @@ finish_results_kernel(igmk_pair_result* out, long long n) {
     reinterpret_cast<float2*>(out + t)[3] = make_float2(dist, prob);
 }
 
+// ----------------------------------------------------------- packed float32x2
+__device__ __forceinline__ u64 f2sub(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 f2add(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// rn(a * a) per half.  Written as fma(a, a, -0.0) with the -0.0 pair coming from
+// a kernel parameter: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even under --fmad=false, which would break the sequential rounding
+// NumPy performs; an FMA whose addend is opaque cannot be contracted further,
+// and x*x + (-0.0) rounds exactly like x*x.
+__device__ __forceinline__ u64 f2sq(u64 a, u64 negzero2) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(negzero2));
+    return r;
+}
+// a <= b ? 1.0f : 0.0f  (FSET.BF; NaN compares false)
+__device__ __forceinline__ float f_le_one(float a, float b) {
+    float r;
+    asm("set.le.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float f_lt_one(float a, float b) {
+    float r;
+    asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ u64 f2pack(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2split(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// x / y / z of 4 consecutive structures as packed pairs (s0,s1) (s2,s3)
+struct Row6 { u64 x01, x23, y01, y23, z01, z23; };
+
+// Row loads with an L1 policy: the rows of locus i are shared by every warp of the
+// CTA (consecutive pairs of the CSR-ordered list) and should stay in L1; the rows
+// of locus j are streamed once and must not evict them.
+enum : int { LD_KEEP = 0, LD_STREAM = 1, LD_PLAIN = 2 };
+template <int HINT>
+__device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b) {
+#ifdef IGMK_NO_L1_HINTS
+    asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+#else
+    if (HINT == LD_KEEP)
+        asm("ld.global.nc.L1::evict_last.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else if (HINT == LD_STREAM)
+        asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else
+        asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+#endif
+}
+__device__ __forceinline__ void lds_v2b64(const float* p, u64& a, u64& b) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];"
+                 : "=l"(a), "=l"(b) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+}
+template <int HINT>
+__device__ __forceinline__ Row6 load_row6(const float* p) {
+    Row6 r;
+    ldg_v2b64<HINT>(p, r.x01, r.x23);
+    ldg_v2b64<HINT>(p + kSeg, r.y01, r.y23);
+    ldg_v2b64<HINT>(p + 2 * kSeg, r.z01, r.z23);
+    return r;
+}
+// d2 of structures (4c+2h, 4c+2h+1), h = 0 / 1
+template <int H>
+__device__ __forceinline__ u64 d2pair(const Row6& a, const Row6& b, u64 nz) {
+    const u64 dx = f2sub(H ? a.x23 : a.x01, H ? b.x23 : b.x01);
+    const u64 dy = f2sub(H ? a.y23 : a.y01, H ? b.y23 : b.y01);
+    const u64 dz = f2sub(H ? a.z23 : a.z01, H ? b.z23 : b.z01);
+    return f2add(f2add(f2sq(dx, nz), f2sq(dy, nz)), f2sq(dz, nz));
+}
+
 // ---- packed bf16x2 primitives (sm_90+ PTX; keys are the high 16 bits of the
 // non-negative float32 d2, so bf16 order == unsigned order == float order) ----
 __device__ __forceinline__ uint32_t bf2_le(uint32_t a, uint32_t b) {   // 1.0 / 0.0 per half
