@@ -140,6 +140,20 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None}
 
 
+def measured_traffic(nstruct, n_pairs, mode):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel on this
+    workload, from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by profiles/summarize.py --traffic); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        for e in json.load(open(p))["captures"]:
+            if e["nstruct"] == nstruct and e["n_pairs"] == n_pairs and e["mode"] == mode:
+                return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -363,7 +377,8 @@ def main():
                 "parity_sample_ok": parity,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         "traffic": measured_traffic(args.nstruct, n_pairs, args.mode),
                          "kernel": "actdist_warp_kernel" if args.nstruct <= 1024 else "actdist_block_kernel",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
                          "peak_source": peak_src},
@@ -373,8 +388,9 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline:
-            # bounded CPU sample: needs host copies of the beads the sample touches
-            nb = 4000
+            # bounded CPU sample (about --cpu-seconds of work on all host cores):
+            # needs host copies of the beads the sample touches
+            nb = 320000
             hap_needed = np.unique(np.concatenate([ii[:nb * 8], jj[:nb * 8]]))
             beads = np.unique(np.concatenate([ci[h] for h in hap_needed]))
             remap = -np.ones(nbead, np.int64)

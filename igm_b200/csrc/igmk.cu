@@ -56,6 +56,9 @@ struct igmk_ctx {
     void* d_stage = nullptr; size_t stage_bytes = 0;
     void* d_pairs = nullptr; size_t pairs_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of igmk_actdist_host
+    std::vector<cudaEvent_t> ev_in, ev_k;
+    long long host_slice_pairs = 1 << 19;             // IGMK_HOST_SLICE
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_kernel_ms = 0.f;
     int group_threads = 0;       // IGMK_GROUP_THREADS
@@ -102,12 +105,16 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     cudaMemset(c->d_coords, 0, bytes);
     cudaMalloc(&c->d_radii, (size_t)nbead * sizeof(float));
     cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
     const char* ov = getenv("IGMK_GROUP_THREADS");
     if (ov) c->group_threads = atoi(ov);
     ov = getenv("IGMK_PREFETCH");
     if (ov) c->prefetch = atoi(ov);
+    ov = getenv("IGMK_HOST_SLICE");
+    if (ov && atoll(ov) > 0) c->host_slice_pairs = atoll(ov);
     ov = getenv("IGMK_WARPS_PER_CTA");
     if (ov) c->warps_per_cta = atoi(ov);
     *out = c;
@@ -124,6 +131,10 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_pairs);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return IGMK_OK;
@@ -328,18 +339,40 @@ extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
     int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
     if (rc) return rc;
     char* base = (char*)c->d_pairs;
-    CUDA_TRY(cudaMemcpyAsync(base, i, n * 4, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + off_j, j, n * 4, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + off_pw, pwish, n * 8, cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(base + off_pl, plast, n * 8, cudaMemcpyHostToDevice, c->stream));
+    // Three-stage pipeline over slices of the pair list: inputs of slice k+1 go up
+    // (copy-in stream) and results of slice k-1 come down (copy-out stream) while
+    // the kernel works on slice k.  Overlap needs pinned host buffers
+    // (igmk_host_alloc); pageable ones still work, serialised by the driver.
+    const size_t slice = (size_t)c->host_slice_pairs;
+    const int nsl = (int)((n + slice - 1) / slice);
+    if ((int)c->ev_in.size() < nsl) {
+        const size_t old = c->ev_in.size();
+        c->ev_in.resize(nsl); c->ev_k.resize(nsl);
+        for (size_t t = old; t < (size_t)nsl; ++t) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[t], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_k[t], cudaEventDisableTiming));
+        }
+    }
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    rc = igmk_actdist_device(c, n_pairs, (const int32_t*)base, (const int32_t*)(base + off_j),
-                             (const double*)(base + off_pw), (const double*)(base + off_pl),
-                             contact_range, it_corr, mode, algo,
-                             (igmk_pair_result*)(base + off_out), c->stream);
-    if (rc) return rc;
+    for (int k = 0; k < nsl; ++k) {
+        const size_t lo = (size_t)k * slice, cnt = (n - lo < slice) ? n - lo : slice;
+        CUDA_TRY(cudaMemcpyAsync(base + lo * 4, i + lo, cnt * 4, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaMemcpyAsync(base + off_j + lo * 4, j + lo, cnt * 4, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaMemcpyAsync(base + off_pw + lo * 8, pwish + lo, cnt * 8, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaMemcpyAsync(base + off_pl + lo * 8, plast + lo, cnt * 8, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        igmk_pair_result* d_out = (igmk_pair_result*)(base + off_out) + lo;
+        rc = igmk_actdist_device(c, (int64_t)cnt, (const int32_t*)base + lo, (const int32_t*)(base + off_j) + lo,
+                                 (const double*)(base + off_pw) + lo, (const double*)(base + off_pl) + lo,
+                                 contact_range, it_corr, mode, algo, d_out, c->stream);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CUDA_TRY(cudaEventRecord(c->ev_k[k], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+        CUDA_TRY(cudaMemcpyAsync(out + lo, d_out, cnt * sizeof(igmk_pair_result), cudaMemcpyDeviceToHost, c->s_out));
+    }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(out, base + off_out, n * sizeof(igmk_pair_result), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->s_out));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
     return IGMK_OK;
