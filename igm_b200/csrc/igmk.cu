@@ -20,6 +20,8 @@
 #include "igmk_actdist.cuh"
 #include "igmk_contact.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 using namespace igmk;
 
 static thread_local std::string g_err;
@@ -63,7 +65,11 @@ struct igmk_ctx {
     float last_kernel_ms = 0.f;
     int group_threads = 0;       // IGMK_GROUP_THREADS
     int warps_per_cta = 0;       // IGMK_WARPS_PER_CTA
-    int prefetch = 0;            // IGMK_PREFETCH
+    long long l2_budget = 80ll << 20;   // IGMK_L2_BUDGET: bytes of locus-j rows one J-block may hold
+    long long order_min_pairs = 65536;  // IGMK_ORDER_MIN: shorter lists keep the input order
+    void* d_order = nullptr; size_t order_bytes = 0;    // keys / values / cub temp of order_pairs()
+    int tile_block = 512;        // IGMK_TILE_BLOCK (0: no shared-memory locus-i tile)
+    int tile_slots = 1;          // IGMK_TILE_SLOTS (2 slots shrink L1 to 15 KB at N = 1000: slower)
 };
 
 static int ensure(void** p, size_t* cap, size_t bytes) {
@@ -111,8 +117,14 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     cudaEventCreate(&c->ev1);
     const char* ov = getenv("IGMK_GROUP_THREADS");
     if (ov) c->group_threads = atoi(ov);
-    ov = getenv("IGMK_PREFETCH");
-    if (ov) c->prefetch = atoi(ov);
+    ov = getenv("IGMK_L2_BUDGET");
+    if (ov) c->l2_budget = atoll(ov);
+    ov = getenv("IGMK_ORDER_MIN");
+    if (ov) c->order_min_pairs = atoll(ov);
+    ov = getenv("IGMK_TILE_SLOTS");
+    if (ov) c->tile_slots = atoi(ov);
+    ov = getenv("IGMK_TILE_BLOCK");
+    if (ov) c->tile_block = atoi(ov);
     ov = getenv("IGMK_HOST_SLICE");
     if (ov && atoll(ov) > 0) c->host_slice_pairs = atoll(ov);
     ov = getenv("IGMK_WARPS_PER_CTA");
@@ -129,6 +141,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_hap);
     cudaFree(c->d_stage);
     cudaFree(c->d_pairs);
+    cudaFree(c->d_order);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
@@ -220,19 +233,26 @@ static int launch_finish(const ActdistParams& P, cudaStream_t st) {
     return IGMK_OK;
 }
 
-static int launch_warp(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
+static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     const int V = (c->nchunks + 31) / 32;
-    // one CTA per SM; as many warps as the key arrays (V KiB per warp) leave room for
-    int warps = (int)((200 * 1024) / ((size_t)2 * V * 32 * 16));
+    // one CTA per SM: two locus-i tiles (2 rows of 12 * npad bytes each) plus as many
+    // warps as the key arrays (V KiB per warp) leave room for
+    const size_t budget = 208 * 1024;
+    const int slots = (c->tile_slots == 1) ? 1 : 2;
+    size_t tile_bytes = (c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)slots * 24 * c->npad : 0;
+    if (tile_bytes + (size_t)8 * 2 * V * 32 * 16 > budget) tile_bytes = 0;     // keep >= 8 warps
+    int warps = (int)((budget - tile_bytes) / ((size_t)2 * V * 32 * 16));
     if (warps > kWarpsPerBlock) warps = kWarpsPerBlock;
     if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
     if (warps < 1) return fail(IGMK_ELIMIT, "actdist_warp_kernel: nstruct = %d is too large for one warp per pair", c->nstruct);
+    P.tile_block = tile_bytes ? c->tile_block : 0;
+    P.tile_slots = slots;
     int per_sm = 0;
-    const size_t smem = (size_t)warps * 2 * V * 32 * 16;
+    const size_t smem = (size_t)warps * 2 * V * 32 * 16 + tile_bytes;
     CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel, 32 * warps, smem));
     if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_warp_kernel cannot run with V = %d", V);
-    long long want = (P.n_pairs + warps - 1) / warps;
+    long long want = P.tile_block ? (P.n_pairs + P.tile_block - 1) / P.tile_block : (P.n_pairs + warps - 1) / warps;
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((want < cap) ? want : cap);
     actdist_warp_kernel<<<grid, 32 * warps, smem, st>>>(P, V);
@@ -274,6 +294,55 @@ static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t
     return launch_finish(P, st);
 }
 
+// ------------------------------------------------------- processing order
+// The rows of locus j are streamed once per pair; when the whole population does not
+// fit in L2 they come from HBM again for every row i of the list.  Processing the
+// list one J-block at a time (loci whose rows fit the L2 budget together), in the
+// caller's order inside a block, turns those into L2 hits: DRAM traffic drops from
+// ~11 KB to < 1 KB per pair at N = 1000.  Stable 1-pass radix sort on the block id.
+__global__ void jblock_keys_kernel(const int32_t* __restrict__ pj, long long n, int loci_per_block,
+                                   int n_hap, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int j = pj[t];
+    j = (j < 0) ? 0 : (j >= n_hap ? n_hap - 1 : j);
+    keys[t] = (uint32_t)(j / loci_per_block);
+    vals[t] = (int32_t)t;
+}
+
+static int order_pairs(igmk_ctx* c, int64_t n_pairs, const int32_t* d_j, cudaStream_t st,
+                       const int32_t** perm_out) {
+    *perm_out = nullptr;
+    if (c->l2_budget <= 0 || n_pairs < c->order_min_pairs || n_pairs > 0x7fffffffLL) return IGMK_OK;
+    const long long per_locus = 2ll * 12 * c->npad;
+    long long lpb = c->l2_budget / per_locus;
+    if (lpb < 1) lpb = 1;
+    const int nblk = (int)((c->n_hap + lpb - 1) / lpb);
+    if (nblk <= 1) return IGMK_OK;
+    int bits = 1;
+    while ((1 << bits) < nblk) ++bits;
+    const size_t n = (size_t)n_pairs;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, bits, st);
+    const size_t total = 4 * up(n * 4) + up(temp);
+    int rc = ensure(&c->d_order, &c->order_bytes, total);
+    if (rc) return rc;
+    char* base = (char*)c->d_order;
+    uint32_t* k_in = (uint32_t*)base;
+    uint32_t* k_out = (uint32_t*)(base + up(n * 4));
+    int32_t* v_in = (int32_t*)(base + 2 * up(n * 4));
+    int32_t* v_out = (int32_t*)(base + 3 * up(n * 4));
+    void* d_temp = base + 4 * up(n * 4);
+    jblock_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_j, (long long)n, (int)lpb, c->n_hap, k_in, v_in);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_temp, temp, k_in, k_out, v_in, v_out, (int)n, 0, bits, st));
+    *perm_out = v_out;
+    return IGMK_OK;
+}
+
 extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
                                    const int32_t* d_i, const int32_t* d_j,
                                    const double* d_pwish, const double* d_plast,
@@ -293,10 +362,16 @@ extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
     P.n_pairs = n_pairs; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
     P.n_hap = c->n_hap; P.contact_range = contact_range; P.it_corr = it_corr; P.mode = mode;
     P.negzero2 = 0x8000000080000000ull;
-    P.prefetch = c->prefetch;
+    P.perm = nullptr;
+    P.tile_block = 0;
+    P.tile_slots = 0;
 
     if (algo == IGMK_ALGO_SIMPLE) return launch_simple(c, P, st);
     if (algo != IGMK_ALGO_FAST) return fail(IGMK_EINVAL, "igmk_actdist: bad algo %d", algo);
+    {
+        int rc = order_pairs(c, n_pairs, d_j, st, &P.perm);
+        if (rc) return rc;
+    }
 
     // Thread-group shape (igmk_actdist.cuh): V float4 chunks (4 structures x <= 4
     // combinations each) per thread.

@@ -121,10 +121,12 @@ __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const Pair
     return pp;
 }
 
-template <int SH>
+// AS: the rows of locus i come from the CTA's shared-memory tile (as0 / as1 =
+// shared addresses of the a0 / a1 rows, same layout as in HBM).
+template <int SH, bool AS>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
                                           const PairPtrs& pp, int tid, int nthr, int V,
-                                          uint32_t kscr, uint32_t kstride,
+                                          uint32_t kscr, uint32_t kstride, uint32_t as0, uint32_t as1,
                                           int& cnt, uint32_t& mn2, uint32_t& mx2) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
@@ -138,6 +140,7 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
     const float* pb0 = pp.B0 + off0;
     const float* pa1 = pp.A1 + off0;
     const float* pb1 = pp.B1 + off0;
+    uint32_t sa0 = as0 + (uint32_t)off0 * 4u, sa1 = as1 + (uint32_t)off0 * 4u;
     u64 c_local = 0ull;            // {count of even, count of odd structures} as floats
     uint32_t lmn = 0x7fff7fffu, lmx = 0x7fff7fffu;
     // in generic pairs only NH is not known at compile time
@@ -146,10 +149,14 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
 
     // The chunk loop is deliberately NOT unrolled (instruction-cache footprint and
     // register pressure: 48 registers of loaded coordinates are live here).
+    // (Software-pipelining the locus-j loads of chunk v + 1 over the arithmetic of
+    // chunk v was tried for the shared-tile path: at 96 registers it spills and
+    // loses 12 %, at 118 registers / 16 warps it only reaches parity.)
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
         const int c = tid + v * nthr;
         uint32_t nk[NS][2];
+        Row6 a0, a1, b0, b1;
         if (c >= P.nchunks) {              // padding chunk: NaN keys, nothing to load
             sts128(dst, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
             if (NS == 4) {
@@ -160,16 +167,18 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
         }
         {
             float s[4][NS];   // [q][slot]
+            b0 = load_row6<LD_STREAM>(pb0); b1 = load_row6<LD_STREAM>(pb1);
+            if (AS) {
+                a0 = load_row6_shared(sa0); a1 = load_row6_shared(sa1);
+            } else {
+                a0 = load_row6<LD_KEEP>(pa0); a1 = load_row6<LD_KEEP>(pa1);
+            }
             if (SH == SH_INTRA2) {
-                const Row6 a0 = load_row6<LD_KEEP>(pa0), b0 = load_row6<LD_STREAM>(pb0);
-                const Row6 a1 = load_row6<LD_KEEP>(pa1), b1 = load_row6<LD_STREAM>(pb1);
                 f2split(d2pair<0>(a0, b0, nz), s[0][0], s[1][0]);
                 f2split(d2pair<1>(a0, b0, nz), s[2][0], s[3][0]);
                 f2split(d2pair<0>(a1, b1, nz), s[0][1], s[1][1]);
                 f2split(d2pair<1>(a1, b1, nz), s[2][1], s[3][1]);
             } else {
-                const Row6 a0 = load_row6<LD_KEEP>(pa0), b0 = load_row6<LD_STREAM>(pb0);
-                const Row6 a1 = load_row6<LD_KEEP>(pa1), b1 = load_row6<LD_STREAM>(pb1);
                 float e[4][4];   // [q][combination d0..d3]
                 f2split(d2pair<0>(a0, b0, nz), e[0][0], e[1][0]);
                 f2split(d2pair<1>(a0, b0, nz), e[2][0], e[3][0]);
@@ -232,6 +241,7 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
         }
         dst += (uint32_t)nh * kstride;
         pa0 += vstride; pb0 += vstride; pa1 += vstride; pb1 += vstride;
+        sa0 += (uint32_t)vstride * 4u; sa1 += (uint32_t)vstride * 4u;
     }
     float c_lo, c_hi;
     f2split(c_local, c_lo, c_hi);
@@ -377,31 +387,120 @@ __device__ __forceinline__ uint32_t warp_select(uint32_t list, int n, int r, int
     return prefix;
 }
 
-// Fire-and-forget L2 prefetch of the bead rows the group's NEXT pair will
-// stream (about a third of the row sectors otherwise come from HBM with the full
-// DRAM latency exposed in the fill loop).  One 128-byte line per thread and trip.
-__device__ __forceinline__ void prefetch_rows_l2(const ActdistParams& P, long long next_pair,
-                                                 int tid, int nthr) {
-    if (next_pair >= P.n_pairs) return;
-    const int j = __ldg(P.pj + next_pair);
-    if (j < 0 || j >= P.n_hap) return;
-    const int4 hb = __ldg(reinterpret_cast<const int4*>(P.hap + j));
-    const size_t row_bytes = (size_t)12 * P.npad;
-    const int lines = (int)(row_bytes >> 7);           // npad is a multiple of 128: exact
-    const char* base = reinterpret_cast<const char*>(P.coords);
-    const char* r0 = base + (size_t)hb.x * row_bytes;
-    const char* r1 = base + (size_t)(hb.y >= 0 ? hb.y : hb.x) * row_bytes;
-    for (int l = tid; l < lines; l += nthr) {
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(r0 + ((size_t)l << 7)));
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(r1 + ((size_t)l << 7)));
+// ------------------------------------------------------------- one pair
+// ---------------------------------------------------- locus-i tile (warp kernel)
+// Two shared-memory slots per CTA, each holding the coordinate rows (both copies) of
+// one locus i, so the warps that work on the consecutive pairs (i, j1), (i, j2), ...
+// read them from shared memory instead of L2.  No warp ever waits: a warp whose locus
+// is not resident either claims a free slot and loads the rows itself (one extra
+// shared-memory round trip for that one pair) or simply streams them from L2 as
+// before.  Slot word = locus << 12 | state << 10 | users; every transition is a
+// single-word atomic, so there is no ABA window.
+enum : uint32_t { TS_EMPTY = 0u, TS_LOADING = 1u, TS_READY = 2u };
+struct TileCtl {
+    uint32_t base;        // shared address of slot 0 (0: tiles disabled)
+    uint32_t slot_bytes;  // 2 rows * 12 * npad
+    uint32_t words;       // shared address of the slot words
+    int nslots;           // 1 or 2
+};
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
+    uint32_t old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCtl& tile, int i,
+                                            const PairDesc& d, const PairPtrs& pp, int lane) {
+    int found = -1, claimed = -1;
+    if (lane == 0) {
+        const uint32_t want = (uint32_t)i;
+        uint32_t w[2];
+        w[1] = (0xfffffu << 12) | (TS_LOADING << 10);      // a missing second slot never matches
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s >= tile.nslots) break;
+            w[s] = lds32_volatile(tile.words + 4u * s);
+            for (int tries = 0; tries < 4 && found < 0; ++tries) {
+                if ((w[s] >> 12) != want || ((w[s] >> 10) & 3u) != TS_READY) break;
+                const uint32_t old = atoms_cas(tile.words + 4u * s, w[s], w[s] + 1u);
+                if (old == w[s]) found = s; else w[s] = old;
+            }
+        }
+        if (found < 0) {
+            const bool busy_same = ((w[0] >> 12) == want && ((w[0] >> 10) & 3u) == TS_LOADING) ||
+                                   ((w[1] >> 12) == want && ((w[1] >> 10) & 3u) == TS_LOADING);
+            if (!busy_same) {
+                // victim: an idle slot (no users, not loading); empty first, then the
+                // smaller locus (CSR order: the older one)
+                int order0 = 0;
+                if (((w[0] >> 10) & 3u) != TS_EMPTY &&
+                    (((w[1] >> 10) & 3u) == TS_EMPTY || (w[1] >> 12) < (w[0] >> 12))) order0 = 1;
+#pragma unroll
+                for (int t = 0; t < 2 && claimed < 0; ++t) {
+                    const int s = order0 ^ t;
+                    if (s >= tile.nslots) continue;
+                    const uint32_t st = (w[s] >> 10) & 3u;
+                    if ((w[s] & 0x3ffu) != 0u || st == TS_LOADING) continue;
+                    if (st == TS_READY && (w[s] >> 12) == want) continue;
+                    const uint32_t nw = (want << 12) | (TS_LOADING << 10);
+                    if (atoms_cas(tile.words + 4u * s, w[s], nw) == w[s]) claimed = s;
+                }
+            }
+        }
     }
+    found = __shfl_sync(0xffffffffu, found, 0);
+    claimed = __shfl_sync(0xffffffffu, claimed, 0);
+    if (found >= 0) {
+        __threadfence_block();               // acquire: the loader's stores are visible
+        return found;
+    }
+    if (claimed < 0) return -1;
+    // load both rows of locus i (global -> shared, 128-bit, whole warp)
+    const uint32_t dst0 = tile.base + (uint32_t)claimed * tile.slot_bytes;
+    const int n16 = (int)(tile.slot_bytes >> 5);          // 16-byte words per row
+    const float4* r0 = reinterpret_cast<const float4*>(pp.A0);
+    const float4* r1 = reinterpret_cast<const float4*>(pp.A1);
+    for (int k = lane; k < n16; k += 32) {
+        const float4 x0 = __ldg(r0 + k);
+        sts128(dst0 + (uint32_t)k * 16u, __float_as_uint(x0.x), __float_as_uint(x0.y),
+               __float_as_uint(x0.z), __float_as_uint(x0.w));
+    }
+    if (d.a1 >= 0) {
+        const uint32_t dst1 = dst0 + (tile.slot_bytes >> 1);
+        for (int k = lane; k < n16; k += 32) {
+            const float4 x1 = __ldg(r1 + k);
+            sts128(dst1 + (uint32_t)k * 16u, __float_as_uint(x1.x), __float_as_uint(x1.y),
+                   __float_as_uint(x1.z), __float_as_uint(x1.w));
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+        // publish with one user (this warp); nobody touches a LOADING word
+        const uint32_t ready = ((uint32_t)i << 12) | (TS_READY << 10) | 1u;
+        uint32_t prev;
+        asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(prev) : "r"(tile.words + 4u * claimed), "r"(ready) : "memory");
+        (void)prev;
+    }
+    __syncwarp();
+    return claimed;
+}
+__device__ __forceinline__ void tile_release(const TileCtl& tile, int slot, int lane) {
+    __syncwarp();                            // every lane's tile reads are done
+    if (lane == 0)
+        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(tile.words + 4u * slot), "r"(0xffffffffu) : "memory");
 }
 
-// ------------------------------------------------------------- one pair
 template <bool BLOCK>
 __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK>& g, int V,
-                                             long long pair, long long next_pair) {
-    if (P.prefetch) prefetch_rows_l2(P, next_pair, g.tid, g.nthr);
+                                             long long slot, const TileCtl& tile) {
+    // slot = position in processing order; perm maps it to the pair's index in the
+    // caller's list (results stay in input order)
+    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
     const int i = __ldg(P.pi + pair), j = __ldg(P.pj + pair);
     const PairDesc d = make_pair_desc(P, i, j);
     igmk_pair_result* out = P.out + pair;
@@ -414,11 +513,24 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
 
     int cnt;
     uint32_t mn2, mx2;
-    switch (pair_shape(d, P.mode)) {       // uniform over the group
-        case SH_FULL4:  fill_keys<SH_FULL4>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
-        case SH_INTRA2: fill_keys<SH_INTRA2>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
-        case SH_GP4:    fill_keys<SH_GP4>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
-        default:        fill_keys<SH_GENERIC>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, cnt, mn2, mx2); break;
+    const int tslot = (!BLOCK && tile.base) ? tile_acquire(P, tile, i, d, pp, g.tid) : -1;
+    if (tslot >= 0) {
+        const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
+        const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
+        switch (pair_shape(d, P.mode)) {       // uniform over the group
+            case SH_FULL4:  fill_keys<SH_FULL4, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+        }
+        tile_release(tile, tslot, g.tid);
+    } else {
+        switch (pair_shape(d, P.mode)) {       // uniform over the group
+            case SH_FULL4:  fill_keys<SH_FULL4, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+        }
     }
     const int nh = (d.keep > 2) ? 2 : 1;
     const int nq = V * nh;
@@ -520,10 +632,13 @@ constexpr int kWarpsPerBlock = IGMK_WPB;
 
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, IGMK_MINB)
 actdist_warp_kernel(const ActdistParams P, const int V) {
-    extern __shared__ uint4 s_keys[];             // [warp][2 V][32] key quads
+    extern __shared__ uint4 s_keys[];             // [warp][2 V][32] key quads, then 2 locus-i tiles
     __shared__ uint32_t s_list[kWarpsPerBlock][kWarpListCap];
     __shared__ uint32_t s_cnt[kWarpsPerBlock];
+    __shared__ uint32_t s_slot[2];
+    __shared__ unsigned int s_ticket;
     const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;           // <= kWarpsPerBlock (fewer when V is large)
     Group<false> g;
     g.tid = threadIdx.x & 31;
     g.nthr = 32;
@@ -534,11 +649,39 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     g.kstride = 32u * 16u;
     g.red = 0u;
     g.parity = 0;
-    const int nwarps = blockDim.x >> 5;           // <= kWarpsPerBlock (fewer when V is large)
+    TileCtl tile;
+    tile.base = 0u; tile.slot_bytes = 0u; tile.words = smem_addr(s_slot); tile.nslots = P.tile_slots;
+    if (P.tile_block > 0) {
+        tile.base = smem_addr(s_keys) + (uint32_t)nwarps * 2u * (uint32_t)V * 512u;
+        tile.slot_bytes = 24u * (uint32_t)P.npad;
+        if (threadIdx.x == 0) {
+            s_slot[0] = (0xfffffu << 12) | (TS_EMPTY << 10);
+            s_slot[1] = (0xfffffu << 12) | (TS_EMPTY << 10);
+            s_ticket = 0u;
+        }
+        __syncthreads();
+        // CTA-contiguous blocks of tile_block pairs (block k of this CTA = list block
+        // blockIdx + k * gridDim), handed to the warps one pair at a time by a
+        // shared ticket counter: consecutive pairs share locus i, and fast / slow
+        // pairs balance out across the warps.
+        const unsigned int B = (unsigned int)P.tile_block;
+        for (;;) {
+            unsigned int t = 0u;
+            if (g.tid == 0) t = atomicAdd(&s_ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const unsigned int k = t / B, r = t - k * B;
+            const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
+            if (base >= P.n_pairs) break;
+            const long long pair = base + r;
+            if (pair < P.n_pairs) process_pair<false>(P, g, V, pair, tile);
+            __syncwarp();
+        }
+        return;
+    }
     const long long stride = (long long)gridDim.x * nwarps;
     for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < P.n_pairs;
          pair += stride) {
-        process_pair<false>(P, g, V, pair, pair + stride);
+        process_pair<false>(P, g, V, pair, tile);
         __syncwarp();
     }
 }
@@ -563,8 +706,10 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     g.kstride = (uint32_t)blockDim.x * 16u;
     g.red = smem_addr(s_red);
     g.parity = 0;
+    TileCtl tile;
+    tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;
     for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        process_pair<true>(P, g, V, pair, pair + gridDim.x);
+        process_pair<true>(P, g, V, pair, tile);
         __syncthreads();
     }
 }

@@ -55,7 +55,9 @@ struct ActdistParams {
     float contact_range;      // already float32 (NEP-50: python float * f32 -> f32)
     int   it_corr;
     int   mode;
-    int   prefetch;           // L2-prefetch the next pair's rows (igmk_actdist.cuh)
+    const int32_t* perm;      // processing order (NULL: input order), see igmk.cu order_pairs()
+    int   tile_slots;         // 1 or 2 locus-i tiles per CTA
+    int   tile_block;         // warp kernel: pairs per CTA-contiguous block; 0 = no locus-i tile in shared memory
     u64   negzero2;           // {-0.0f, -0.0f}: opaque addend of the packed squares (igmk_actdist.cuh)
 };
 
@@ -309,6 +311,13 @@ __device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b) {
 __device__ __forceinline__ void lds_v2b64(const float* p, u64& a, u64& b) {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];"
                  : "=l"(a), "=l"(b) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+}
+__device__ __forceinline__ Row6 load_row6_shared(uint32_t addr) {   // same layout, shared window address
+    Row6 r;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r.x01), "=l"(r.x23) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+512];" : "=l"(r.y01), "=l"(r.y23) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+1024];" : "=l"(r.z01), "=l"(r.z23) : "r"(addr) : "memory");
+    return r;
 }
 template <int HINT>
 __device__ __forceinline__ Row6 load_row6(const float* p) {

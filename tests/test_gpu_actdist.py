@@ -124,6 +124,37 @@ def test_oracle_synthetic_block_mode(nstruct, group_threads, monkeypatch):
             _check_against_details(res, dets)
 
 
+@pytest.mark.parametrize("nstruct,tile_block", [(300, 0), (300, 7), (1000, 64), (2600, 0)])
+def test_jblock_order_and_locus_tile(nstruct, tile_block, monkeypatch):
+    """Forced J-block processing order (tiny L2 budget -> many blocks) and the
+    shared-memory locus-i tile with short CTA blocks; results stay in input order."""
+    from igm_b200 import synthetic
+    monkeypatch.setenv("IGMK_L2_BUDGET", str(24 * 1024 * 7))
+    monkeypatch.setenv("IGMK_ORDER_MIN", "1")
+    monkeypatch.setenv("IGMK_TILE_BLOCK", str(tile_block))
+    pop = synthetic.make_population(2_000_000, nstruct, seed=31 + nstruct, genome_scale=0.03)
+    rng = np.random.default_rng(nstruct + tile_block)
+    nh = pop.n_hap
+    # CSR-like list: runs of equal i with many j, as setup() produces
+    ii = np.repeat(np.arange(0, nh - 1, 2), 9)
+    jj = (ii + 1 + rng.integers(0, nh, len(ii))) % nh
+    k = ii != jj
+    ii, jj = ii[k].astype(np.int32), jj[k].astype(np.int32)
+    lo, hi = np.minimum(ii, jj), np.maximum(ii, jj)
+    nc = pop.copy_index.ncopies()
+    ch = pop.chrom_hap()
+    ok = ~((ch[lo] == ch[hi]) & (nc[lo] != nc[hi]))
+    ii, jj = lo[ok], hi[ok]
+    pw = rng.uniform(0.001, 1.0, len(ii)).astype(np.float32).astype(np.float64)
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, 1, 2.0, MODES[mode])
+            res = eng.actdist(ii, jj, pw, pl, 2.0, 1, mode, 0)
+            _check_against_details(res, dets)
+
+
 def test_degenerate_inputs():
     """Identical coordinates (all distances equal), empty and i == j inputs."""
     from igm_b200.population import CopyIndex, Population
