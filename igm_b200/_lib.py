@@ -33,6 +33,7 @@ EXPORTS = (
     "igmk_upload_coords", "igmk_upload_coords_range", "igmk_set_index",
     "igmk_actdist_device", "igmk_actdist_host", "igmk_expand_records",
     "igmk_contact_counts_device", "igmk_contact_counts_host",
+    "igmk_contact_counts_haploid_device", "igmk_contact_counts_haploid_host",
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms",
 )
 
@@ -66,6 +67,8 @@ def _declare(lib: C.CDLL) -> None:
                                                C.c_int, vp, vp]
     lib.igmk_contact_counts_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                              C.c_int, vp]
+    lib.igmk_contact_counts_haploid_device.argtypes = lib.igmk_contact_counts_device.argtypes
+    lib.igmk_contact_counts_haploid_host.argtypes = lib.igmk_contact_counts_host.argtypes
     lib.igmk_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
     lib.igmk_host_free.argtypes = [vp]
     lib.igmk_last_kernel_ms.argtypes = [vp]

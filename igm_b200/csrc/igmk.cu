@@ -488,12 +488,12 @@ extern "C" int igmk_expand_records(igmk_ctx* c, int64_t n_pairs,
 }
 
 // ------------------------------------------------------------- K2 launches
-extern "C" int igmk_contact_counts_device(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
-                                          float contact_range, int strict,
-                                          uint32_t* d_counts, void* stream) {
+static int contact_launch(igmk_ctx* c, int haploid, int row0, int nrows, int col0, int ncols,
+                          float contact_range, int strict, uint32_t* d_counts, void* stream) {
     if (!c) return fail(IGMK_EINVAL, "igmk_contact_counts: NULL context");
     if (!c->have_coords || !c->have_index) return fail(IGMK_ESTATE, "igmk_contact_counts: upload coordinates and index first");
-    if (row0 < 0 || col0 < 0 || nrows < 0 || ncols < 0 || row0 + nrows > c->nbead || col0 + ncols > c->nbead)
+    const int lim = haploid ? c->n_hap : c->nbead;
+    if (row0 < 0 || col0 < 0 || nrows < 0 || ncols < 0 || row0 + nrows > lim || col0 + ncols > lim)
         return fail(IGMK_EINVAL, "igmk_contact_counts: tile out of range");
     if (nrows == 0 || ncols == 0) return IGMK_OK;
     if (!d_counts) return fail(IGMK_EINVAL, "igmk_contact_counts: NULL output");
@@ -504,15 +504,17 @@ extern "C" int igmk_contact_counts_device(igmk_ctx* c, int row0, int nrows, int 
     P.row0 = row0; P.nrows = nrows; P.col0 = col0; P.ncols = ncols;
     P.contact_range = contact_range; P.strict = strict;
     P.negzero2 = 0x8000000080000000ull;
+    P.hap = c->d_hap; P.haploid = haploid;
     dim3 grid((ncols + kCtTile - 1) / kCtTile, (nrows + kCtTile - 1) / kCtTile);
-    contact_tile_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
+    if (haploid) contact_tile_hap_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
+    else         contact_tile_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return IGMK_OK;
 }
 
-extern "C" int igmk_contact_counts_host(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
-                                        float contact_range, int strict, uint32_t* counts) {
+static int contact_host(igmk_ctx* c, int haploid, int row0, int nrows, int col0, int ncols,
+                        float contact_range, int strict, uint32_t* counts) {
     if (!c) return fail(IGMK_EINVAL, "igmk_contact_counts_host: NULL context");
     if (nrows == 0 || ncols == 0) return IGMK_OK;
     if (nrows < 0 || ncols < 0 || !counts) return fail(IGMK_EINVAL, "igmk_contact_counts_host: bad argument");
@@ -521,14 +523,33 @@ extern "C" int igmk_contact_counts_host(igmk_ctx* c, int row0, int nrows, int co
     int rc = ensure(&c->d_stage, &c->stage_bytes, bytes);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    rc = igmk_contact_counts_device(c, row0, nrows, col0, ncols, contact_range, strict,
-                                    (uint32_t*)c->d_stage, c->stream);
+    rc = contact_launch(c, haploid, row0, nrows, col0, ncols, contact_range, strict,
+                        (uint32_t*)c->d_stage, c->stream);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaMemcpyAsync(counts, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
     return IGMK_OK;
+}
+
+extern "C" int igmk_contact_counts_device(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
+                                          float contact_range, int strict,
+                                          uint32_t* d_counts, void* stream) {
+    return contact_launch(c, 0, row0, nrows, col0, ncols, contact_range, strict, d_counts, stream);
+}
+extern "C" int igmk_contact_counts_host(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
+                                        float contact_range, int strict, uint32_t* counts) {
+    return contact_host(c, 0, row0, nrows, col0, ncols, contact_range, strict, counts);
+}
+extern "C" int igmk_contact_counts_haploid_device(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
+                                                  float contact_range, int strict,
+                                                  uint32_t* d_counts, void* stream) {
+    return contact_launch(c, 1, row0, nrows, col0, ncols, contact_range, strict, d_counts, stream);
+}
+extern "C" int igmk_contact_counts_haploid_host(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
+                                                float contact_range, int strict, uint32_t* counts) {
+    return contact_host(c, 1, row0, nrows, col0, ncols, contact_range, strict, counts);
 }
 
 extern "C" int igmk_host_alloc(void** ptr, int64_t bytes) {

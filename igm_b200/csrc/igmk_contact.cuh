@@ -38,6 +38,8 @@ struct ContactParams {
     float contact_range;
     int strict;
     u64 negzero2;          // {-0.0f, -0.0f}, see f2sq()
+    const HapEntry* hap;   // haploid mode: copies of every locus
+    int haploid;           // 0: tile indices are beads, 1: haploid loci (copies summed)
 };
 
 // Full chunks: packed float32x2 arithmetic (two structures per FADD2 / FFMA2,
@@ -97,6 +99,7 @@ __device__ __forceinline__ void contact_accumulate_packed(const float* sa, const
     }
 }
 
+// Bead-level tile: tile indices are bead ids.
 __global__ void __launch_bounds__(kCtThreads, 2)
 contact_tile_kernel(const ContactParams P) {
     __shared__ __align__(16) float s_a[kCtTile * kCtRow];
@@ -159,6 +162,127 @@ contact_tile_kernel(const ContactParams P) {
         __syncthreads();
         if (P.strict) contact_accumulate_packed<true>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
         else          contact_accumulate_packed<false>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
+    }
+
+    // combine the 4 structure slices
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb)
+        {
+#ifndef IGMK_CT_INTCOUNT
+            float c_lo, c_hi;
+            f2split(cnt2[aa][bb], c_lo, c_hi);
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)(int)(c_lo + c_hi));
+#else
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)cnt2[aa][bb]);
+#endif
+        }
+    __syncthreads();
+    for (int e = t; e < kCtTile * kCtTile; e += kCtThreads) {
+        const int a = a_base + (e >> 5), b = b_base + (e & 31);
+        if (a < a_end && b < b_end)
+            P.counts[(size_t)(a - P.row0) * P.ncols + (b - P.col0)] = s_cnt[e];
+    }
+}
+
+
+// Haploid variant: tile indices are haploid loci and the counts of all copy combinations of a locus pair are summed
+// (Contactmatrix.sumCopies() after buildContactMap, HicEvaluationStep.py:109-111):
+//   counts[i][j] = sum over a in copies(i), b in copies(j) of #{s : d2_s(a,b) <= rc2(a,b)}
+__global__ void __launch_bounds__(kCtThreads, 2)
+contact_tile_hap_kernel(const ContactParams P) {
+    constexpr bool HAP = true;
+    __shared__ __align__(16) float s_a[kCtTile * kCtRow];
+    __shared__ __align__(16) float s_b[kCtTile * kCtRow];
+    __shared__ uint32_t s_cnt[kCtTile * kCtTile];
+    __shared__ float s_rc[kCtTile * kCtRcRow];
+    __shared__ int s_ida[2][kCtTile], s_idb[2][kCtTile];     // bead id per copy, -1: absent
+
+    const int t = threadIdx.x;
+    const int pos = t & 63, slice = t >> 6;
+    const int ta = pos >> 3, tb = pos & 7;
+    const int a_base = P.row0 + blockIdx.y * kCtTile;
+    const int b_base = P.col0 + blockIdx.x * kCtTile;
+    const int a_end = P.row0 + P.nrows, b_end = P.col0 + P.ncols;
+
+    for (int e = t; e < kCtTile * kCtTile; e += kCtThreads) s_cnt[e] = 0u;
+    if (HAP && t < 2 * kCtTile) {
+        const int side = t >> 5, k = t & 31;
+        const int idx = (side ? b_base : a_base) + k;
+        const bool in = idx < (side ? b_end : a_end);
+        int id0 = -1, id1 = -1;
+        if (in) {
+            const int4 h = __ldg(reinterpret_cast<const int4*>(P.hap + idx));
+            id0 = h.x; id1 = h.y;
+        }
+        if (side) { s_idb[0][k] = id0; s_idb[1][k] = id1; }
+        else      { s_ida[0][k] = id0; s_ida[1][k] = id1; }
+    }
+    u64 cnt2[4][4];        // {even, odd structures} hit counts as floats (exact: < 2^24)
+#pragma unroll
+    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) cnt2[aa][bb] = 0ull;
+
+    const size_t row = (size_t)3 * P.npad;
+    constexpr int ncopy = HAP ? 2 : 1;
+    const float qn = __int_as_float(0x7fffffff);
+    for (int ca = 0; ca < ncopy; ++ca)
+    for (int cb = 0; cb < ncopy; ++cb) {
+        __syncthreads();                                   // ids visible / previous combination done
+        // squared cut-offs of the tile (float32, as the A-step computes rcutsq)
+        for (int e = t; e < kCtTile * kCtTile; e += kCtThreads) {
+            int a, b;
+            if (HAP) { a = s_ida[ca][e >> 5]; b = s_idb[cb][e & 31]; }
+            else {
+                a = a_base + (e >> 5); b = b_base + (e & 31);
+                a = (a < a_end) ? a : -1; b = (b < b_end) ? b : -1;
+            }
+            const float ra = (a >= 0) ? __ldg(P.radii + a) : 0.f;
+            const float rb = (b >= 0) ? __ldg(P.radii + b) : 0.f;
+            const float r = __fmul_rn(P.contact_range, __fadd_rn(ra, rb));
+            s_rc[(e >> 5) * kCtRcRow + (e & 31)] = __fmul_rn(r, r);
+        }
+        for (int s0 = 0; s0 < P.nstruct; s0 += kCtStruct) {
+            __syncthreads();
+            // stage 32 beads x 3 components x 32 structures of each side
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int f = t + kCtThreads * k;          // 0 .. 767
+                const int bead = f / 24, rem = f - bead * 24;
+                const int comp = rem >> 3, v4 = rem & 7;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                int a, b;
+                if (HAP) { a = s_ida[ca][bead]; b = s_idb[cb][bead]; }
+                else {
+                    a = a_base + bead; b = b_base + bead;
+                    a = (a < a_end) ? a : -1; b = (b < b_end) ? b : -1;
+                }
+                const size_t so = coord_off(s0 + 4 * v4) + (size_t)comp * kSeg;
+                // absent beads (outside the tile / haploid locus without a second copy)
+                // and structures past the end of the population: NaN on the row side,
+                // so their d2 is NaN and never counts (the padding in HBM is zero)
+                float4 va = (a >= 0)
+                    ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)a * row + so))
+                    : make_float4(qn, qn, qn, qn);
+                const int sv = s0 + 4 * v4;
+                if (sv + 3 >= P.nstruct) {
+                    if (sv >= P.nstruct) va.x = qn;
+                    if (sv + 1 >= P.nstruct) va.y = qn;
+                    if (sv + 2 >= P.nstruct) va.z = qn;
+                    va.w = qn;
+                }
+                const float4 vb = (b >= 0)
+                    ? __ldg(reinterpret_cast<const float4*>(P.coords + (size_t)b * row + so))
+                    : (HAP ? make_float4(qn, qn, qn, qn) : z);
+                *reinterpret_cast<float4*>(s_a + bead * kCtRow + comp * kCtStruct + 4 * v4) = va;
+                *reinterpret_cast<float4*>(s_b + bead * kCtRow + comp * kCtStruct + 4 * v4) = vb;
+            }
+            __syncthreads();
+            if (P.strict) contact_accumulate_packed<true>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
+            else          contact_accumulate_packed<false>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
+        }
     }
 
     // combine the 4 structure slices

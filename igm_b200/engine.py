@@ -163,6 +163,21 @@ class ActdistEngine:
                                                    int(ncols), float(np.float32(contact_range)),
                                                    1 if strict else 0, ptr(d_counts), stream or None))
 
+    def contact_counts_haploid(self, row0: int, nrows: int, col0: int, ncols: int,
+                               contact_range: float = 2.0, strict: bool = False) -> np.ndarray:
+        """Copy-summed counts for a tile of haploid loci (sumCopies of the bead map)."""
+        out = np.zeros((nrows, ncols), dtype=np.uint32)
+        check(self._lib.igmk_contact_counts_haploid_host(self._ctx, int(row0), int(nrows), int(col0),
+                                                         int(ncols), float(np.float32(contact_range)),
+                                                         1 if strict else 0, ptr(out)))
+        return out
+
+    def contact_counts_haploid_device(self, row0, nrows, col0, ncols, d_counts, contact_range=2.0,
+                                      strict=False, stream: int = 0) -> None:
+        check(self._lib.igmk_contact_counts_haploid_device(self._ctx, int(row0), int(nrows), int(col0),
+                                                           int(ncols), float(np.float32(contact_range)),
+                                                           1 if strict else 0, ptr(d_counts), stream or None))
+
     def last_kernel_ms(self) -> float:
         return float(self._lib.igmk_last_kernel_ms(self._ctx))
 

@@ -106,8 +106,10 @@ class Population:
             radii = np.asarray(f["radii"][:], dtype=np.float32)
             chrom = np.asarray(f["index"]["chrom"][:], dtype=np.int32)
             ci = f["index"]["copy_index"][()]
-            if isinstance(ci, bytes):
-                ci = ci.decode("utf-8")
+            if isinstance(ci, np.ndarray):            # fixed-length string dataset (save_hss)
+                ci = ci.tobytes() if ci.dtype.kind in "SV" else ci.item()
+            if isinstance(ci, (bytes, np.bytes_)):
+                ci = bytes(ci).rstrip(b"\x00").decode("utf-8")
             copy = np.asarray(f["index"]["copy"][:], dtype=np.int32)
         return cls(crd, radii, chrom, CopyIndex.from_dict(json.loads(ci)), copy)
 

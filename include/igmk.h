@@ -125,6 +125,20 @@ int igmk_contact_counts_device(igmk_ctx* ctx, int row0, int nrows, int col0, int
 int igmk_contact_counts_host(igmk_ctx* ctx, int row0, int nrows, int col0, int ncols,
                              float contact_range, int strict, uint32_t* counts);
 
+/* The same counts summed over the copies of each haploid locus - what
+ * Contactmatrix.sumCopies() makes of the bead-level map
+ * (igm/steps/HicEvaluationStep.py:109-111; igm/report/hic.py:51 reads the
+ * haploid matrix of get_simulated_hic):
+ *   counts[(i - row0) * ncols + (j - col0)] =
+ *       sum over a in copies(i), b in copies(j) of #{s : d2_s(a,b) <= (cr*(r_a+r_b))^2}
+ * Row / column indices are haploid loci in [0, n_hap).  alabtools is not in the
+ * reference tree: the normalisation of sumCopies is UNPINNED. */
+int igmk_contact_counts_haploid_device(igmk_ctx* ctx, int row0, int nrows, int col0, int ncols,
+                                       float contact_range, int strict,
+                                       uint32_t* d_counts, void* stream);
+int igmk_contact_counts_haploid_host(igmk_ctx* ctx, int row0, int nrows, int col0, int ncols,
+                                     float contact_range, int strict, uint32_t* counts);
+
 /* Pinned host memory for zero-staging transfers (optional). */
 int igmk_host_alloc(void** ptr, int64_t bytes);
 int igmk_host_free(void* ptr);

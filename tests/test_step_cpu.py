@@ -9,7 +9,9 @@ import scipy.sparse
 
 from igm_b200 import hdf5, synthetic
 from igm_b200.population import ProbMatrix
-from igm_b200.steps import ActivationDistanceStep as S
+import importlib
+
+S = importlib.import_module("igm_b200.steps.ActivationDistanceStep")   # the module (the package exports the class)
 from igm_b200.steps._compat import Config
 from oracle import actdist_oracle as orc
 from tests import helpers as H
