@@ -252,11 +252,19 @@ def main():
     mine = gather[rank]
     stream = torch.cuda.current_stream().cuda_stream
 
+    # N > 1: the kernel stores its results straight into every GPU's gather buffer
+    # over NVLink (peer-mapped memory); NCCL all-gather is the fallback
+    from igm_b200.dist import PeerGather, peer_gather_available
+    pg = PeerGather(n_pairs, rank, world, dev) if (world > 1 and peer_gather_available(world)) else None
+
     def step():
+        if pg is not None:
+            return pg.step(eng, d_i, d_j, d_pw, d_pl, n_pairs, 2.0, args.it_corr, args.mode, stream)
         eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode,
                            stream=stream)
         if world > 1:
             dist.all_gather_into_tensor(gather.view(world * n_pairs, 32), mine)
+        return gather
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -274,13 +282,24 @@ def main():
     l0 = launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     ev[0].record()
+    last = gather
     for k in range(args.steps):
         ev[2 * k + 1].record()
-        eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode,
-                           stream=stream)
-        ev[2 * k + 2].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gather.view(world * n_pairs, 32), mine)
+        if pg is not None:
+            b = pg.k % len(pg.bufs)
+            pg.k += 1
+            eng.actdist_device_peers(d_i, d_j, d_pw, d_pl, pg.peer_slices[b], world, n_pairs, 2.0,
+                                     args.it_corr, args.mode, stream)
+            ev[2 * k + 2].record()
+            pg.hdls[b].barrier()
+            eng.finish_results(pg.bufs[b], world * n_pairs, stream)
+            last = pg.bufs[b]
+        else:
+            eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode,
+                               stream=stream)
+            ev[2 * k + 2].record()
+            if world > 1:
+                dist.all_gather_into_tensor(gather.view(world * n_pairs, 32), mine)
     ev[-1].record()
     torch.cuda.synchronize()
     sampler.mark_stop()
@@ -305,7 +324,7 @@ def main():
         from oracle import actdist_oracle as orc
         rng = np.random.default_rng(1)
         sel = np.sort(rng.choice(n_pairs, size=min(300, n_pairs), replace=False))
-        got = mine.cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)[sel]
+        got = last[rank].cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)[sel]
         hap_needed = np.unique(np.concatenate([ii[sel], jj[sel]]))
         beads = np.unique(np.concatenate([ci[h] for h in hap_needed]))
         remap = -np.ones(nbead, np.int64)
@@ -370,8 +389,10 @@ def main():
                                                   args.mode, args.sigma, n_pairs),
                 "pairs_per_gpu": n_pairs, "nstruct": args.nstruct, "nbead": nbead,
                 "pair_structs_per_s": value * args.nstruct,
-                "parallelism": "pairs sharded over %d GPU(s), coordinates replicated, one NCCL "
-                               "all-gather of results" % world,
+                "parallelism": "pairs sharded over %d GPU(s), coordinates replicated, %s" % (
+                    world, "results stored into every GPU's gather buffer from inside the kernel "
+                    "(NVLink peer stores) + one barrier" if pg is not None else
+                    "one NCCL all-gather of results"),
                 "l2": "inputs larger than L2 (coordinates %.0f MB, pair list %.0f MB)" % (
                     nbead * 3 * eng.nstruct * 4 / 1e6, n_pairs * 24 / 1e6),
                 "parity_sample_ok": parity,

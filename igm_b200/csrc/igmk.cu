@@ -226,6 +226,7 @@ extern "C" int igmk_set_index(igmk_ctx* c, int n_hap, const int32_t* copy_ptr,
 
 // ------------------------------------------------------------- K1 launches
 static int launch_finish(const ActdistParams& P, cudaStream_t st) {
+    if (P.n_peers > 0) return IGMK_OK;      // raw results went to the peers; each GPU finishes its gather buffer
     const long long blocks = (P.n_pairs + 255) / 256;
     finish_results_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.out, P.n_pairs);
     g_launches++;
@@ -343,17 +344,19 @@ static int order_pairs(igmk_ctx* c, int64_t n_pairs, const int32_t* d_j, cudaStr
     return IGMK_OK;
 }
 
-extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
-                                   const int32_t* d_i, const int32_t* d_j,
-                                   const double* d_pwish, const double* d_plast,
-                                   float contact_range, int it_corr, int mode, int algo,
-                                   igmk_pair_result* d_out, void* stream) {
+static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
+                          const int32_t* d_i, const int32_t* d_j,
+                          const double* d_pwish, const double* d_plast,
+                          float contact_range, int it_corr, int mode, int algo,
+                          igmk_pair_result* d_out, const uint64_t* d_peers, int n_peers, void* stream) {
     if (!c) return fail(IGMK_EINVAL, "igmk_actdist: NULL context");
     if (!c->have_coords || !c->have_index) return fail(IGMK_ESTATE, "igmk_actdist: upload coordinates and index first");
     if (n_pairs < 0) return fail(IGMK_EINVAL, "igmk_actdist: negative n_pairs");
     if (mode != IGMK_MODE_LB && mode != IGMK_MODE_GP) return fail(IGMK_EINVAL, "igmk_actdist: bad mode %d", mode);
     if (n_pairs == 0) return IGMK_OK;
-    if (!d_i || !d_j || !d_pwish || !d_plast || !d_out) return fail(IGMK_EINVAL, "igmk_actdist: NULL buffer");
+    if (!d_i || !d_j || !d_pwish || !d_plast || (!d_out && n_peers == 0)) return fail(IGMK_EINVAL, "igmk_actdist: NULL buffer");
+    if (n_peers < 0 || n_peers > 32 || (n_peers > 0 && (!d_peers || algo != IGMK_ALGO_FAST)))
+        return fail(IGMK_EINVAL, "igmk_actdist: bad peer table");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     ActdistParams P;
@@ -363,6 +366,7 @@ extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
     P.n_hap = c->n_hap; P.contact_range = contact_range; P.it_corr = it_corr; P.mode = mode;
     P.negzero2 = 0x8000000080000000ull;
     P.perm = nullptr;
+    P.peers = (const u64*)d_peers; P.n_peers = n_peers;
     P.tile_block = 0;
     P.tile_slots = 0;
 
@@ -395,6 +399,35 @@ extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
     T = (T + 31) / 32 * 32;
     if (T <= 320) return launch_block<320>(c, P, T, st);
     return launch_block<512>(c, P, T, st);
+}
+
+extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
+                                   const int32_t* d_i, const int32_t* d_j,
+                                   const double* d_pwish, const double* d_plast,
+                                   float contact_range, int it_corr, int mode, int algo,
+                                   igmk_pair_result* d_out, void* stream) {
+    return actdist_launch(c, n_pairs, d_i, d_j, d_pwish, d_plast, contact_range, it_corr, mode, algo,
+                          d_out, nullptr, 0, stream);
+}
+
+extern "C" int igmk_actdist_device_peers(igmk_ctx* c, int64_t n_pairs,
+                                         const int32_t* d_i, const int32_t* d_j,
+                                         const double* d_pwish, const double* d_plast,
+                                         float contact_range, int it_corr, int mode,
+                                         const uint64_t* d_peer_slices, int n_peers, void* stream) {
+    return actdist_launch(c, n_pairs, d_i, d_j, d_pwish, d_plast, contact_range, it_corr, mode,
+                          IGMK_ALGO_FAST, nullptr, d_peer_slices, n_peers, stream);
+}
+
+extern "C" int igmk_finish_results_device(igmk_ctx* c, igmk_pair_result* d_results, int64_t n, void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_finish_results: NULL context");
+    if (n < 0 || (n > 0 && !d_results)) return fail(IGMK_EINVAL, "igmk_finish_results: bad argument");
+    if (n == 0) return IGMK_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    finish_results_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_results, n);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
 }
 
 extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,

@@ -503,9 +503,8 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
     const int i = __ldg(P.pi + pair), j = __ldg(P.pj + pair);
     const PairDesc d = make_pair_desc(P, i, j);
-    igmk_pair_result* out = P.out + pair;
     if (!d.valid) {                        // uniform over the group
-        if (g.tid == 0) write_empty(out);
+        emit_empty(P, g.tid, pair);
         return;
     }
     const double pwish = __ldg(P.pwish + pair), plast = __ldg(P.plast + pair);
@@ -547,7 +546,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     int o;
     compute_p_o(cnt, d.keep, P.nstruct, pwish, plast, P.it_corr, p, o);
     if (o < 0) {
-        if (g.tid == 0) write_result(out, d, 0u, cnt, -1, 0.0);
+        emit_result(P, g.tid, pair, d, 0u, cnt, -1, 0.0);
         return;
     }
 
@@ -596,7 +595,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
         const uint32_t vlo = (lo << 16) | l2, vhi = (lo << 16) | h2;
         if ((ch - cb) > g.cap) {
             // l2 == h2: every remaining candidate has the same bit pattern.
-            if (g.tid == 0) write_result(out, d, vlo, cnt, o, p);
+            emit_result(P, g.tid, pair, d, vlo, cnt, o, p);
             return;
         }
         g.sync();
@@ -614,7 +613,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     // ---- exact rank inside one warp: the (o - cb)-th smallest candidate
     if (g.leader_warp()) {
         const uint32_t ans = warp_select(g.list, n_list, o - cb, g.tid & 31);
-        if ((g.tid & 31) == 0) write_result(out, d, ans, cnt, o, p);
+        emit_result(P, g.tid, pair, d, ans, cnt, o, p);
     }
 }
 

@@ -55,6 +55,8 @@ struct ActdistParams {
     float contact_range;      // already float32 (NEP-50: python float * f32 -> f32)
     int   it_corr;
     int   mode;
+    const u64* peers;         // multi-GPU: where this rank's result slice starts in each GPU's gather buffer
+    int   n_peers;            // 0: results go to `out` only
     const int32_t* perm;      // processing order (NULL: input order), see igmk.cu order_pairs()
     int   tile_slots;         // 1 or 2 locus-i tiles per CTA
     int   tile_block;         // warp kernel: pairs per CTA-contiguous block; 0 = no locus-i tile in shared memory
@@ -217,19 +219,44 @@ __device__ __forceinline__ float round4_to_f32(double x) {
 
 // Raw per-pair result; dist / prob (the 4-decimal text round trip) are filled in
 // by finish_results_kernel, one thread per pair.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                              uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
+// One 256-bit store per record (sm_100 STG.256): a single NVLink packet when the
+// destination is a peer GPU's gather buffer.
 __device__ __forceinline__ void write_result(igmk_pair_result* out, const PairDesc& d,
                                              uint32_t d2_bits, int count, int o, double p) {
     const int nrec = (o >= 0) ? d.nrec : 0;
     const long long pb = __double_as_longlong(p);
-    uint4* dst = reinterpret_cast<uint4*>(out);
-    dst[0] = make_uint4(d2_bits, (uint32_t)count, (uint32_t)o, (uint32_t)nrec);
-    dst[1] = make_uint4((uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32), 0u, 0u);
+    st_global_256(out, d2_bits, (uint32_t)count, (uint32_t)o, (uint32_t)nrec,
+                  (uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32), 0u, 0u);
+}
+
+// Group-level emit: one thread writes the local result, or - multi-GPU - thread t
+// writes the same 32 bytes straight into GPU t's gather buffer over NVLink (peer
+// stores issued from inside K1: the "all-gather" overlaps the compute and needs no
+// separate collective).  All arguments are uniform over the group.
+__device__ __forceinline__ void emit_result(const ActdistParams& P, int tid, long long pair,
+                                            const PairDesc& d, uint32_t d2_bits, int count, int o, double p) {
+    if (P.n_peers == 0) {
+        if (tid == 0) write_result(P.out + pair, d, d2_bits, count, o, p);
+    } else if (tid < P.n_peers) {
+        write_result(reinterpret_cast<igmk_pair_result*>(__ldg(P.peers + tid)) + pair, d, d2_bits, count, o, p);
+    }
 }
 
 __device__ __forceinline__ void write_empty(igmk_pair_result* out) {
-    uint4* dst = reinterpret_cast<uint4*>(out);
-    dst[0] = make_uint4(0, 0, 0xffffffffu, 0);   // o = -1
-    dst[1] = make_uint4(0, 0, 0, 0);
+    st_global_256(out, 0u, 0u, 0xffffffffu, 0u, 0u, 0u, 0u, 0u);   // o = -1
+}
+
+__device__ __forceinline__ void emit_empty(const ActdistParams& P, int tid, long long pair) {
+    if (P.n_peers == 0) {
+        if (tid == 0) write_empty(P.out + pair);
+    } else if (tid < P.n_peers) {
+        write_empty(reinterpret_cast<igmk_pair_result*>(__ldg(P.peers + tid)) + pair);
+    }
 }
 
 __global__ void __launch_bounds__(256)

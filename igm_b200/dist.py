@@ -11,6 +11,7 @@ writes each rank's results straight into its slice of the all-gather buffer.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Tuple
 
 import numpy as np
@@ -52,6 +53,75 @@ def run_sharded(compute_shard: Callable, n_pairs: int, rank: int, world: int, de
         else:
             dist.all_gather_into_tensor(flat, full[rank].clone(), group=group)
     return full, per, bounds
+
+
+class PeerGather:
+    """Gather buffers the A-step kernel writes into directly over NVLink.
+
+    Every rank owns `nbuf` buffers of shape (world, per, 32) uint8 in peer-mapped
+    ("symmetric") device memory.  igmk_actdist_device_peers stores each raw pair
+    result of rank r into slice [r] of the current buffer of EVERY rank from inside
+    the kernel, so by the time the kernel ends the all-gather has already happened;
+    what is left is one cross-rank barrier and the per-GPU finish pass (dist / prob).
+    Alternating between two buffers makes that single barrier per step sufficient:
+    a rank can only start writing buffer b again after every rank has passed the
+    barrier of the step that last read it.
+
+    torch supplies the plumbing (symmetric allocation, rendezvous, barrier)."""
+
+    def __init__(self, per: int, rank: int, world: int, device, group=None, nbuf: int = 2):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        name = grp.group_name
+        if hasattr(symm, "enable_symm_mem_for_group"):
+            try:
+                symm.enable_symm_mem_for_group(name)
+            except Exception:
+                pass
+        self.rank, self.world, self.per = rank, world, max(per, 1)
+        self.bufs, self.hdls, self.peer_slices = [], [], []
+        for _ in range(nbuf):
+            buf = symm.empty((world, self.per, RESULT_BYTES), dtype=torch.uint8, device=device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, name)
+            off = rank * self.per * RESULT_BYTES
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.peer_slices.append(torch.tensor([int(p) + off for p in hdl.buffer_ptrs],
+                                                 dtype=torch.int64, device=device))
+        self.k = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=grp)
+
+    def step(self, eng, d_i, d_j, d_pw, d_pl, n_pairs: int, contact_range=2.0, it_corr=0, mode="LB",
+             stream: int = 0):
+        """One sharded A-step: kernel with peer stores -> barrier -> finish.  Returns
+        the (world, per, 32) uint8 tensor holding every rank's results (valid once the
+        stream has been synchronised)."""
+        b = self.k % len(self.bufs)
+        self.k += 1
+        eng.actdist_device_peers(d_i, d_j, d_pw, d_pl, self.peer_slices[b], self.world, n_pairs,
+                                 contact_range, it_corr, mode, stream)
+        self.hdls[b].barrier()
+        eng.finish_results(self.bufs[b], self.world * self.per, stream)
+        return self.bufs[b]
+
+
+def peer_gather_available(world: int = 0) -> bool:
+    """In-kernel peer stores beat NCCL's all-gather from 4 GPUs up (measured on
+    8 x B200, config 2: 1.648 vs 1.608 G pairs/s; at 2 GPUs 431 vs 440 M)."""
+    if world and world < 4 and os.environ.get("IGMK_PEER_GATHER", "") != "1":
+        return False
+    try:
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory  # noqa: F401
+        return (torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+                and os.environ.get("IGMK_NO_PEER_GATHER", "0") != "1")
+    except Exception:
+        return False
 
 
 def gathered_to_results(full, per: int, bounds) -> np.ndarray:

@@ -132,6 +132,21 @@ class ActdistEngine:
                                             ptr(d_plast), float(np.float32(contact_range)), int(it_corr),
                                             _MODES[mode], int(algo), ptr(d_out), stream or None))
 
+    def actdist_device_peers(self, d_i, d_j, d_pwish, d_plast, d_peer_slices, n_peers: int,
+                             n_pairs: Optional[int] = None, contact_range: float = 2.0,
+                             it_corr: int = 0, mode="LB", stream: int = 0) -> None:
+        """Multi-GPU form: raw results are stored into every GPU's gather buffer from
+        inside the kernel (d_peer_slices: device int64 array of n_peers addresses);
+        finish_results() must follow a cross-rank barrier."""
+        n = int(n_pairs if n_pairs is not None else d_i.numel())
+        check(self._lib.igmk_actdist_device_peers(self._ctx, n, ptr(d_i), ptr(d_j), ptr(d_pwish),
+                                                  ptr(d_plast), float(np.float32(contact_range)),
+                                                  int(it_corr), _MODES[mode], ptr(d_peer_slices),
+                                                  int(n_peers), stream or None))
+
+    def finish_results(self, d_results, n: int, stream: int = 0) -> None:
+        check(self._lib.igmk_finish_results_device(self._ctx, ptr(d_results), int(n), stream or None))
+
     def expand_records(self, i, j, res) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
         """Pair results -> (row, col, dist, prob), the four actdist.hdf5 columns."""
         i = np.ascontiguousarray(i, dtype=np.int32)

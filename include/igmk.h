@@ -103,6 +103,25 @@ int igmk_actdist_host(igmk_ctx* ctx, int64_t n_pairs,
                       float contact_range, int it_corr, int mode, int algo,
                       igmk_pair_result* out);
 
+/* Multi-GPU form (one process per GPU, pairs sharded, coordinates replicated;
+ * the reference farms 1000-pair batches to CPU workers and meets again on the
+ * shared filesystem, igm/steps/ActivationDistanceStep.py:181-194,
+ * igm/core/step.py:274): the kernel stores every raw pair result straight into
+ * the gather buffers of all n_peers GPUs over NVLink (peer stores from inside the
+ * kernel, so the all-gather overlaps the compute and no collective follows).
+ * d_peer_slices: device array of n_peers addresses - where THIS rank's slice of
+ * igmk_pair_result records starts in GPU p's gather buffer (peer-mapped memory,
+ * e.g. torch symmetric memory).  dist / prob are NOT filled in: after a barrier
+ * across ranks every GPU calls igmk_finish_results_device on its whole buffer. */
+int igmk_actdist_device_peers(igmk_ctx* ctx, int64_t n_pairs,
+                              const int32_t* d_i, const int32_t* d_j,
+                              const double* d_pwish, const double* d_plast,
+                              float contact_range, int it_corr, int mode,
+                              const uint64_t* d_peer_slices, int n_peers, void* stream);
+/* dist / prob (float64 sqrt + the reference's 4-decimal text round trip,
+ * ActivationDistanceStep.py:38,230,249,473) for n raw results in device memory. */
+int igmk_finish_results_device(igmk_ctx* ctx, igmk_pair_result* d_results, int64_t n, void* stream);
+
 /* Record expansion of task()/reduce() (ActivationDistanceStep.py:221-222,
  * 476-483, 249-257): pair results -> the four actdist.hdf5 columns, reference
  * order.  Host pointers; row/col/dist/prob must hold sum(nrec) entries;
