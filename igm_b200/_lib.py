@@ -33,6 +33,7 @@ EXPORTS = (
     "igmk_upload_coords", "igmk_upload_coords_range", "igmk_set_index",
     "igmk_actdist_device", "igmk_actdist_host", "igmk_actdist_device_peers",
     "igmk_finish_results_device", "igmk_expand_records",
+    "igmk_damid_actdist_device", "igmk_damid_actdist_host",
     "igmk_contact_counts_device", "igmk_contact_counts_host",
     "igmk_contact_counts_haploid_device", "igmk_contact_counts_haploid_host",
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms",
@@ -65,6 +66,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.igmk_actdist_device_peers.argtypes = [vp, C.c_int64, i32p, i32p, f64p, f64p, C.c_float,
                                               C.c_int, C.c_int, vp, C.c_int, vp]
     lib.igmk_finish_results_device.argtypes = [vp, vp, C.c_int64, vp]
+    lib.igmk_damid_actdist_device.argtypes = [vp, C.c_int64, i32p, f32p, f32p, C.c_double, C.c_double,
+                                              C.c_int, vp, vp]
+    lib.igmk_damid_actdist_host.argtypes = [vp, C.c_int64, i32p, f32p, f32p, C.c_double, C.c_double,
+                                            C.c_int, vp]
     lib.igmk_expand_records.argtypes = [vp, C.c_int64, i32p, i32p, vp, i32p, i32p, f32p, f32p,
                                         C.c_int64, C.POINTER(C.c_int64)]
     lib.igmk_contact_counts_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

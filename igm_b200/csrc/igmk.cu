@@ -105,7 +105,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    const size_t bytes = (size_t)nbead * 3 * c->npad * sizeof(float);
+    // one extra all-zero row behind the population: the "origin bead" of the DamID path
+    const size_t bytes = (size_t)(nbead + 1) * 3 * c->npad * sizeof(float);
     e = cudaMalloc(&c->d_coords, bytes);
     if (e != cudaSuccess) { delete c; return fail(IGMK_ECUDA, "igmk_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
     cudaMemset(c->d_coords, 0, bytes);
@@ -228,19 +229,21 @@ extern "C" int igmk_set_index(igmk_ctx* c, int n_hap, const int32_t* copy_ptr,
 static int launch_finish(const ActdistParams& P, cudaStream_t st) {
     if (P.n_peers > 0) return IGMK_OK;      // raw results went to the peers; each GPU finishes its gather buffer
     const long long blocks = (P.n_pairs + 255) / 256;
-    finish_results_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.out, P.n_pairs);
+    if (P.pexp32) finish_damid_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.out, P.n_pairs);
+    else          finish_results_kernel<<<(unsigned)blocks, 256, 0, st>>>(P.out, P.n_pairs);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return IGMK_OK;
 }
 
+template <bool DAMID>
 static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     const int V = (c->nchunks + 31) / 32;
     // one CTA per SM: two locus-i tiles (2 rows of 12 * npad bytes each) plus as many
     // warps as the key arrays (V KiB per warp) leave room for
     const size_t budget = 208 * 1024;
     const int slots = (c->tile_slots == 1) ? 1 : 2;
-    size_t tile_bytes = (c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)slots * 24 * c->npad : 0;
+    size_t tile_bytes = (!DAMID && c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)slots * 24 * c->npad : 0;
     if (tile_bytes + (size_t)8 * 2 * V * 32 * 16 > budget) tile_bytes = 0;     // keep >= 8 warps
     int warps = (int)((budget - tile_bytes) / ((size_t)2 * V * 32 * 16));
     if (warps > kWarpsPerBlock) warps = kWarpsPerBlock;
@@ -250,31 +253,31 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     P.tile_slots = slots;
     int per_sm = 0;
     const size_t smem = (size_t)warps * 2 * V * 32 * 16 + tile_bytes;
-    CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel, 32 * warps, smem));
+    CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel<DAMID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_warp_kernel<DAMID>, 32 * warps, smem));
     if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_warp_kernel cannot run with V = %d", V);
     long long want = P.tile_block ? (P.n_pairs + P.tile_block - 1) / P.tile_block : (P.n_pairs + warps - 1) / warps;
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((want < cap) ? want : cap);
-    actdist_warp_kernel<<<grid, 32 * warps, smem, st>>>(P, V);
+    actdist_warp_kernel<DAMID><<<grid, 32 * warps, smem, st>>>(P, V);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
 }
 
-template <int MAXT>
+template <int MAXT, bool DAMID>
 static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, cudaStream_t st) {
     const int V = (c->nchunks + threads - 1) / threads;
     int per_sm = 0;
     const size_t smem = (size_t)2 * V * threads * 16;
     if (2 * V > kMaxQuads || smem > 200 * 1024)
         return fail(IGMK_ELIMIT, "igmk_actdist: nstruct = %d exceeds the supported 25600", c->nstruct);
-    CUDA_TRY(cudaFuncSetAttribute(actdist_block_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<MAXT>, threads, smem));
+    CUDA_TRY(cudaFuncSetAttribute(actdist_block_kernel<MAXT, DAMID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_block_kernel<MAXT, DAMID>, threads, smem));
     if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_block_kernel cannot run with %d threads, V = %d", threads, V);
     long long cap = (long long)c->sm_count * per_sm;
     const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
-    actdist_block_kernel<MAXT><<<grid, threads, smem, st>>>(P, V);
+    actdist_block_kernel<MAXT, DAMID><<<grid, threads, smem, st>>>(P, V);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
@@ -344,6 +347,25 @@ static int order_pairs(igmk_ctx* c, int64_t n_pairs, const int32_t* d_j, cudaStr
     return IGMK_OK;
 }
 
+template <bool DAMID>
+static int dispatch_groups(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
+    int T = c->group_threads;
+    if (T == 0) {
+        if (c->nchunks <= 32 * 8) T = 32;
+        else {
+            T = ((c->nchunks + 7) / 8 + 31) / 32 * 32;          // about 8 chunks per thread
+            if (T < 64) T = 64;
+            if (T > 320) T = ((c->nchunks + 319) / 320 <= 12) ? 320 : 512;
+        }
+    }
+    if (T == 32 && c->nchunks <= 32 * 32) return launch_warp<DAMID>(c, P, st);
+    if (T < 64) T = 64;
+    if (T > 512) T = 512;
+    T = (T + 31) / 32 * 32;
+    if (T <= 320) return launch_block<320, DAMID>(c, P, T, st);
+    return launch_block<512, DAMID>(c, P, T, st);
+}
+
 static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
                           const int32_t* d_i, const int32_t* d_j,
                           const double* d_pwish, const double* d_plast,
@@ -367,6 +389,7 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     P.negzero2 = 0x8000000080000000ull;
     P.perm = nullptr;
     P.peers = (const u64*)d_peers; P.n_peers = n_peers;
+    P.pexp32 = nullptr; P.plast32 = nullptr; P.damid_R = 0.0; P.zero_bead = c->nbead;
     P.tile_block = 0;
     P.tile_slots = 0;
 
@@ -384,21 +407,7 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     //                    (T = 512 beyond nstruct = 15360)
     // IGMK_GROUP_THREADS (tuning knob): 0 = default, 32 = force one warp per pair
     // (nstruct <= 4096), otherwise the CTA size to use.
-    int T = c->group_threads;
-    if (T == 0) {
-        if (c->nchunks <= 32 * 8) T = 32;
-        else {
-            T = ((c->nchunks + 7) / 8 + 31) / 32 * 32;          // about 8 chunks per thread
-            if (T < 64) T = 64;
-            if (T > 320) T = ((c->nchunks + 319) / 320 <= 12) ? 320 : 512;
-        }
-    }
-    if (T == 32 && c->nchunks <= 32 * 32) return launch_warp(c, P, st);
-    if (T < 64) T = 64;
-    if (T > 512) T = 512;
-    T = (T + 31) / 32 * 32;
-    if (T <= 320) return launch_block<320>(c, P, T, st);
-    return launch_block<512>(c, P, T, st);
+    return dispatch_groups<false>(c, P, st);
 }
 
 extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,
@@ -427,6 +436,59 @@ extern "C" int igmk_finish_results_device(igmk_ctx* c, igmk_pair_result* d_resul
     finish_results_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_results, n);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+// ------------------------------------------------------------- DamID (next row f1)
+extern "C" int igmk_damid_actdist_device(igmk_ctx* c, int64_t n_loci, const int32_t* d_loci,
+                                         const float* d_pexp, const float* d_plast,
+                                         double nucleus_radius, double contact_range, int it_corr,
+                                         igmk_pair_result* d_out, void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_damid_actdist: NULL context");
+    if (!c->have_coords || !c->have_index) return fail(IGMK_ESTATE, "igmk_damid_actdist: upload coordinates and index first");
+    if (n_loci < 0) return fail(IGMK_EINVAL, "igmk_damid_actdist: negative n_loci");
+    if (n_loci == 0) return IGMK_OK;
+    if (!d_loci || !d_pexp || !d_plast || !d_out) return fail(IGMK_EINVAL, "igmk_damid_actdist: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ActdistParams P;
+    memset(&P, 0, sizeof P);
+    P.coords = c->d_coords; P.hap = c->d_hap;
+    P.pi = d_loci; P.pj = nullptr; P.pwish = nullptr; P.plast = nullptr; P.out = d_out;
+    P.n_pairs = n_loci; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
+    P.n_hap = c->n_hap; P.contact_range = 0.f; P.it_corr = it_corr; P.mode = IGMK_MODE_LB;
+    P.negzero2 = 0x8000000080000000ull;
+    P.pexp32 = d_pexp; P.plast32 = d_plast;
+    P.damid_R = nucleus_radius * (1.0 - contact_range);       // np.array(nucleus_param) * (1 - contact_range), :436
+    P.zero_bead = c->nbead;
+    return dispatch_groups<true>(c, P, (cudaStream_t)stream);
+}
+
+extern "C" int igmk_damid_actdist_host(igmk_ctx* c, int64_t n_loci, const int32_t* loci,
+                                       const float* pexp, const float* plast,
+                                       double nucleus_radius, double contact_range, int it_corr,
+                                       igmk_pair_result* out) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_damid_actdist_host: NULL context");
+    if (n_loci == 0) return IGMK_OK;
+    if (n_loci < 0 || !loci || !pexp || !plast || !out) return fail(IGMK_EINVAL, "igmk_damid_actdist_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)n_loci;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t off_pe = up(n * 4), off_pl = off_pe + up(n * 4), off_out = off_pl + up(n * 4);
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, off_out + n * sizeof(igmk_pair_result));
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, loci, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_pe, pexp, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_pl, plast, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = igmk_damid_actdist_device(c, n_loci, (const int32_t*)base, (const float*)(base + off_pe),
+                                   (const float*)(base + off_pl), nucleus_radius, contact_range, it_corr,
+                                   (igmk_pair_result*)(base + off_out), c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(out, base + off_out, n * sizeof(igmk_pair_result), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
     return IGMK_OK;
 }
 

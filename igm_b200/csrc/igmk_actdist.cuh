@@ -495,24 +495,30 @@ __device__ __forceinline__ void tile_release(const TileCtl& tile, int slot, int 
         asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(tile.words + 4u * slot), "r"(0xffffffffu) : "memory");
 }
 
-template <bool BLOCK>
+// DAMID: the same machinery computes the lamina-DamID activation distance of one
+// locus (igm/steps/DamidActivationDistanceStep.py:375-470, spherical envelope): the
+// "pair" is (locus, origin) - the partner row is the all-zero bead kept behind the
+// population, so d2 is the float32 sum of squares of the coordinates, exactly
+// np.sum(np.square(x), axis=1) - the order statistic is taken in descending order and
+// the probability arithmetic is float32 (see compute_p_o_damid).
+template <bool BLOCK, bool DAMID>
 __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK>& g, int V,
                                              long long slot, const TileCtl& tile) {
     // slot = position in processing order; perm maps it to the pair's index in the
     // caller's list (results stay in input order)
     const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-    const int i = __ldg(P.pi + pair), j = __ldg(P.pj + pair);
-    const PairDesc d = make_pair_desc(P, i, j);
+    const int i = __ldg(P.pi + pair);
+    double extra = 0.0;                    // DAMID: (R - r)^2, handed to the finish pass
+    const PairDesc d = DAMID ? make_damid_desc(P, i, extra) : make_pair_desc(P, i, __ldg(P.pj + pair));
     if (!d.valid) {                        // uniform over the group
         emit_empty(P, g.tid, pair);
         return;
     }
-    const double pwish = __ldg(P.pwish + pair), plast = __ldg(P.plast + pair);
     const PairPtrs pp = pair_ptrs(P, d);
 
     int cnt;
     uint32_t mn2, mx2;
-    const int tslot = (!BLOCK && tile.base) ? tile_acquire(P, tile, i, d, pp, g.tid) : -1;
+    const int tslot = (!BLOCK && !DAMID && tile.base) ? tile_acquire(P, tile, i, d, pp, g.tid) : -1;
     if (tslot >= 0) {
         const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
         const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
@@ -543,10 +549,21 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     g.sum_min_max(cnt, kmin, kmax);
 
     double p;
-    int o;
-    compute_p_o(cnt, d.keep, P.nstruct, pwish, plast, P.it_corr, p, o);
+    int o;                                 // ascending index of the element to select
+    int o_rep;                             // index reported to the caller
+    if (DAMID) {
+        const int M = d.keep * P.nstruct;
+        float pf;
+        cnt = M - cnt;                     // #{d_sq >= 1}: fill counted s <= largest float32 below (R-r)^2
+        compute_p_o_damid(cnt, M, __ldg(P.pexp32 + pair), __ldg(P.plast32 + pair), P.it_corr, pf, o_rep);
+        p = (double)pf;
+        o = (o_rep >= 0) ? M - 1 - o_rep : -1;     // d_sq[::-1].sort(): descending order statistic
+    } else {
+        compute_p_o(cnt, d.keep, P.nstruct, __ldg(P.pwish + pair), __ldg(P.plast + pair), P.it_corr, p, o);
+        o_rep = o;
+    }
     if (o < 0) {
-        emit_result(P, g.tid, pair, d, 0u, cnt, -1, 0.0);
+        emit_result(P, g.tid, pair, d, 0u, cnt, -1, 0.0, extra);
         return;
     }
 
@@ -595,7 +612,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
         const uint32_t vlo = (lo << 16) | l2, vhi = (lo << 16) | h2;
         if ((ch - cb) > g.cap) {
             // l2 == h2: every remaining candidate has the same bit pattern.
-            emit_result(P, g.tid, pair, d, vlo, cnt, o, p);
+            emit_result(P, g.tid, pair, d, vlo, cnt, o_rep, p, extra);
             return;
         }
         g.sync();
@@ -613,7 +630,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     // ---- exact rank inside one warp: the (o - cb)-th smallest candidate
     if (g.leader_warp()) {
         const uint32_t ans = warp_select(g.list, n_list, o - cb, g.tid & 31);
-        emit_result(P, g.tid, pair, d, ans, cnt, o, p);
+        emit_result(P, g.tid, pair, d, ans, cnt, o_rep, p, extra);
     }
 }
 
@@ -629,6 +646,7 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
 #endif
 constexpr int kWarpsPerBlock = IGMK_WPB;
 
+template <bool DAMID>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock, IGMK_MINB)
 actdist_warp_kernel(const ActdistParams P, const int V) {
     extern __shared__ uint4 s_keys[];             // [warp][2 V][32] key quads, then 2 locus-i tiles
@@ -672,7 +690,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
             const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
             if (base >= P.n_pairs) break;
             const long long pair = base + r;
-            if (pair < P.n_pairs) process_pair<false>(P, g, V, pair, tile);
+            if (pair < P.n_pairs) process_pair<false, DAMID>(P, g, V, pair, tile);
             __syncwarp();
         }
         return;
@@ -680,7 +698,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     const long long stride = (long long)gridDim.x * nwarps;
     for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < P.n_pairs;
          pair += stride) {
-        process_pair<false>(P, g, V, pair, tile);
+        process_pair<false, DAMID>(P, g, V, pair, tile);
         __syncwarp();
     }
 }
@@ -688,7 +706,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
 // G = blockDim.x (multiple of 32, <= MAXT): one pair per CTA, two CTAs per SM.
 // MAXT = 320 leaves 96 registers per thread (all 12 row loads of a chunk in
 // flight at once); MAXT = 512 (64 registers) is for very large populations.
-template <int MAXT>
+template <int MAXT, bool DAMID>
 __global__ void __launch_bounds__(MAXT, 2)
 actdist_block_kernel(const ActdistParams P, const int V) {
     extern __shared__ uint4 s_keys[];             // [2 V][blockDim] key quads
@@ -708,7 +726,7 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;
     for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
-        process_pair<true>(P, g, V, pair, tile);
+        process_pair<true, DAMID>(P, g, V, pair, tile);
         __syncthreads();
     }
 }

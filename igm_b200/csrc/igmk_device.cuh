@@ -55,6 +55,10 @@ struct ActdistParams {
     float contact_range;      // already float32 (NEP-50: python float * f32 -> f32)
     int   it_corr;
     int   mode;
+    const float* pexp32;      // DamID: p_exp / plast of the float32 batch file
+    const float* plast32;
+    double damid_R;           // DamID: nucleus_radius * (1 - contact_range), float64
+    int   zero_bead;          // DamID: index of the all-zero row behind the population
     const u64* peers;         // multi-GPU: where this rank's result slice starts in each GPU's gather buffer
     int   n_peers;            // 0: results go to `out` only
     const int32_t* perm;      // processing order (NULL: input order), see igmk.cu order_pairs()
@@ -73,6 +77,7 @@ struct PairDesc {
     int   keep;             // n_possible_contacts: values kept per structure
     int   nrec;             // records the pair expands to when p > 0
     int   valid;            // 0: i == j / out of range -> empty result
+    int   always_rec;       // DamID: records are written even when p <= 0
     float rcutsq;
 };
 
@@ -90,7 +95,7 @@ __device__ __forceinline__ PairDesc make_pair_desc(const ActdistParams& P, int i
     PairDesc d;
     d.valid = (i != j) && i >= 0 && j >= 0 && i < P.n_hap && j < P.n_hap;
     d.a0 = d.a1 = d.b0 = d.b1 = -1;
-    d.cmask = 0; d.keep = 0; d.nrec = 0; d.rcutsq = 0.f;
+    d.cmask = 0; d.keep = 0; d.nrec = 0; d.rcutsq = 0.f; d.always_rec = 0;
     if (!d.valid) return d;
     const int4 ha = __ldg(reinterpret_cast<const int4*>(P.hap + i));
     const int4 hb = __ldg(reinterpret_cast<const int4*>(P.hap + j));
@@ -117,6 +122,66 @@ __device__ __forceinline__ PairDesc make_pair_desc(const ActdistParams& P, int i
     }
     d.nrec = intra ? ((na < nb) ? na : nb) : na * nb;
     return d;
+}
+
+// DamID "pair" (locus I, origin): copies of I against the all-zero bead
+// (DamidActivationDistanceStep.py:424-438).  D = (R - r)^2 in float64; a value is "in
+// contact with the lamina" when float64(s) / D >= 1.0 (:441,:449), which for a
+// correctly rounded division is exactly s >= D - so the fill counts s <= T with T the
+// largest float32 below D and the caller takes the complement.
+__device__ __forceinline__ PairDesc make_damid_desc(const ActdistParams& P, int I, double& D) {
+    PairDesc d;
+    d.valid = I >= 0 && I < P.n_hap;
+    d.a0 = d.a1 = d.b0 = d.b1 = -1;
+    d.cmask = 0; d.keep = 0; d.nrec = 0; d.rcutsq = 0.f; d.always_rec = 1;
+    D = 0.0;
+    if (!d.valid) return d;
+    const int4 ha = __ldg(reinterpret_cast<const int4*>(P.hap + I));
+    d.a0 = ha.x; d.a1 = ha.y; d.b0 = P.zero_bead;
+    const int na = (d.a1 >= 0) ? 2 : 1;
+    d.cmask = CM_D0 | (na == 2 ? CM_D2 : 0);
+    d.keep = na;
+    d.nrec = na;
+    const double x = __dsub_rn(P.damid_R, (double)__int_as_float(ha.w));
+    D = __dmul_rn(x, x);
+    float t = __double2float_rd(D);                     // largest float32 <= D
+    if ((double)t >= D) t = __uint_as_float(__float_as_uint(t) - 1u);   // strictly below (D > 0)
+    d.rcutsq = (D > 0.0) ? t : __int_as_float(0xff800000);             // D == 0: everything is in contact
+    return d;
+}
+
+// cleanProbability + order index of get_damid_actdist_I (:445-466) with the types
+// NumPy >= 2 gives them: p_exp / plast are np.float32 (float32 batch file), pnow is a
+// Python float, so every operation that involves p_exp or plast is float32; only
+// `1.0 - t` with t = pnow (plast >= 1 branch) is float64, rounded to float32 when it
+// meets p_exp.  o_desc = -1 when p <= 0.
+__device__ __forceinline__ void compute_p_o_damid(int cnt_ge, int M, float p_exp, float plast,
+                                                  int it_corr, float& p, int& o_desc) {
+    if (it_corr == 1) {
+        const double pnow = __ddiv_rn((double)cnt_ge, (double)M);
+        float num, den;
+        if (plast < 1.0f) {
+            float t = __fdiv_rn(__fsub_rn((float)pnow, plast), __fsub_rn(1.0f, plast));
+            t = (t > 0.0f) ? t : 0.0f;                                   // max(0, t)
+            if (t < 1.0f) { num = __fsub_rn(p_exp, t); den = __fsub_rn(1.0f, t); p = __fdiv_rn(num, den); }
+            else p = p_exp;
+        } else {
+            const double t = (pnow > 0.0) ? pnow : 0.0;                  // Python float
+            if (t < 1.0) { num = __fsub_rn(p_exp, (float)t); den = (float)__dsub_rn(1.0, t); p = __fdiv_rn(num, den); }
+            else p = p_exp;
+        }
+    } else {
+        p = p_exp;
+    }
+    o_desc = -1;
+    if (p > 0.0f) {
+        const float x = __fmul_rn((float)M, p);                          // n_copies * n_struct * p in float32
+        const float r = rintf(x);                                        // round(): half to even
+        o_desc = (r >= (float)(M - 1)) ? (M - 1) : (int)r;
+        if (o_desc < 0) o_desc = 0;
+    } else {
+        p = 0.0f;
+    }
 }
 
 // Four copy-combination values of one structure -> the `keep` kept values in
@@ -217,6 +282,18 @@ __device__ __forceinline__ float round4_to_f32(double x) {
     return __double2float_rn(__ddiv_rn(r, 1e4));
 }
 
+// float32(float("%.5f" % x)) for x >= 0 (DamID text format, :35,:270,:289)
+__device__ __forceinline__ float round5_to_f32(double x) {
+    const double hi = __dmul_rn(x, 1e5);
+    if (!(hi < 4.0e15)) return __double2float_rn(x);
+    const double lo = __fma_rn(x, 1e5, -hi);
+    double r = rint(hi);
+    const double e = __dsub_rn(hi, r);
+    if (e == 0.5 && lo > 0.0) r += 1.0;
+    else if (e == -0.5 && lo < 0.0) r -= 1.0;
+    return __double2float_rn(__ddiv_rn(r, 1e5));
+}
+
 // Raw per-pair result; dist / prob (the 4-decimal text round trip) are filled in
 // by finish_results_kernel, one thread per pair.
 __device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
@@ -227,11 +304,14 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, u
 // One 256-bit store per record (sm_100 STG.256): a single NVLink packet when the
 // destination is a peer GPU's gather buffer.
 __device__ __forceinline__ void write_result(igmk_pair_result* out, const PairDesc& d,
-                                             uint32_t d2_bits, int count, int o, double p) {
-    const int nrec = (o >= 0) ? d.nrec : 0;
-    const long long pb = __double_as_longlong(p);
+                                             uint32_t d2_bits, int count, int o, double p,
+                                             double extra = 0.0) {
+    // Hi-C: no record when p <= 0 (:464,:485); DamID: every copy gets a record (:468)
+    const int nrec = (o >= 0 || d.always_rec) ? d.nrec : 0;
+    const long long pb = __double_as_longlong(p), eb = __double_as_longlong(extra);
     st_global_256(out, d2_bits, (uint32_t)count, (uint32_t)o, (uint32_t)nrec,
-                  (uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32), 0u, 0u);
+                  (uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32),
+                  (uint32_t)(eb & 0xffffffffll), (uint32_t)((unsigned long long)eb >> 32));
 }
 
 // Group-level emit: one thread writes the local result, or - multi-GPU - thread t
@@ -239,11 +319,12 @@ __device__ __forceinline__ void write_result(igmk_pair_result* out, const PairDe
 // stores issued from inside K1: the "all-gather" overlaps the compute and needs no
 // separate collective).  All arguments are uniform over the group.
 __device__ __forceinline__ void emit_result(const ActdistParams& P, int tid, long long pair,
-                                            const PairDesc& d, uint32_t d2_bits, int count, int o, double p) {
+                                            const PairDesc& d, uint32_t d2_bits, int count, int o, double p,
+                                            double extra = 0.0) {
     if (P.n_peers == 0) {
-        if (tid == 0) write_result(P.out + pair, d, d2_bits, count, o, p);
+        if (tid == 0) write_result(P.out + pair, d, d2_bits, count, o, p, extra);
     } else if (tid < P.n_peers) {
-        write_result(reinterpret_cast<igmk_pair_result*>(__ldg(P.peers + tid)) + pair, d, d2_bits, count, o, p);
+        write_result(reinterpret_cast<igmk_pair_result*>(__ldg(P.peers + tid)) + pair, d, d2_bits, count, o, p, extra);
     }
 }
 
@@ -361,6 +442,25 @@ __device__ __forceinline__ u64 d2pair(const Row6& a, const Row6& b, u64 nz) {
     const u64 dy = f2sub(H ? a.y23 : a.y01, H ? b.y23 : b.y01);
     const u64 dz = f2sub(H ? a.z23 : a.z01, H ? b.z23 : b.z01);
     return f2add(f2add(f2sq(dx, nz), f2sq(dy, nz)), f2sq(dz, nz));
+}
+
+// DamID finish: activation distance sqrt(float64(s) / D) (:441,:466), 2 when p <= 0
+// (:459); 5-decimal text round trip.  D travels in the record's last 8 bytes.
+__global__ void __launch_bounds__(256)
+finish_damid_kernel(igmk_pair_result* out, long long n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4 a = reinterpret_cast<const uint4*>(out + t)[0];
+    const uint4 b = reinterpret_cast<const uint4*>(out + t)[1];
+    const int o = (int)a.z;
+    float dist = 0.f, prob = 0.f;
+    if ((int)a.w > 0) {                              // a record exists
+        const double D = __longlong_as_double(((long long)b.w << 32) | (long long)b.z);
+        const double p = __longlong_as_double(((long long)b.y << 32) | (long long)b.x);
+        dist = (o >= 0) ? round5_to_f32(sqrt(__ddiv_rn((double)__uint_as_float(a.x), D))) : 2.0f;
+        prob = round5_to_f32(p);
+    }
+    reinterpret_cast<float2*>(out + t)[3] = make_float2(dist, prob);
 }
 
 // ---- packed bf16x2 primitives (sm_90+ PTX; keys are the high 16 bits of the

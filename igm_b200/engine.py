@@ -147,6 +147,35 @@ class ActdistEngine:
     def finish_results(self, d_results, n: int, stream: int = 0) -> None:
         check(self._lib.igmk_finish_results_device(self._ctx, ptr(d_results), int(n), stream or None))
 
+    # -- DamID ----------------------------------------------------------
+    def damid_actdist(self, loci, p_exp, plast=None, nucleus_radius: float = 5000.0,
+                      contact_range: float = 0.05, it_corr: int = 0) -> np.ndarray:
+        """get_damid_actdist_I for every locus (spherical envelope); one result per locus."""
+        loci = np.ascontiguousarray(loci, dtype=np.int32)
+        p_exp = np.ascontiguousarray(p_exp, dtype=np.float32)
+        plast = np.zeros(len(loci), np.float32) if plast is None else np.ascontiguousarray(plast, dtype=np.float32)
+        if not (len(loci) == len(p_exp) == len(plast)):
+            raise ValueError("locus arrays must have equal length")
+        if len(loci) and (loci.min() < 0 or loci.max() >= self.n_hap):
+            raise ValueError("locus index out of range [0, %d)" % self.n_hap)
+        out = np.zeros(len(loci), dtype=PAIR_RESULT_DTYPE)
+        check(self._lib.igmk_damid_actdist_host(self._ctx, len(loci), ptr(loci), ptr(p_exp), ptr(plast),
+                                                float(nucleus_radius), float(contact_range), int(it_corr),
+                                                ptr(out)))
+        return out
+
+    def expand_damid_records(self, loci, res, copy_ptr, copy_beads):
+        """(loc, dist, prob) columns of damid_actdist.hdf5: one record per copy of each
+        locus, in locus order (DamidActivationDistanceStep.py:468, :287-296)."""
+        loci = np.asarray(loci, dtype=np.int64)
+        nrec = res["nrec"].astype(np.int64)
+        first = np.asarray(copy_ptr, dtype=np.int64)[loci]
+        assert np.array_equal(nrec, np.asarray(copy_ptr, dtype=np.int64)[loci + 1] - first)
+        rep = np.repeat(np.arange(len(loci)), nrec)
+        within = np.arange(len(rep)) - np.repeat(np.cumsum(nrec) - nrec, nrec)
+        loc = np.asarray(copy_beads)[first[rep] + within].astype(np.int32)
+        return loc, res["dist"][rep].astype(np.float32), res["prob"][rep].astype(np.float32)
+
     def expand_records(self, i, j, res) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
         """Pair results -> (row, col, dist, prob), the four actdist.hdf5 columns."""
         i = np.ascontiguousarray(i, dtype=np.int32)

@@ -1,5 +1,6 @@
-"""Drop-in steps (same class names as igm/steps/__init__.py:4,9 exports)."""
+"""Drop-in steps (same class names as igm/steps/__init__.py:4,5,9 exports)."""
 from .ActivationDistanceStep import ActivationDistanceStep
 from .HicEvaluationStep import HicEvaluationStep
+from .DamidActivationDistanceStep import DamidActivationDistanceStep
 
-__all__ = ["ActivationDistanceStep", "HicEvaluationStep"]
+__all__ = ["ActivationDistanceStep", "HicEvaluationStep", "DamidActivationDistanceStep"]

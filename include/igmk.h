@@ -122,6 +122,26 @@ int igmk_actdist_device_peers(igmk_ctx* ctx, int64_t n_pairs,
  * ActivationDistanceStep.py:38,230,249,473) for n raw results in device memory. */
 int igmk_finish_results_device(igmk_ctx* ctx, igmk_pair_result* d_results, int64_t n, void* stream);
 
+/* Lamina-DamID activation distance, spherical envelope
+ * (get_damid_actdist_I, igm/steps/DamidActivationDistanceStep.py:375-470; loop at
+ * :246-253).  One entry per locus: loci[] = haploid index I, pexp[] / plast[] = the
+ * float32 columns of the '%d.damid.in.npy' batch (:178-186).  Result fields:
+ * d2_sel_bits = float32 sum of squares behind d_sq[o]; contact_count =
+ * #{d_sq >= 1}; o = index in DESCENDING order (-1 when p <= 0, the reference then
+ * stores distance 2); nrec = number of copies (records are written even for
+ * p <= 0, :468); p = corrected probability (a float32 value);
+ * dist / prob = float32("%.5f" % value) as reduce() stores them (:35,:289).
+ * Ellipsoidal envelopes never reach this function in the reference (:245 compares
+ * two string literals) and are not supported. */
+int igmk_damid_actdist_device(igmk_ctx* ctx, int64_t n_loci, const int32_t* d_loci,
+                              const float* d_pexp, const float* d_plast,
+                              double nucleus_radius, double contact_range, int it_corr,
+                              igmk_pair_result* d_out, void* stream);
+int igmk_damid_actdist_host(igmk_ctx* ctx, int64_t n_loci, const int32_t* loci,
+                            const float* pexp, const float* plast,
+                            double nucleus_radius, double contact_range, int it_corr,
+                            igmk_pair_result* out);
+
 /* Record expansion of task()/reduce() (ActivationDistanceStep.py:221-222,
  * 476-483, 249-257): pair results -> the four actdist.hdf5 columns, reference
  * order.  Host pointers; row/col/dist/prob must hold sum(nrec) entries;
