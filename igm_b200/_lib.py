@@ -36,6 +36,8 @@ EXPORTS = (
     "igmk_damid_actdist_device", "igmk_damid_actdist_host",
     "igmk_contact_counts_device", "igmk_contact_counts_host",
     "igmk_contact_counts_haploid_device", "igmk_contact_counts_haploid_host",
+    "igmk_set_bead_chrom", "igmk_restraint_words", "igmk_restraint_select_device",
+    "igmk_restraint_select_host",
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms",
 )
 
@@ -78,6 +80,10 @@ def _declare(lib: C.CDLL) -> None:
                                              C.c_int, vp]
     lib.igmk_contact_counts_haploid_device.argtypes = lib.igmk_contact_counts_device.argtypes
     lib.igmk_contact_counts_haploid_host.argtypes = lib.igmk_contact_counts_host.argtypes
+    lib.igmk_set_bead_chrom.argtypes = [vp, i32p]
+    lib.igmk_restraint_words.argtypes = [vp]
+    lib.igmk_restraint_select_device.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int, vp, vp, vp]
+    lib.igmk_restraint_select_host.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int, vp, vp]
     lib.igmk_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]
     lib.igmk_host_free.argtypes = [vp]
     lib.igmk_last_kernel_ms.argtypes = [vp]

@@ -19,6 +19,7 @@
 #include "../../include/igmk.h"
 #include "igmk_actdist.cuh"
 #include "igmk_contact.cuh"
+#include "igmk_restraint.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -51,6 +52,7 @@ struct igmk_ctx {
     int sm_count = 0;
     float* d_coords = nullptr;       // [nbead][3][npad]
     float* d_radii = nullptr;        // [nbead]
+    int32_t* d_chrom = nullptr;      // [nbead] (igmk_set_bead_chrom)
     HapEntry* d_hap = nullptr;       // [n_hap]
     std::vector<HapEntry> h_hap;
     bool have_coords = false, have_index = false;
@@ -139,6 +141,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_coords);
     cudaFree(c->d_radii);
+    cudaFree(c->d_chrom);
     cudaFree(c->d_hap);
     cudaFree(c->d_stage);
     cudaFree(c->d_pairs);
@@ -645,6 +648,68 @@ extern "C" int igmk_contact_counts_haploid_device(igmk_ctx* c, int row0, int nro
 extern "C" int igmk_contact_counts_haploid_host(igmk_ctx* c, int row0, int nrows, int col0, int ncols,
                                                 float contact_range, int strict, uint32_t* counts) {
     return contact_host(c, 1, row0, nrows, col0, ncols, contact_range, strict, counts);
+}
+
+// ------------------------------------------------------------- K3 (next row f2)
+extern "C" int igmk_set_bead_chrom(igmk_ctx* c, const int32_t* chrom_bead) {
+    if (!c || !chrom_bead) return fail(IGMK_EINVAL, "igmk_set_bead_chrom: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (!c->d_chrom) CUDA_TRY(cudaMalloc(&c->d_chrom, (size_t)c->nbead * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(c->d_chrom, chrom_bead, (size_t)c->nbead * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return IGMK_OK;
+}
+
+extern "C" int igmk_restraint_words(igmk_ctx* c) { return c ? c->npad / 32 : 0; }
+
+extern "C" int igmk_restraint_select_device(igmk_ctx* c, int64_t n_rec, const int32_t* d_row,
+                                            const int32_t* d_col, const float* d_dist, int kind,
+                                            uint32_t* d_bitmap, int32_t* d_counts, void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_restraint_select: NULL context");
+    if (!c->have_coords) return fail(IGMK_ESTATE, "igmk_restraint_select: upload coordinates first");
+    if (kind < 0 || kind > 2) return fail(IGMK_EINVAL, "igmk_restraint_select: bad kind %d", kind);
+    if (kind != 2 && !c->d_chrom) return fail(IGMK_ESTATE, "igmk_restraint_select: igmk_set_bead_chrom first");
+    if (n_rec < 0) return fail(IGMK_EINVAL, "igmk_restraint_select: negative n_rec");
+    if (n_rec == 0) return IGMK_OK;
+    if (!d_row || !d_col || !d_dist || !d_bitmap || !d_counts) return fail(IGMK_EINVAL, "igmk_restraint_select: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    RestraintParams P;
+    P.coords = c->d_coords; P.chrom = c->d_chrom; P.row = d_row; P.col = d_col; P.dist = d_dist;
+    P.bitmap = d_bitmap; P.counts = d_counts; P.n_rec = n_rec;
+    P.nstruct = c->nstruct; P.npad = c->npad; P.nbead = c->nbead; P.kind = kind;
+    long long want = (n_rec + kRsWarps - 1) / kRsWarps, cap = (long long)c->sm_count * 8;
+    restraint_select_kernel<<<(unsigned)(want < cap ? want : cap), 32 * kRsWarps, 0, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+extern "C" int igmk_restraint_select_host(igmk_ctx* c, int64_t n_rec, const int32_t* row,
+                                          const int32_t* col, const float* dist, int kind,
+                                          uint32_t* bitmap, int32_t* counts) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_restraint_select_host: NULL context");
+    if (n_rec == 0) return IGMK_OK;
+    if (n_rec < 0 || !row || !col || !dist || !bitmap || !counts) return fail(IGMK_EINVAL, "igmk_restraint_select_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)n_rec, words = (size_t)c->npad / 32;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t off_c = up(n * 4), off_d = off_c + up(n * 4), off_n = off_d + up(n * 4), off_b = off_n + up(n * 4);
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, off_b + n * words * 4);
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, row, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_c, col, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_d, dist, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = igmk_restraint_select_device(c, n_rec, (const int32_t*)base, (const int32_t*)(base + off_c),
+                                      (const float*)(base + off_d), kind, (uint32_t*)(base + off_b),
+                                      (int32_t*)(base + off_n), c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(counts, base + off_n, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(bitmap, base + off_b, n * words * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
+    return IGMK_OK;
 }
 
 extern "C" int igmk_host_alloc(void** ptr, int64_t bytes) {

@@ -37,6 +37,7 @@ class ActdistEngine:
         if pop is not None:
             self.upload_coordinates(pop.coordinates)
             self.set_index(pop.copy_index.ptr, pop.copy_index.beads, pop.chrom_hap(), pop.radii)
+            self.set_bead_chrom(pop.chrom)
 
     # -- lifetime --------------------------------------------------------
     def close(self):
@@ -146,6 +147,36 @@ class ActdistEngine:
 
     def finish_results(self, d_results, n: int, stream: int = 0) -> None:
         check(self._lib.igmk_finish_results_device(self._ctx, ptr(d_results), int(n), stream or None))
+
+    # -- M-step restraint selection (K3) ----------------------------------
+    KINDS = {"intra": 0, "inter": 1, "any": 2}
+
+    def set_bead_chrom(self, chrom_bead) -> None:
+        chrom_bead = np.ascontiguousarray(chrom_bead, dtype=np.int32)
+        if len(chrom_bead) != self.nbead:
+            raise ValueError("chrom must have one entry per bead")
+        check(self._lib.igmk_set_bead_chrom(self._ctx, ptr(chrom_bead)))
+
+    def restraint_select(self, row, col, dist, kind="intra"):
+        """(bitmap, counts): bitmap[k, s // 32] >> (s % 32) & 1 says whether structure s
+        gets the restraint of actdist record k (intraHiC / interHiC._apply)."""
+        row = np.ascontiguousarray(row, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        dist = np.ascontiguousarray(dist, dtype=np.float32)
+        if not (len(row) == len(col) == len(dist)):
+            raise ValueError("record arrays must have equal length")
+        words = int(self._lib.igmk_restraint_words(self._ctx))
+        bitmap = np.zeros((len(row), words), dtype=np.uint32)
+        counts = np.zeros(len(row), dtype=np.int32)
+        check(self._lib.igmk_restraint_select_host(self._ctx, len(row), ptr(row), ptr(col), ptr(dist),
+                                                   self.KINDS[kind], ptr(bitmap), ptr(counts)))
+        return bitmap, counts
+
+    @staticmethod
+    def records_of_structure(bitmap: np.ndarray, s: int) -> np.ndarray:
+        """Indices of the records whose restraint structure s receives, in record order
+        (what _apply iterates for one model)."""
+        return np.nonzero((bitmap[:, s >> 5] >> np.uint32(s & 31)) & np.uint32(1))[0]
 
     # -- DamID ----------------------------------------------------------
     def damid_actdist(self, loci, p_exp, plast=None, nucleus_radius: float = 5000.0,

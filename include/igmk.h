@@ -178,6 +178,24 @@ int igmk_contact_counts_haploid_device(igmk_ctx* ctx, int row0, int nrows, int c
 int igmk_contact_counts_haploid_host(igmk_ctx* ctx, int row0, int nrows, int col0, int ncols,
                                      float contact_range, int strict, uint32_t* counts);
 
+/* Hi-C restraint selection of the M-step (intraHiC / interHiC._apply,
+ * igm/restraints/intra_hic.py:39-58, inter_hic.py:39-58; one call per structure in
+ * igm/steps/ModelingStep.py:376-398): for every actdist record k = (row, col, dist)
+ * and every structure s,  bit s of record k =
+ *     np.linalg.norm(x[row,s] - x[col,s]) <= dist      (igm/model/particle.py:35-36)
+ *     and chrom[row] == chrom[col] (kind 0) / != (kind 1) / no test (kind 2).
+ * bitmap: n_rec rows of igmk_restraint_words() uint32 words, structure s at bit
+ * s % 32 of word s / 32; counts[k] = number of structures that get restraint k.
+ * igmk_set_bead_chrom: hss index chrom, one id per bead (host pointer). */
+int igmk_set_bead_chrom(igmk_ctx* ctx, const int32_t* chrom_bead);
+int igmk_restraint_words(igmk_ctx* ctx);
+int igmk_restraint_select_device(igmk_ctx* ctx, int64_t n_rec, const int32_t* d_row,
+                                 const int32_t* d_col, const float* d_dist, int kind,
+                                 uint32_t* d_bitmap, int32_t* d_counts, void* stream);
+int igmk_restraint_select_host(igmk_ctx* ctx, int64_t n_rec, const int32_t* row,
+                               const int32_t* col, const float* dist, int kind,
+                               uint32_t* bitmap, int32_t* counts);
+
 /* Pinned host memory for zero-staging transfers (optional). */
 int igmk_host_alloc(void** ptr, int64_t bytes);
 int igmk_host_free(void* ptr);
