@@ -20,6 +20,7 @@
 #include "igmk_actdist.cuh"
 #include "igmk_contact.cuh"
 #include "igmk_restraint.cuh"
+#include "igmk_sprite.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -707,6 +708,72 @@ extern "C" int igmk_restraint_select_host(igmk_ctx* c, int64_t n_rec, const int3
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaMemcpyAsync(counts, base + off_n, n * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(bitmap, base + off_b, n * words * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
+    return IGMK_OK;
+}
+
+// ------------------------------------------------------------- K4 (next row f3)
+extern "C" int igmk_sprite_rg2_host(igmk_ctx* c, int n_clusters, const int32_t* region_ptr,
+                                    const int32_t* copy_ptr, const int32_t* beads,
+                                    float* rg2s, int32_t* copy_idx, int32_t* min_struct) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_sprite_rg2: NULL context");
+    if (!c->have_coords) return fail(IGMK_ESTATE, "igmk_sprite_rg2: upload coordinates first");
+    if (n_clusters < 0) return fail(IGMK_EINVAL, "igmk_sprite_rg2: negative n_clusters");
+    if (n_clusters == 0) return IGMK_OK;
+    if (!region_ptr || !copy_ptr || !beads || !rg2s || !copy_idx || !min_struct)
+        return fail(IGMK_EINVAL, "igmk_sprite_rg2: NULL buffer");
+    const int nreg_tot = region_ptr[n_clusters];
+    if (region_ptr[0] != 0 || copy_ptr[0] != 0) return fail(IGMK_EINVAL, "igmk_sprite_rg2: CSR arrays must start at 0");
+    const int ncopy_tot = copy_ptr[nreg_tot];
+    for (int k = 0; k < n_clusters; ++k) {
+        const int r0 = region_ptr[k], r1 = region_ptr[k + 1];
+        if (r1 <= r0 || r1 - r0 > kSpMaxRegions)
+            return fail(IGMK_ELIMIT, "igmk_sprite_rg2: cluster %d has %d regions (1..%d supported)", k, r1 - r0, kSpMaxRegions);
+        double comb = 1.0;
+        for (int i = r0; i < r1; ++i) {
+            if (copy_ptr[i + 1] <= copy_ptr[i]) return fail(IGMK_EINVAL, "igmk_sprite_rg2: region %d has no location", i);
+            comb *= copy_ptr[i + 1] - copy_ptr[i];
+        }
+        if (copy_ptr[r1] - copy_ptr[r0] > kSpMaxCopies || comb > 16777216.0)
+            return fail(IGMK_ELIMIT, "igmk_sprite_rg2: cluster %d is too large (%d locations, %.0f combinations)", k, copy_ptr[r1] - copy_ptr[r0], comb);
+    }
+    for (int b = 0; b < ncopy_tot; ++b)
+        if (beads[b] < 0 || beads[b] >= c->nbead) return fail(IGMK_EINVAL, "igmk_sprite_rg2: bead id out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t N = (size_t)c->nstruct;
+    const size_t o_cp = up((size_t)(n_clusters + 1) * 4), o_b = o_cp + up((size_t)(nreg_tot + 1) * 4);
+    const size_t o_rg = o_b + up((size_t)ncopy_tot * 4), o_ci = o_rg + up((size_t)n_clusters * N * 4);
+    const size_t o_ms = o_ci + up((size_t)nreg_tot * N * 4), total = o_ms + up((size_t)n_clusters * 4);
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, region_ptr, (size_t)(n_clusters + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_cp, copy_ptr, (size_t)(nreg_tot + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_b, beads, (size_t)ncopy_tot * 4, cudaMemcpyHostToDevice, c->stream));
+    SpriteParams P;
+    P.coords = c->d_coords; P.region_ptr = (const int32_t*)base; P.copy_ptr = (const int32_t*)(base + o_cp);
+    P.beads = (const int32_t*)(base + o_b); P.rg2s = (float*)(base + o_rg); P.copy_idx = (int32_t*)(base + o_ci);
+    P.min_struct = (int32_t*)(base + o_ms);
+    P.n_clusters = n_clusters; P.nstruct = c->nstruct; P.npad = c->npad; P.nbead = c->nbead;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    for (int k0 = 0; k0 < n_clusters; k0 += 65535) {        // gridDim.y limit
+        SpriteParams Q = P;
+        const int nk = (n_clusters - k0 < 65535) ? n_clusters - k0 : 65535;
+        Q.region_ptr = P.region_ptr + k0; Q.rg2s = P.rg2s + (size_t)k0 * N; Q.n_clusters = nk;
+        dim3 grid((c->nstruct + 127) / 128, nk);
+        sprite_rg2_kernel<<<grid, 128, 0, c->stream>>>(Q);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    sprite_argmin_kernel<<<n_clusters, 256, 0, c->stream>>>(P.rg2s, c->nstruct, P.min_struct);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(rg2s, base + o_rg, (size_t)n_clusters * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(copy_idx, base + o_ci, (size_t)nreg_tot * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(min_struct, base + o_ms, (size_t)n_clusters * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
     return IGMK_OK;

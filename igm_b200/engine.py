@@ -178,6 +178,34 @@ class ActdistEngine:
         (what _apply iterates for one model)."""
         return np.nonzero((bitmap[:, s >> 5] >> np.uint32(s & 31)) & np.uint32(1))[0]
 
+    # -- SPRITE (K4) ------------------------------------------------------
+    def sprite_rg2(self, clusters):
+        """clusters: list of clusters, each a list of regions, each a list of bead ids
+        (the alternative locations).  Returns a list of (rg2s[nstruct], best_structure,
+        copy_idxs[nstruct, n_regions]) - get_rgs2's return value per cluster
+        (igm/cython_compiled/sprite.pyx:36-101)."""
+        region_ptr, copy_ptr, beads = [0], [0], []
+        for cl in clusters:
+            for reg in cl:
+                beads.extend(int(b) for b in reg)
+                copy_ptr.append(len(beads))
+            region_ptr.append(len(copy_ptr) - 1)
+        region_ptr = np.asarray(region_ptr, np.int32)
+        copy_ptr = np.asarray(copy_ptr, np.int32)
+        beads = np.asarray(beads, np.int32)
+        n = len(clusters)
+        rg2s = np.zeros((n, self.nstruct), np.float32)
+        cidx = np.zeros(int(region_ptr[-1]) * self.nstruct, np.int32)
+        ms = np.zeros(n, np.int32)
+        check(self._lib.igmk_sprite_rg2_host(self._ctx, n, ptr(region_ptr), ptr(copy_ptr), ptr(beads),
+                                             ptr(rg2s), ptr(cidx), ptr(ms)))
+        out = []
+        for k in range(n):
+            m = int(region_ptr[k + 1] - region_ptr[k])
+            lo = int(region_ptr[k]) * self.nstruct
+            out.append((rg2s[k], int(ms[k]), cidx[lo:lo + m * self.nstruct].reshape(self.nstruct, m)))
+        return out
+
     # -- DamID ----------------------------------------------------------
     def damid_actdist(self, loci, p_exp, plast=None, nucleus_radius: float = 5000.0,
                       contact_range: float = 0.05, it_corr: int = 0) -> np.ndarray:

@@ -196,6 +196,20 @@ int igmk_restraint_select_host(igmk_ctx* ctx, int64_t n_rec, const int32_t* row,
                                const int32_t* col, const float* dist, int kind,
                                uint32_t* bitmap, int32_t* counts);
 
+/* SPRITE cluster radius of gyration with exhaustive choice of copies - the GPU form
+ * of the reference's one native function, get_rg2s_cpp
+ * (igm/cython_compiled/cpp_sprite_assignment.cpp:79-143, bound by Cython at
+ * igm/cython_compiled/sprite.pyx:21-31,98-99), batched over clusters and reading
+ * the population resident in HBM instead of a per-cluster gathered array.
+ * Cluster k has regions region_ptr[k] .. region_ptr[k+1]-1; region i has the
+ * alternative locations beads[copy_ptr[i] .. copy_ptr[i+1]-1] (bead ids).  Out:
+ * rg2s[k * nstruct + s]; copy_idx[region_ptr[k] * nstruct + s * M_k + i] (M_k = regions
+ * of cluster k; the reference's copy_idxs[n_regions*s + i]); min_struct[k] (first
+ * structure with the strictly smallest Rg^2, -1 if none is below 1e8).  Host pointers. */
+int igmk_sprite_rg2_host(igmk_ctx* ctx, int n_clusters, const int32_t* region_ptr,
+                         const int32_t* copy_ptr, const int32_t* beads,
+                         float* rg2s, int32_t* copy_idx, int32_t* min_struct);
+
 /* Pinned host memory for zero-staging transfers (optional). */
 int igmk_host_alloc(void** ptr, int64_t bytes);
 int igmk_host_free(void* ptr);
