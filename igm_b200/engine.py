@@ -57,6 +57,47 @@ class ActdistEngine:
     def __exit__(self, *a):
         self.close()
 
+    @classmethod
+    def from_hss(cls, path: str, device: int = 0) -> "ActdistEngine":
+        """Engine for the population of a .hss file, coordinates streamed chunk by chunk
+        into HBM (igmk_upload_coords_range) instead of being materialised on the host:
+        replaces HssFile(...) + per-pair get_bead_crd chunk reads
+        (igm/steps/ActivationDistanceStep.py:202,415-416; igm/core/step.py:386-392)."""
+        import json
+        from . import hdf5
+        from .population import CopyIndex
+        with hdf5.open_h5(path) as f:
+            ds = f["coordinates"]
+            nbead, nstruct = int(ds.shape[0]), int(ds.shape[1])
+            eng = cls(nbead=nbead, nstruct=nstruct, device=device)
+            try:
+                if hasattr(ds, "iter_chunks"):
+                    for offs, chunk in ds.iter_chunks():
+                        if offs[1] != 0 or offs[2] != 0 or chunk.shape[1] != nstruct or chunk.shape[2] != 3:
+                            # chunking splits the structure axis: fall back to one full read
+                            eng.upload_coordinates(np.asarray(ds[:], dtype=np.float32))
+                            break
+                        eng.upload_coordinates(np.ascontiguousarray(chunk, dtype=np.float32), bead0=int(offs[0]))
+                else:                                   # real h5py
+                    step = max(1, (64 << 20) // (nstruct * 12))
+                    for b0 in range(0, nbead, step):
+                        eng.upload_coordinates(np.asarray(ds[b0:b0 + step], dtype=np.float32), bead0=b0)
+                radii = np.asarray(f["radii"][:], dtype=np.float32)
+                chrom = np.asarray(f["index"]["chrom"][:], dtype=np.int32)
+                ci = f["index"]["copy_index"][()]
+                if isinstance(ci, np.ndarray):
+                    ci = ci.tobytes() if ci.dtype.kind in "SV" else ci.item()
+                if isinstance(ci, (bytes, np.bytes_)):
+                    ci = bytes(ci).rstrip(b"\x00").decode("utf-8")
+                cidx = CopyIndex.from_dict(json.loads(ci))
+                eng.set_index(cidx.ptr, cidx.beads, np.ascontiguousarray(chrom[:len(cidx)]), radii)
+                eng.set_bead_chrom(chrom)
+                eng.copy_index, eng.chrom = cidx, chrom
+            except Exception:
+                eng.close()
+                raise
+        return eng
+
     # -- staging ---------------------------------------------------------
     def upload_coordinates(self, xyz, bead0: int = 0) -> None:
         """xyz: (nb, nstruct, 3) float32, bead-major - NumPy array (host) or a

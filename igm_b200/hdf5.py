@@ -171,6 +171,60 @@ class Dataset:
             arr = arr.astype(dt.np_dtype.newbyteorder("<"))
         return arr.copy()
 
+    def _chunk_layout(self):
+        """(btree address, chunk dims) of a chunked dataset, else None."""
+        lay = self._layout
+        if lay[0] == 3 and lay[1] == 2:
+            ndim = lay[2]
+            (btree,) = struct.unpack_from("<Q", lay, 3)
+            cdims = struct.unpack_from("<%dI" % ndim, lay, 11)
+            return btree, cdims[:-1]
+        if lay[0] in (1, 2) and lay[2] == 2:
+            ndim = lay[1]
+            (addr,) = struct.unpack_from("<Q", lay, 8)
+            dims = struct.unpack_from("<%dI" % ndim, lay, 16)
+            return addr, dims[:-1]
+        return None
+
+    def iter_chunks(self):
+        """Yields (offsets, ndarray) for every stored chunk of a chunked dataset, clipped
+        to the dataset extent (one pseudo-chunk at offset 0 for other layouts).  Lets a
+        loader stream a large .hss straight to the GPU without holding it in host memory
+        (the production files are chunked pack_beads x nstruct x 3,
+        igm/steps/ModelingStep.py:753-760)."""
+        cl = self._chunk_layout()
+        if cl is None or cl[0] == _UNDEF:
+            yield tuple(0 for _ in self.shape), self.read()
+            return
+        btree, cdims = cl
+        for offs, chunk in self._decoded_chunks(btree, cdims):
+            sl = tuple(slice(0, min(cdims[d], self.shape[d] - offs[d])) for d in range(len(self.shape)))
+            yield tuple(offs[:len(self.shape)]), chunk[sl]
+
+    def _decoded_chunks(self, btree: int, cdims):
+        f = self._f
+        ndim = len(self.shape)
+        esize = self._dt.size
+        for csize, fmask, offs, addr in f._iter_chunks(btree, ndim):
+            raw = f._read(addr, csize)
+            for pos in range(len(self._filters) - 1, -1, -1):
+                fid, cd = self._filters[pos]
+                if fmask & (1 << pos):
+                    continue
+                if fid == 1:
+                    raw = zlib.decompress(raw)
+                elif fid == 2:
+                    k = cd[0] if cd else esize
+                    a = np.frombuffer(raw, dtype=np.uint8)
+                    m = len(a) // k
+                    raw = a[:m * k].reshape(k, m).T.tobytes() + a[m * k:].tobytes()
+                elif fid == 3:
+                    raw = raw[:-4]  # fletcher32 checksum trailer
+                else:
+                    raise Hdf5FormatError("unsupported HDF5 filter id %d" % fid)
+            yield offs, np.frombuffer(raw, dtype=self._dt.np_dtype,
+                                      count=int(np.prod(cdims))).reshape(cdims)
+
     def _read_chunked(self, btree: int, cdims) -> np.ndarray:
         f = self._f
         shape = self.shape

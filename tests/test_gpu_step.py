@@ -62,3 +62,29 @@ def test_step_run_demo_two_iterations(tmp_path):
         # next A-step: the runtime sigma is consumed by the driver (bin/igm-run:175-305)
         del cfg["runtime"]["Hi-C"]["inter_sigma"], cfg["runtime"]["Hi-C"]["intra_sigma"]
         cfg["runtime"].pop("current_iteration_name", None)
+
+
+def test_engine_from_hss_streams_chunks(tmp_path):
+    """ActdistEngine.from_hss (chunk-wise staging, no host copy of the population) gives
+    the same answers as the Population path; iter_chunks covers the dataset."""
+    import numpy as np
+    from igm_b200 import hdf5, synthetic
+    from igm_b200.engine import ActdistEngine
+    pop = synthetic.make_population(2_000_000, 90, seed=6, genome_scale=0.02)
+    p = str(tmp_path / "pop.hss")
+    pop.save_hss(p)
+    with hdf5.open_h5(p) as f:
+        got = np.zeros_like(pop.coordinates)
+        for offs, ch in f["coordinates"].iter_chunks():
+            got[offs[0]:offs[0] + ch.shape[0]] = ch
+        assert np.array_equal(got, pop.coordinates)
+    rng = np.random.default_rng(0)
+    ii = rng.integers(0, pop.n_hap - 1, 300).astype(np.int32)
+    jj = (ii + 1 + rng.integers(0, 5, 300)).clip(max=pop.n_hap - 1).astype(np.int32)
+    nc, ch = pop.copy_index.ncopies(), pop.chrom_hap()
+    ok = ~((ch[ii] == ch[jj]) & (nc[ii] != nc[jj])) & (ii != jj)
+    ii, jj = ii[ok], jj[ok]
+    pw = rng.uniform(0.01, 1, len(ii))
+    with ActdistEngine(pop, 0) as a, ActdistEngine.from_hss(p, 0) as b:
+        assert a.actdist(ii, jj, pw).tobytes() == b.actdist(ii, jj, pw).tobytes()
+        assert np.array_equal(a.contact_counts_haploid(0, 9, 0, 9), b.contact_counts_haploid(0, 9, 0, 9))
