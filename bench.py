@@ -255,7 +255,18 @@ def main():
     # N > 1: the kernel stores its results straight into every GPU's gather buffer
     # over NVLink (peer-mapped memory); NCCL all-gather is the fallback
     from igm_b200.dist import PeerGather, peer_gather_available
-    pg = PeerGather(n_pairs, rank, world, dev) if (world > 1 and peer_gather_available(world)) else None
+    pg = None
+    if world > 1 and peer_gather_available(world):
+        try:
+            pg = PeerGather(n_pairs, rank, world, dev)
+        except Exception as e:                       # no peer mapping on this box: NCCL all-gather
+            if rank == 0:
+                sys.stderr.write("peer gather unavailable (%s); using NCCL all-gather\n" % e)
+            pg = None
+        ok = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # all ranks must agree on the path
+        if not int(ok.item()):
+            pg = None
 
     def step():
         if pg is not None:
