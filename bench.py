@@ -81,6 +81,17 @@ def build_index_and_pairs(args, rank):
     return chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw
 
 
+def config_name(args):
+    """Which BASELINE.json config the arguments correspond to."""
+    if args.resolution == 200_000 and args.nstruct == 1000:
+        return "config 2"
+    if args.resolution == 200_000 and args.nstruct == 10000:
+        return "config 3 (per-GPU shard)"
+    if args.resolution == 50_000 and args.nstruct == 1000:
+        return "config 5"
+    return "custom"
+
+
 def algorithmic_bytes(ci, ii, jj, nstruct):
     """B_pair = 12 N (c_i + c_j) + 24 (input record) + 24 (result)."""
     nc = ci.ncopies().astype(np.int64)
@@ -394,10 +405,10 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "config 2: synthetic %d-structure population at %d kb male diploid "
+                "workload": "%s: synthetic %d-structure population at %d kb male diploid "
                             "(%d beads), Hi-C A-step (%s) over the sigma=%g candidate list, "
-                            "%d pairs per GPU" % (args.nstruct, args.resolution // 1000, nbead,
-                                                  args.mode, args.sigma, n_pairs),
+                            "%d pairs per GPU" % (config_name(args), args.nstruct, args.resolution // 1000,
+                                                  nbead, args.mode, args.sigma, n_pairs),
                 "pairs_per_gpu": n_pairs, "nstruct": args.nstruct, "nbead": nbead,
                 "pair_structs_per_s": value * args.nstruct,
                 "parallelism": "pairs sharded over %d GPU(s), coordinates replicated, %s" % (
@@ -484,9 +495,10 @@ def run_reference_arm(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(per_ms)),
         "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config 2: synthetic %d-structure population at %d kb male diploid "
+        "config": {"workload": "%s: synthetic %d-structure population at %d kb male diploid "
                                "(%d beads), Hi-C A-step (%s) over the sigma=%g candidate list; "
-                               "bounded CPU sample per step" % (args.nstruct, args.resolution // 1000,
+                               "bounded CPU sample per step" % (config_name(args), args.nstruct,
+                                                                args.resolution // 1000,
                                                                 nbead, args.mode, args.sigma),
                    "nstruct": args.nstruct, "nbead": nbead},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
