@@ -15,9 +15,10 @@
 // L2 and reused 32 times out of shared memory.  Tensor cores do not apply
 // (3-term non-FMA float32 sums that must match NumPy bit for bit).
 //
-// CTA = 256 threads = 64 (8 x 8) pair-positions x 4 structure slices; each
-// thread owns a 4 x 4 block of bead pairs (beads ta + 8 aa, tb + 8 bb) and, per
-// staged chunk of 32 structures, the 8 structures of its slice.
+// CTA = 256 threads = 128 (8 x 16) pair-positions x 2 structure slices; each
+// thread owns a 4 x 2 block of bead pairs (beads ta + 8 aa, tb + 16 bb) and, per
+// staged chunk of 32 structures, the 16 structures of its slice.  (4 x 4 blocks with
+// 4 slices need 128 registers and spill: 2.59 T vs 2.87 T bead-pair-structs/s.)
 #pragma once
 #include "igmk_device.cuh"
 
@@ -27,6 +28,17 @@ constexpr int kCtTile = 32;            // beads per tile side
 constexpr int kCtThreads = 256;
 constexpr int kCtStruct = 32;          // structures staged per step
 constexpr int kCtRow = 3 * kCtStruct + 4;   // floats per bead in smem; /4 is odd -> conflict-free LDS.128
+#ifndef IGMK_CT_MINB
+#define IGMK_CT_MINB 2
+#endif
+#ifndef IGMK_CT_BB
+#define IGMK_CT_BB 2
+#endif
+constexpr int kCtBB = IGMK_CT_BB;           // column beads per thread (row beads: 4)
+constexpr int kCtTbN = kCtTile / kCtBB;     // column positions (8 or 16)
+constexpr int kCtPos = 8 * kCtTbN;          // pair positions per structure slice
+constexpr int kCtSlices = kCtThreads / kCtPos;       // structure slices (4 or 2)
+constexpr int kCtGq = kCtStruct / kCtSlices / 4;     // float4 groups per slice and step
 constexpr int kCtRcRow = kCtTile + 8;       // cut-off tile row: (ta * 40 + tb) % 32 distinct within a warp
 
 struct ContactParams {
@@ -49,10 +61,10 @@ struct ContactParams {
 template <bool STRICT>
 __device__ __forceinline__ void contact_accumulate_packed(const float* sa, const float* sb, int ta, int tb,
                                                           int slice, u64 nz,
-                                                          const float* s_rc, u64 (&cnt2)[4][4]) {
+                                                          const float* s_rc, u64 (&cnt2)[4][kCtBB]) {
 #pragma unroll
-    for (int gq = 0; gq < 2; ++gq) {
-        const int s4 = slice * 8 + gq * 4;       // first of 4 structures within the chunk
+    for (int gq = 0; gq < kCtGq; ++gq) {
+        const int s4 = slice * (4 * kCtGq) + gq * 4;       // first of 4 structures within the chunk
         // two row beads at a time (24 registers of row coordinates live)
 #pragma unroll
         for (int ah = 0; ah < 4; ah += 2) {
@@ -65,8 +77,8 @@ __device__ __forceinline__ void contact_accumulate_packed(const float* sa, const
                 lds_v2b64(p + 2 * kCtStruct, a[a2].z01, a[a2].z23);
             }
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-                const float* p = sb + (tb + 8 * bb) * kCtRow + s4;
+            for (int bb = 0; bb < kCtBB; ++bb) {
+                const float* p = sb + (tb + kCtTbN * bb) * kCtRow + s4;
                 Row6 b;
                 lds_v2b64(p, b.x01, b.x23);
                 lds_v2b64(p + kCtStruct, b.y01, b.y23);
@@ -77,7 +89,7 @@ __device__ __forceinline__ void contact_accumulate_packed(const float* sa, const
                     float d0, d1, d2, d3;
                     f2split(d2pair<0>(a[a2], b, nz), d0, d1);
                     f2split(d2pair<1>(a[a2], b, nz), d2, d3);
-                    const float r = s_rc[(ta + 8 * aa) * kCtRcRow + tb + 8 * bb];
+                    const float r = s_rc[(ta + 8 * aa) * kCtRcRow + tb + kCtTbN * bb];
 #ifndef IGMK_CT_INTCOUNT
                     if (STRICT) {
                         cnt2[aa][bb] = f2add(cnt2[aa][bb], f2pack(f_lt_one(d0, r), f_lt_one(d1, r)));
@@ -100,7 +112,7 @@ __device__ __forceinline__ void contact_accumulate_packed(const float* sa, const
 }
 
 // Bead-level tile: tile indices are bead ids.
-__global__ void __launch_bounds__(kCtThreads, 2)
+__global__ void __launch_bounds__(kCtThreads, IGMK_CT_MINB)
 contact_tile_kernel(const ContactParams P) {
     __shared__ __align__(16) float s_a[kCtTile * kCtRow];
     __shared__ __align__(16) float s_b[kCtTile * kCtRow];
@@ -108,8 +120,8 @@ contact_tile_kernel(const ContactParams P) {
     __shared__ float s_rc[kCtTile * kCtRcRow];
 
     const int t = threadIdx.x;
-    const int pos = t & 63, slice = t >> 6;
-    const int ta = pos >> 3, tb = pos & 7;
+    const int pos = t % kCtPos, slice = t / kCtPos;
+    const int ta = pos / kCtTbN, tb = pos % kCtTbN;
     const int a_base = P.row0 + blockIdx.y * kCtTile;
     const int b_base = P.col0 + blockIdx.x * kCtTile;
     const int a_end = P.row0 + P.nrows, b_end = P.col0 + P.ncols;
@@ -124,11 +136,11 @@ contact_tile_kernel(const ContactParams P) {
         const float r = __fmul_rn(P.contact_range, __fadd_rn(ra, rb));
         s_rc[(e >> 5) * kCtRcRow + (e & 31)] = __fmul_rn(r, r);
     }
-    u64 cnt2[4][4];        // {even, odd structures} hit counts as floats (exact: < 2^24)
+    u64 cnt2[4][kCtBB];        // {even, odd structures} hit counts as floats (exact: < 2^24)
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) cnt2[aa][bb] = 0ull;
+        for (int bb = 0; bb < kCtBB; ++bb) cnt2[aa][bb] = 0ull;
 
     const size_t row = (size_t)3 * P.npad;
     for (int s0 = 0; s0 < P.nstruct; s0 += kCtStruct) {
@@ -168,14 +180,14 @@ contact_tile_kernel(const ContactParams P) {
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb)
+        for (int bb = 0; bb < kCtBB; ++bb)
         {
 #ifndef IGMK_CT_INTCOUNT
             float c_lo, c_hi;
             f2split(cnt2[aa][bb], c_lo, c_hi);
-            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)(int)(c_lo + c_hi));
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + kCtTbN * bb)], (uint32_t)(int)(c_lo + c_hi));
 #else
-            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)cnt2[aa][bb]);
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + kCtTbN * bb)], (uint32_t)cnt2[aa][bb]);
 #endif
         }
     __syncthreads();
@@ -190,7 +202,7 @@ contact_tile_kernel(const ContactParams P) {
 // Haploid variant: tile indices are haploid loci and the counts of all copy combinations of a locus pair are summed
 // (Contactmatrix.sumCopies() after buildContactMap, HicEvaluationStep.py:109-111):
 //   counts[i][j] = sum over a in copies(i), b in copies(j) of #{s : d2_s(a,b) <= rc2(a,b)}
-__global__ void __launch_bounds__(kCtThreads, 2)
+__global__ void __launch_bounds__(kCtThreads, IGMK_CT_MINB)
 contact_tile_hap_kernel(const ContactParams P) {
     constexpr bool HAP = true;
     __shared__ __align__(16) float s_a[kCtTile * kCtRow];
@@ -200,8 +212,8 @@ contact_tile_hap_kernel(const ContactParams P) {
     __shared__ int s_ida[2][kCtTile], s_idb[2][kCtTile];     // bead id per copy, -1: absent
 
     const int t = threadIdx.x;
-    const int pos = t & 63, slice = t >> 6;
-    const int ta = pos >> 3, tb = pos & 7;
+    const int pos = t % kCtPos, slice = t / kCtPos;
+    const int ta = pos / kCtTbN, tb = pos % kCtTbN;
     const int a_base = P.row0 + blockIdx.y * kCtTile;
     const int b_base = P.col0 + blockIdx.x * kCtTile;
     const int a_end = P.row0 + P.nrows, b_end = P.col0 + P.ncols;
@@ -219,11 +231,11 @@ contact_tile_hap_kernel(const ContactParams P) {
         if (side) { s_idb[0][k] = id0; s_idb[1][k] = id1; }
         else      { s_ida[0][k] = id0; s_ida[1][k] = id1; }
     }
-    u64 cnt2[4][4];        // {even, odd structures} hit counts as floats (exact: < 2^24)
+    u64 cnt2[4][kCtBB];        // {even, odd structures} hit counts as floats (exact: < 2^24)
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) cnt2[aa][bb] = 0ull;
+        for (int bb = 0; bb < kCtBB; ++bb) cnt2[aa][bb] = 0ull;
 
     const size_t row = (size_t)3 * P.npad;
     constexpr int ncopy = HAP ? 2 : 1;
@@ -289,14 +301,14 @@ contact_tile_hap_kernel(const ContactParams P) {
 #pragma unroll
     for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb)
+        for (int bb = 0; bb < kCtBB; ++bb)
         {
 #ifndef IGMK_CT_INTCOUNT
             float c_lo, c_hi;
             f2split(cnt2[aa][bb], c_lo, c_hi);
-            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)(int)(c_lo + c_hi));
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + kCtTbN * bb)], (uint32_t)(int)(c_lo + c_hi));
 #else
-            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + 8 * bb)], (uint32_t)cnt2[aa][bb]);
+            atomicAdd(&s_cnt[(ta + 8 * aa) * kCtTile + (tb + kCtTbN * bb)], (uint32_t)cnt2[aa][bb]);
 #endif
         }
     __syncthreads();
