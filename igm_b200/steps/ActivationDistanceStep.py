@@ -103,8 +103,7 @@ def _get_engine(hss_path, device):
     if eng is None:
         for k in list(_engine_cache):
             _engine_cache.pop(k).close()
-        pop = Population.from_hss(hss_path)
-        eng = ActdistEngine(pop, device=device)
+        eng = ActdistEngine.from_hss(hss_path, device)     # chunk-wise staging, no host copy
         _engine_cache[key] = eng
     return eng
 

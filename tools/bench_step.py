@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Whole Hi-C A-step through the Step drop-in (setup -> task -> reduce) on config 2 of
+BASELINE.json, files included: a synthetic .hss (1000 structures x 29 838 beads) and .hcs
+are written to a scratch directory, then igm_b200.steps.ActivationDistanceStep(cfg).run()
+is timed phase by phase.  What `igm-run` would see (bin/igm-run:164-166)."""
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    from igm_b200 import hdf5, synthetic
+    from igm_b200.population import CopyIndex, Population
+    from igm_b200.steps import ActivationDistanceStep
+    from igm_b200.steps._compat import Config
+    nstruct = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    tmp = tempfile.mkdtemp(prefix="igmk_step_")
+    dev = torch.device("cuda:0")
+    bins = synthetic.genome_bins(200_000)
+    chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins)
+    nbead = len(chrom_bead)
+    radius = float(synthetic.bead_radius(nbead))
+    coords = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, nstruct, radius, 20261018, dev).cpu().numpy()
+    pop = Population(coords, np.full(nbead, radius, np.float32), chrom_bead, ci, copy_bead)
+    t0 = time.perf_counter()
+    hss = os.path.join(tmp, "igm-model.hss")
+    pop.save_hss(hss)
+    pm = synthetic.make_prob_matrix(chrom_hap, seed=20261018)
+    hcs = os.path.join(tmp, "in.hcs")
+    pm.save_hcs(hcs)
+    t_files = time.perf_counter() - t0
+    del pop, coords
+    out = {"nstruct": nstruct, "nbead": nbead, "write_inputs_s": t_files, "sigmas": []}
+    cfg = Config({"parameters": {"workdir": tmp, "tmp_dir": os.path.join(tmp, "tmp")},
+                  "optimization": {"structure_output": hss, "iter_corr_knob": 1},
+                  "restraints": {"Hi-C": {"input_matrix": hcs, "intra_sigma_list": [0.05, 0.01],
+                                          "inter_sigma_list": [0.05, 0.01], "contact_range": 2.0}},
+                  "runtime": {"Hi-C": {}, "opt_iter": 0}})
+    for k in range(2):
+        step = ActivationDistanceStep(cfg)
+        ph = {}
+        t = time.perf_counter(); step.setup(); ph["setup_s"] = time.perf_counter() - t
+        t = time.perf_counter()
+        for a in step.argument_list:
+            step.task(a, cfg, step.tmp_dir)
+        ph["task_s"] = time.perf_counter() - t
+        t = time.perf_counter(); step.reduce(); ph["reduce_s"] = time.perf_counter() - t
+        with hdf5.open_h5(cfg["runtime"]["Hi-C"]["actdist_file"]) as f:
+            ph["records"] = int(len(f["row"]))
+        ph["pairs"] = int(sum(len(np.load(os.path.join(step.tmp_dir, "%d.in.npy" % a))) for a in step.argument_list))
+        ph["sigma"] = cfg["runtime"]["Hi-C"]["intra_sigma"]
+        ph["total_s"] = ph["setup_s"] + ph["task_s"] + ph["reduce_s"]
+        ph["pairs_per_s_whole_step"] = ph["pairs"] / ph["total_s"]
+        out["sigmas"].append(ph)
+        # next sigma (what igm-run does between A/M iterations, bin/igm-run:175-305)
+        cfg["runtime"]["Hi-C"].pop("intra_sigma"); cfg["runtime"]["Hi-C"].pop("inter_sigma")
+        cfg["runtime"]["opt_iter"] += 1
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
