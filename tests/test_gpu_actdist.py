@@ -281,3 +281,33 @@ def test_device_entry_point_and_errors():
             eng.actdist(np.array([0], np.int32), np.array([pop.n_hap], np.int32), np.array([0.5]))
     with pytest.raises(_lib.IgmkError):
         ActdistEngine(nbead=10, nstruct=10, device=99)
+
+
+@pytest.mark.parametrize("nstruct", [300, 2600])
+def test_peer_store_entry_point_single_gpu(nstruct):
+    """igmk_actdist_device_peers with the 'peers' being two buffers on this one GPU
+    (warp and CTA groups): every copy equals the ordinary path after the finish pass."""
+    import torch
+    from igm_b200 import synthetic, _lib
+    from igm_b200.engine import ActdistEngine
+    pop = synthetic.make_population(2_000_000, nstruct, seed=77, genome_scale=0.01)
+    rng = np.random.default_rng(4)
+    n = 3000
+    ii = rng.integers(0, pop.n_hap - 1, n).astype(np.int32)
+    jj = (ii + 1 + rng.integers(0, 9, n)).clip(max=pop.n_hap - 1).astype(np.int32)
+    nc, ch = pop.copy_index.ncopies(), pop.chrom_hap()
+    bad = ((ch[ii] == ch[jj]) & (nc[ii] != nc[jj]))
+    jj[bad] = ii[bad]                                         # i == j: empty result slot
+    pw = rng.uniform(0.005, 1, n)
+    dev = torch.device("cuda:0")
+    with ActdistEngine(pop, 0) as eng:
+        ref = eng.actdist(ii, jj, pw, None, 2.0, 1, "LB")
+        d_i, d_j = torch.from_numpy(ii).to(dev), torch.from_numpy(jj).to(dev)
+        d_pw, d_pl = torch.from_numpy(pw).to(dev), torch.zeros(n, dtype=torch.float64, device=dev)
+        bufs = torch.zeros((2, n, 32), dtype=torch.uint8, device=dev)
+        peers = torch.tensor([bufs[0].data_ptr(), bufs[1].data_ptr()], dtype=torch.int64, device=dev)
+        eng.actdist_device_peers(d_i, d_j, d_pw, d_pl, peers, 2, n, 2.0, 1, "LB")
+        eng.finish_results(bufs, 2 * n)
+        torch.cuda.synchronize()
+        got = bufs.cpu().numpy().reshape(2, -1).view(_lib.PAIR_RESULT_DTYPE)
+    assert got[0].tobytes() == ref.tobytes() and got[1].tobytes() == ref.tobytes()
