@@ -311,3 +311,31 @@ def test_peer_store_entry_point_single_gpu(nstruct):
         torch.cuda.synchronize()
         got = bufs.cpu().numpy().reshape(2, -1).view(_lib.PAIR_RESULT_DTYPE)
     assert got[0].tobytes() == ref.tobytes() and got[1].tobytes() == ref.tobytes()
+
+
+def test_swapped_and_duplicate_pairs():
+    """i > j pairs, duplicates and unsorted order behave like independent get_actdist calls."""
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, 150, seed=5, genome_scale=0.02)
+    rng = np.random.default_rng(9)
+    nh = pop.n_hap
+    ii = rng.integers(0, nh, 400)
+    jj = rng.integers(0, nh, 400)
+    nc, ch = pop.copy_index.ncopies(), pop.chrom_hap()
+    ok = (ii != jj) & ~((ch[ii] == ch[jj]) & (nc[ii] != nc[jj]))
+    ii, jj = ii[ok].astype(np.int32), jj[ok].astype(np.int32)          # both orders occur
+    ii = np.concatenate([ii, ii[:50], jj[:50]])                        # duplicates and swapped duplicates
+    jj = np.concatenate([jj, jj[:50], ii[:50]])
+    assert (ii > jj).any() and (ii < jj).any()
+    pw = rng.uniform(0.001, 1.0, len(ii)).astype(np.float32).astype(np.float64)
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            recs, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                       pop.copy_index, 1, 2.0, MODES[mode])
+            res = eng.actdist(ii, jj, pw, pl, 2.0, 1, mode, 0)
+            _check_against_details(res, dets)
+            row, col, dist, prob = eng.expand_records(ii, jj, res)
+            erow, ecol, edist, eprob = orc.records_to_arrays(recs)
+            assert np.array_equal(row, erow) and np.array_equal(col, ecol)
+            assert np.array_equal(dist, edist) and np.array_equal(prob, eprob)

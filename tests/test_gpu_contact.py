@@ -55,6 +55,9 @@ def test_haploid_counts_are_copy_sums(nstruct):
         from igm_b200.contact import haploid_contact_counts
         dense = haploid_contact_counts(eng, 2.0, False, block=37)
         assert np.array_equal(dense, exp)
+        fulls = co.contact_counts_fast(pop.coordinates, pop.radii, np.arange(nb), np.arange(nb), 3.0, True)
+        exps = co.sum_copies(fulls, pop.copy_index.ptr, pop.copy_index.beads).astype(np.uint32)
+        assert np.array_equal(eng.contact_counts_haploid(0, nh, 0, nh, 3.0, True), exps)      # strict '<'
         # two "ranks" computed separately add up to the whole
         a = haploid_contact_counts(eng, 2.0, False, block=16, rank=0, world=2)
         b = haploid_contact_counts(eng, 2.0, False, block=16, rank=1, world=2)
