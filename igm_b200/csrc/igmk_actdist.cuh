@@ -482,9 +482,7 @@ __device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCt
     if (lane == 0) {
         // publish with one user (this warp); nobody touches a LOADING word
         const uint32_t ready = ((uint32_t)i << 12) | (TS_READY << 10) | 1u;
-        uint32_t prev;
-        asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(prev) : "r"(tile.words + 4u * claimed), "r"(ready) : "memory");
-        (void)prev;
+        sts32(tile.words + 4u * claimed, ready);   // after the block-scope fence above
     }
     __syncwarp();
     return claimed;
