@@ -52,3 +52,28 @@ def test_expand_damid_records_order():
     res["prob"] = [0.25, 0.0]
     loc, dist, prob = ActdistEngine.expand_damid_records(None, np.array([2, 1]), res, ptr, beads)
     assert loc.tolist() == [2, 4, 1] and dist.tolist() == [0.5, 0.5, 2.0] and prob.tolist() == [0.25, 0.25, 0.0]
+
+
+def test_nucl_damid_step_host_logic(tmp_path):
+    """Host side of the nuclear-body twin (NuclDamidActivationDistanceStep.py:120-361): config keys,
+    name string, sigma pop, batch files, and the setup/skip default-directory mismatch (:172 vs :356)."""
+    from igm_b200.steps import NuclDamidActivationDistanceStep
+    from igm_b200.steps._compat import Config
+    prof = str(tmp_path / "p.txt")
+    np.savetxt(prof, np.array([0.5, 0.05, 0.31, 0.9, 0.2], np.float32))
+    cfg = Config({"parameters": {"workdir": str(tmp_path), "tmp_dir": str(tmp_path / "tmp")},
+                  "optimization": {"structure_output": "unused.hss", "iter_corr_knob": 0},
+                  "restraints": {"nuclDamID": {"input_profile": prof, "sigma_list": [0.3, 0.1], "batch_size": 2}},
+                  "runtime": {"nuclDamID": {}, "opt_iter": 4}})
+    step = NuclDamidActivationDistanceStep(cfg)
+    assert step.name() == "NuclDamidActivationDistanceStep (sigma=30.00%, iter=4)"
+    assert cfg["runtime"]["nuclDamID"]["sigma"] == 0.3 and cfg["runtime"]["nuclDamID"]["sigma_list"] == [0.1]
+    assert "DamID" not in cfg["runtime"]
+    step.setup()
+    assert step.tmp_dir == str(tmp_path / "tmp" / "nucldamid_actdist")
+    assert list(step.argument_list) == [0, 1]
+    b0 = np.load(os.path.join(step.tmp_dir, "0.damid.in.npy"))
+    b1 = np.load(os.path.join(step.tmp_dir, "1.damid.in.npy"))
+    assert b0.dtype == np.float32 and b0[:, 0].tolist() == [0.0, 2.0] and b1[:, 0].tolist() == [3.0]
+    step.skip()
+    assert cfg["runtime"]["nuclDamID"]["damid_actdist_file"] == str(tmp_path / "tmp" / "damid_actdist" / "damid_actdist.hdf5")

@@ -69,10 +69,15 @@ def test_damid_oracle_sizes(nstruct):
             assert np.array_equal(res["d2_sel_bits"][sel], np.array([d["s_bits"] for d in dets], np.uint32)[sel])
 
 
-def test_damid_step_end_to_end(tmp_path):
+@pytest.mark.parametrize("variant", ["DamID", "nuclDamID"])
+def test_damid_step_end_to_end(tmp_path, variant):
+    """Lamina step and its nuclear-body twin (NuclDamidActivationDistanceStep.py) through
+    Step.run on files; both must give the oracle's records."""
     from igm_b200 import hdf5, synthetic
-    from igm_b200.steps import DamidActivationDistanceStep
+    from igm_b200 import steps
     from igm_b200.steps._compat import Config
+    body = {"DamID": "envelope", "nuclDamID": "nucleolus"}[variant]
+    cls = {"DamID": steps.DamidActivationDistanceStep, "nuclDamID": steps.NuclDamidActivationDistanceStep}[variant]
     pop = synthetic.make_population(2_000_000, 80, seed=12, genome_scale=0.02)
     hss = str(tmp_path / "pop.hss")
     pop.save_hss(hss)
@@ -83,14 +88,15 @@ def test_damid_step_end_to_end(tmp_path):
     rad = float(np.sqrt(np.quantile(np.sum(np.square(pop.coordinates), axis=2), 0.6))) / 0.95 + float(pop.radii[0])
     cfg = Config({"parameters": {"workdir": str(tmp_path), "tmp_dir": str(tmp_path / "tmp")},
                   "optimization": {"structure_output": hss, "iter_corr_knob": 1},
-                  "model": {"restraints": {"envelope": {"nucleus_shape": "sphere", "nucleus_radius": rad}}},
-                  "restraints": {"DamID": {"input_profile": prof, "sigma_list": [0.3, 0.1], "contact_range": 0.05,
+                  "model": {"restraints": {body: {"nucleus_shape": "sphere", "nucleus_radius": rad}}},
+                  "restraints": {variant: {"input_profile": prof, "sigma_list": [0.3, 0.1], "contact_range": 0.05,
                                            "batch_size": 17, "keep_temporary_files": True}},
-                  "runtime": {"DamID": {}, "opt_iter": 1}})
-    step = DamidActivationDistanceStep(cfg)
-    assert step.name() == "DamidActivationDistanceStep (sigma=30.00%, iter=1)"
+                  "runtime": {variant: {}, "opt_iter": 1}})
+    step = cls(cfg)
+    assert step.name() == cls.__name__ + " (sigma=30.00%, iter=1)"
     step.run()
-    out = cfg["runtime"]["DamID"]["damid_actdist_file"]
+    out = cfg["runtime"][variant]["damid_actdist_file"]
+    assert os.path.basename(os.path.dirname(out)) == {"DamID": "damid_actdist", "nuclDamID": "nucldamid_actdist"}[variant]
     with hdf5.open_h5(out) as f:
         loc, dist, prob = np.asarray(f["loc"][()]), np.asarray(f["dist"][()]), np.asarray(f["prob"][()])
     prof32 = np.loadtxt(prof, dtype="float32")
