@@ -21,6 +21,7 @@
 #include "igmk_contact.cuh"
 #include "igmk_restraint.cuh"
 #include "igmk_sprite.cuh"
+#include "igmk_rank.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -774,6 +775,83 @@ extern "C" int igmk_sprite_rg2_host(igmk_ctx* c, int n_clusters, const int32_t* 
     CUDA_TRY(cudaMemcpyAsync(rg2s, base + o_rg, (size_t)n_clusters * N * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(copy_idx, base + o_ci, (size_t)nreg_tot * N * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(min_struct, base + o_ms, (size_t)n_clusters * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
+    return IGMK_OK;
+}
+
+// ------------------------------------------------------------- K5 (next row f4)
+extern "C" int igmk_rank_match_device(igmk_ctx* c, int64_t n_items, const int32_t* d_a, const int32_t* d_b,
+                                      int reduce, const float* d_target, int64_t target_stride,
+                                      float* d_matched, int32_t* d_rank, float* d_value, void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_rank_match: NULL context");
+    if (!c->have_coords) return fail(IGMK_ESTATE, "igmk_rank_match: upload coordinates first");
+    if (n_items < 0) return fail(IGMK_EINVAL, "igmk_rank_match: negative n_items");
+    if (reduce != 0 && reduce != 1) return fail(IGMK_EINVAL, "igmk_rank_match: bad reduce %d", reduce);
+    if (n_items == 0) return IGMK_OK;
+    if (!d_a || (d_matched && !d_target) || target_stride < 0) return fail(IGMK_EINVAL, "igmk_rank_match: bad buffer");
+    if (c->nstruct > 16384) return fail(IGMK_ELIMIT, "igmk_rank_match: nstruct = %d exceeds the supported 16384", c->nstruct);
+    CUDA_TRY(cudaSetDevice(c->device));
+    RankParams P;
+    P.coords = c->d_coords; P.a = d_a; P.b = d_b; P.target = d_target; P.target_stride = target_stride;
+    P.matched = d_matched; P.rank = d_rank; P.value = d_value;
+    P.n_items = n_items; P.nstruct = c->nstruct; P.npad = c->npad; P.nbead = c->nbead;
+    P.zero_bead = c->nbead; P.reduce = reduce;
+    int m = 2;
+    while (m < c->nstruct) m <<= 1;
+    P.m = m;
+    const int threads = (m >= 2048) ? 512 : ((m >= 512) ? 256 : 128);
+    const size_t smem = (size_t)m * 8 + (size_t)c->nstruct * 4;
+    CUDA_TRY(cudaFuncSetAttribute(rank_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rank_match_kernel, threads, smem));
+    if (per_sm < 1) return fail(IGMK_ECUDA, "rank_match_kernel cannot run with nstruct = %d", c->nstruct);
+    const long long cap = (long long)c->sm_count * per_sm;
+    rank_match_kernel<<<(unsigned)(n_items < cap ? n_items : cap), threads, smem, (cudaStream_t)stream>>>(P);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+extern "C" int igmk_rank_match_host(igmk_ctx* c, int64_t n_items, const int32_t* a, const int32_t* b,
+                                    int reduce, const float* target, int64_t target_stride,
+                                    float* matched, int32_t* rank, float* value) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_rank_match_host: NULL context");
+    if (n_items == 0) return IGMK_OK;
+    if (n_items < 0 || !a || (matched && !target) || target_stride < 0)
+        return fail(IGMK_EINVAL, "igmk_rank_match_host: bad argument");
+    for (int64_t t = 0; t < n_items; ++t) {
+        const int a0 = a[2 * t], a1 = a[2 * t + 1];
+        if (a0 < 0 || a0 >= c->nbead || a1 >= c->nbead) return fail(IGMK_EINVAL, "igmk_rank_match_host: bead id out of range in item %lld", (long long)t);
+        if (b) {
+            const int b0 = b[2 * t], b1 = b[2 * t + 1];
+            if (b0 < 0 || b0 >= c->nbead || b1 >= c->nbead) return fail(IGMK_EINVAL, "igmk_rank_match_host: bead id out of range in item %lld", (long long)t);
+        }
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t n = (size_t)n_items, N = (size_t)c->nstruct;
+    const size_t n_tgt = target ? (target_stride ? n * (size_t)target_stride : N) : 0;
+    if (target && target_stride && (size_t)target_stride < N) return fail(IGMK_EINVAL, "igmk_rank_match_host: target_stride < nstruct");
+    const size_t o_b = up(n * 8), o_t = o_b + up(n * 8), o_m = o_t + up(n_tgt * 4);
+    const size_t o_r = o_m + (matched ? up(n * N * 4) : 0), o_v = o_r + (rank ? up(n * N * 4) : 0);
+    const size_t total = o_v + (value ? up(n * N * 4) : 0);
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, a, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (b) CUDA_TRY(cudaMemcpyAsync(base + o_b, b, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (target) CUDA_TRY(cudaMemcpyAsync(base + o_t, target, n_tgt * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = igmk_rank_match_device(c, n_items, (const int32_t*)base, b ? (const int32_t*)(base + o_b) : nullptr, reduce,
+                                target ? (const float*)(base + o_t) : nullptr, target_stride,
+                                matched ? (float*)(base + o_m) : nullptr, rank ? (int32_t*)(base + o_r) : nullptr,
+                                value ? (float*)(base + o_v) : nullptr, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    if (matched) CUDA_TRY(cudaMemcpyAsync(matched, base + o_m, n * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rank) CUDA_TRY(cudaMemcpyAsync(rank, base + o_r, n * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (value) CUDA_TRY(cudaMemcpyAsync(value, base + o_v, n * N * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
     return IGMK_OK;

@@ -219,6 +219,46 @@ class ActdistEngine:
         (what _apply iterates for one model)."""
         return np.nonzero((bitmap[:, s >> 5] >> np.uint32(s & 31)) & np.uint32(1))[0]
 
+    # -- rank matching (K5: FISH / polymer assignment) ---------------------
+    def rank_match(self, a, b=None, reduce="min", target=None, want_rank=True, want_value=True):
+        """Per item the reduced (min / max over copy combinations) float32 distance of every
+        structure, its rank in the population (ties by structure index) and, with
+        ``target`` (one sorted row of nstruct values, or one row per item), the target handed
+        to each structure: get_min_max_and_idx + ``target[idx]`` of
+        igm/steps/FishAssignmentStep.py:60-79,189-193 and get_polymer_dists of
+        igm/steps/PolymerAssignmentStep.py:24-33.  ``a`` / ``b``: (n_items, 2) bead ids, second
+        column -1 for single-copy loci; ``b=None``: radial distances.  Returns a dict with
+        the requested arrays ``value``, ``rank``, ``matched`` of shape (n_items, nstruct)."""
+        a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, 2)
+        n = len(a)
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.int32).reshape(-1, 2)
+            if len(b) != n:
+                raise ValueError("a and b must have one row per item")
+        stride = 0
+        if target is not None:
+            target = np.ascontiguousarray(target, dtype=np.float32)
+            if target.ndim == 2:
+                if target.shape != (n, self.nstruct):
+                    raise ValueError("target must be (n_items, nstruct) or (nstruct,)")
+                stride = self.nstruct
+            elif target.shape != (self.nstruct,):
+                raise ValueError("target must be (n_items, nstruct) or (nstruct,)")
+        out = {}
+        if target is not None:
+            out["matched"] = np.zeros((n, self.nstruct), np.float32)
+        if want_rank:
+            out["rank"] = np.zeros((n, self.nstruct), np.int32)
+        if want_value:
+            out["value"] = np.zeros((n, self.nstruct), np.float32)
+        check(self._lib.igmk_rank_match_host(
+            self._ctx, n, ptr(a), ptr(b) if b is not None else None, {"min": 0, "max": 1}[reduce],
+            ptr(target) if target is not None else None, stride,
+            ptr(out["matched"]) if "matched" in out else None,
+            ptr(out["rank"]) if "rank" in out else None,
+            ptr(out["value"]) if "value" in out else None))
+        return out
+
     # -- SPRITE (K4) ------------------------------------------------------
     def sprite_rg2(self, clusters):
         """clusters: list of clusters, each a list of regions, each a list of bead ids

@@ -1,7 +1,9 @@
-"""Drop-in steps (same class names as igm/steps/__init__.py:4,5,9,10 exports)."""
+"""Drop-in steps (same class names as igm/steps/__init__.py:4-11 exports)."""
 from .ActivationDistanceStep import ActivationDistanceStep
 from .HicEvaluationStep import HicEvaluationStep
 from .DamidActivationDistanceStep import DamidActivationDistanceStep, NuclDamidActivationDistanceStep
+from .FishAssignmentStep import FishAssignmentStep
+from .PolymerAssignmentStep import PolymerAssignmentStep
 
 __all__ = ["ActivationDistanceStep", "HicEvaluationStep", "DamidActivationDistanceStep",
-           "NuclDamidActivationDistanceStep"]
+           "NuclDamidActivationDistanceStep", "FishAssignmentStep", "PolymerAssignmentStep"]

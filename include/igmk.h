@@ -210,6 +210,27 @@ int igmk_sprite_rg2_host(igmk_ctx* ctx, int n_clusters, const int32_t* region_pt
                          const int32_t* copy_ptr, const int32_t* beads,
                          float* rg2s, int32_t* copy_idx, int32_t* min_struct);
 
+/* Population rank matching - the arithmetic of the FISH and polymer assignment steps
+ * (igm/steps/FishAssignmentStep.py:23-79 get_pair_dists / get_rad_dists /
+ * get_min_max_and_idx and task :189-193, :214-219; igm/steps/PolymerAssignmentStep.py:24-33
+ * get_polymer_dists and task :118-125).  Item t has the bead ids a[2t], a[2t+1] (second
+ * -1 when the locus has one copy) and, when b != NULL, b[2t], b[2t+1]; b == NULL means the
+ * radial distance of a (np.linalg.norm of the coordinates).  Per structure s:
+ *   value[t][s]   = min (reduce 0) or max (reduce 1) over the copy combinations of
+ *                   np.linalg.norm(x_a - x_b) as float32
+ *   rank[t][s]    = np.argsort(np.argsort(value[t]))[s] with ties broken by structure index
+ *   matched[t][s] = target[t * target_stride + rank[t][s]]   (target_stride 0: one shared
+ *                   sorted distribution; target / matched may both be NULL)
+ * nstruct <= 16384.  As intended by the reference's docstring ALL len(ii)*len(jj)
+ * combinations of a pair enter the min / max; the reference's own get_pair_dists never
+ * advances its row counter (:33-40), so only single-copy pairs are defined there. */
+int igmk_rank_match_device(igmk_ctx* ctx, int64_t n_items, const int32_t* d_a, const int32_t* d_b,
+                           int reduce, const float* d_target, int64_t target_stride,
+                           float* d_matched, int32_t* d_rank, float* d_value, void* stream);
+int igmk_rank_match_host(igmk_ctx* ctx, int64_t n_items, const int32_t* a, const int32_t* b,
+                         int reduce, const float* target, int64_t target_stride,
+                         float* matched, int32_t* rank, float* value);
+
 /* Pinned host memory for zero-staging transfers (optional). */
 int igmk_host_alloc(void** ptr, int64_t bytes);
 int igmk_host_free(void* ptr);
