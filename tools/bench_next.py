@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the "next" kernels on the config-2 population (synthetic, 1000
 structures x 29 838 beads): K3 restraint selection over the records of an A-step,
-K4 SPRITE Rg^2 over random clusters, DamID activation distances of every locus,
+K4 SPRITE Rg^2 over random clusters, K5 rank matching of every polymer bond, DamID activation distances of every locus,
 haploid contact map.  Kernel-only times (CUDA events inside the library)."""
 import argparse
 import json
@@ -61,6 +61,13 @@ def main():
     eng.damid_actdist(np.arange(nh), pe, None, 5000.0, 0.05, 1)
     ms = eng.last_kernel_ms()
     out["DamID"] = {"loci": nh, "ms": ms, "loci_per_s": nh / (ms * 1e-3)}
+    # K5: every polymer bond of the population with per-bond targets (PolymerAssignmentStep)
+    bonds = np.arange(nbead - 1, dtype=np.int32)
+    neg = np.full(nbead - 1, -1, np.int32)
+    tgt = np.sort(rng.uniform(50, 900, args.nstruct)).astype(np.float32)
+    eng.rank_match(np.stack([bonds, neg], 1), np.stack([bonds + 1, neg], 1), "min", tgt, want_rank=False, want_value=False)
+    ms = eng.last_kernel_ms()
+    out["K5_polymer"] = {"bonds": int(nbead - 1), "ms": ms, "bond_structs_per_s": (nbead - 1) * args.nstruct / (ms * 1e-3)}
     # haploid contact map, first 2048 rows against all columns
     eng.contact_counts_haploid(0, 2048, 0, nh)
     ms = eng.last_kernel_ms()
