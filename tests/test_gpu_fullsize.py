@@ -89,3 +89,65 @@ def test_fullsize_sample_against_oracle(cfg2):
     assert np.array_equal(got["contact_count"], exp["contact_count"])
     assert np.array_equal(got["o"], exp["o"])
     assert np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))
+
+
+# ---------------------------------------------------------------- config 5
+@pytest.fixture(scope="module")
+def cfg5():
+    """Config 5 of BASELINE.json: 1000 structures at 50 kb male diploid (~119 k beads,
+    1.43 GB of coordinates - far larger than L2), coordinates resident on one GPU."""
+    import torch
+    from igm_b200 import synthetic
+    from igm_b200.engine import ActdistEngine
+    from igm_b200.steps.ActivationDistanceStep import filter_candidates
+    dev = torch.device("cuda:0")
+    bins = synthetic.genome_bins(50_000)
+    chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins)
+    nbead = len(chrom_bead)
+    radius = float(synthetic.bead_radius(nbead))
+    coords = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, 1000, radius, 20261022, dev)
+    eng = ActdistEngine(nbead=nbead, nstruct=1000, device=0)
+    eng.upload_coordinates(coords)
+    radii = np.full(nbead, radius, np.float32)
+    eng.set_index(ci.ptr, ci.beads, chrom_hap, radii)
+    pm = synthetic.make_prob_matrix(chrom_hap, seed=20261022)
+    ii, jj, pw = filter_candidates(pm, 0.01, 0.01)
+    del pm
+    yield dict(eng=eng, ii=ii, jj=jj, pw=pw, coords=coords, radii=radii, chrom_hap=chrom_hap, ci=ci,
+               dev=dev, nbead=nbead)
+    eng.close()
+
+
+def test_config5_stress(cfg5):
+    """The whole sigma = 0.01 list of the 50 kb genome in one call (J-block processing
+    order, locus tile); a strided 1/16 subset recomputed as its own (short, unordered)
+    list and by the cross-check kernel must agree bit for bit; a sample against the oracle."""
+    import torch
+    eng, ii, jj, pw, ci = cfg5["eng"], cfg5["ii"], cfg5["jj"], cfg5["pw"], cfg5["ci"]
+    assert cfg5["nbead"] > 115_000 and len(ii) > 10_000_000
+    fast = eng.actdist(ii, jj, pw, None, 2.0, 0, "LB", 0)
+    assert int((fast["nrec"] > 0).sum()) == len(ii)            # it_corr = 0, p >= sigma > 0
+    sub = np.arange(3, len(ii), 16)
+    again = eng.actdist(ii[sub], jj[sub], pw[sub], None, 2.0, 0, "LB", 0)
+    assert again.tobytes() == fast[sub].tobytes()
+    simple = eng.actdist(ii[sub], jj[sub], pw[sub], None, 2.0, 0, "LB", 1)
+    assert simple.tobytes() == fast[sub].tobytes()
+
+    sel = np.sort(np.random.default_rng(5).choice(len(ii), 300, replace=False))
+    hap = np.unique(np.concatenate([ii[sel], jj[sel]]))
+    beads = np.unique(np.concatenate([ci[h] for h in hap]))
+    remap = -np.ones(cfg5["nbead"], np.int64)
+    remap[beads] = np.arange(len(beads))
+    subc = cfg5["coords"][torch.from_numpy(beads).to(cfg5["dev"])].cpu().numpy()
+
+    class _CI:
+        def __getitem__(self, i):
+            return [int(remap[b]) for b in ci[i]]
+    _, dets = orc.run_pairs(ii[sel], jj[sel], pw[sel], np.zeros(len(sel)), subc, cfg5["radii"][beads],
+                            cfg5["chrom_hap"], _CI(), 0, 2.0, orc.MODE_LB)
+    exp = orc.details_to_arrays(dets)
+    got = fast[sel]
+    assert np.array_equal(got["d2_sel_bits"], exp["d2_sel_bits"])
+    assert np.array_equal(got["contact_count"], exp["contact_count"])
+    assert np.array_equal(got["o"], exp["o"])
+    assert np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))

@@ -2,7 +2,8 @@
 """Whole Hi-C A-step through the Step drop-in (setup -> task -> reduce) on config 2 of
 BASELINE.json, files included: a synthetic .hss (1000 structures x 29 838 beads) and .hcs
 are written to a scratch directory, then igm_b200.steps.ActivationDistanceStep(cfg).run()
-is timed phase by phase.  What `igm-run` would see (bin/igm-run:164-166)."""
+is timed phase by phase for every sigma of the demo sweep (1.0 -> 0.01, iterative
+correction on, each iteration reading the previous actdist.hdf5).  What `igm-run` would see (bin/igm-run:164-166)."""
 import json
 import os
 import sys
@@ -12,6 +13,10 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+# the sigma sweep of demo/config_file.json:35-50 (config 2: "sigma sweep 1.0 -> 0.01")
+SIGMAS = (1.0, 0.2, 0.1, 0.05, 0.02, 0.01)
 
 
 def main():
@@ -40,10 +45,10 @@ def main():
     out = {"nstruct": nstruct, "nbead": nbead, "write_inputs_s": t_files, "sigmas": []}
     cfg = Config({"parameters": {"workdir": tmp, "tmp_dir": os.path.join(tmp, "tmp")},
                   "optimization": {"structure_output": hss, "iter_corr_knob": 1},
-                  "restraints": {"Hi-C": {"input_matrix": hcs, "intra_sigma_list": [0.05, 0.01],
-                                          "inter_sigma_list": [0.05, 0.01], "contact_range": 2.0}},
+                  "restraints": {"Hi-C": {"input_matrix": hcs, "intra_sigma_list": list(SIGMAS),
+                                          "inter_sigma_list": list(SIGMAS), "contact_range": 2.0}},
                   "runtime": {"Hi-C": {}, "opt_iter": 0}})
-    for k in range(2):
+    for k in range(len(SIGMAS)):
         step = ActivationDistanceStep(cfg)
         ph = {}
         t = time.perf_counter(); step.setup(); ph["setup_s"] = time.perf_counter() - t
@@ -62,6 +67,9 @@ def main():
         # next sigma (what igm-run does between A/M iterations, bin/igm-run:175-305)
         cfg["runtime"]["Hi-C"].pop("intra_sigma"); cfg["runtime"]["Hi-C"].pop("inter_sigma")
         cfg["runtime"]["opt_iter"] += 1
+    out["sweep_pairs"] = int(sum(p["pairs"] for p in out["sigmas"]))
+    out["sweep_total_s"] = float(sum(p["total_s"] for p in out["sigmas"]))
+    out["sweep_pairs_per_s_whole_step"] = out["sweep_pairs"] / out["sweep_total_s"]
     print(json.dumps(out))
 
 
