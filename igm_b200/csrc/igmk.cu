@@ -74,6 +74,7 @@ struct igmk_ctx {
     void* d_order = nullptr; size_t order_bytes = 0;    // keys / values / cub temp of order_pairs()
     int tile_block = 512;        // IGMK_TILE_BLOCK (0: no shared-memory locus-i tile)
     int tile_slots = 1;          // IGMK_TILE_SLOTS (2 slots shrink L1 to 15 KB at N = 1000: slower)
+    int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
 };
 
 static int ensure(void** p, size_t* cap, size_t bytes) {
@@ -134,6 +135,10 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov && atoll(ov) > 0) c->host_slice_pairs = atoll(ov);
     ov = getenv("IGMK_WARPS_PER_CTA");
     if (ov) c->warps_per_cta = atoi(ov);
+    ov = getenv("IGMK_BLOCK_STOP");
+    if (ov) c->block_stop = atoi(ov);
+    if (c->block_stop < kRankCap) c->block_stop = kRankCap;
+    if (c->block_stop > kBlockListCap) c->block_stop = kBlockListCap;
     *out = c;
     return IGMK_OK;
 }
@@ -392,6 +397,7 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     P.n_pairs = n_pairs; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
     P.n_hap = c->n_hap; P.contact_range = contact_range; P.it_corr = it_corr; P.mode = mode;
     P.negzero2 = 0x8000000080000000ull;
+    P.block_stop = c->block_stop;
     P.perm = nullptr;
     P.peers = (const u64*)d_peers; P.n_peers = n_peers;
     P.pexp32 = nullptr; P.plast32 = nullptr; P.damid_R = 0.0; P.zero_bead = c->nbead;
@@ -462,6 +468,7 @@ extern "C" int igmk_damid_actdist_device(igmk_ctx* c, int64_t n_loci, const int3
     P.n_pairs = n_loci; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
     P.n_hap = c->n_hap; P.contact_range = 0.f; P.it_corr = it_corr; P.mode = IGMK_MODE_LB;
     P.negzero2 = 0x8000000080000000ull;
+    P.block_stop = c->block_stop;
     P.pexp32 = d_pexp; P.plast32 = d_plast;
     P.damid_R = nucleus_radius * (1.0 - contact_range);       // np.array(nucleus_param) * (1 - contact_range), :436
     P.zero_bead = c->nbead;

@@ -47,6 +47,7 @@ struct Group {
     uint32_t ctl;       // candidate counter
     int cap;            // list capacity
     uint32_t red;       // BLOCK: [2][3][32] words
+    uint32_t list2;     // BLOCK: short list of the final <= kRankCap candidates
     int parity;
 
     __device__ __forceinline__ int sum(int x) {
@@ -80,6 +81,28 @@ struct Group {
         s = __reduce_add_sync(0xffffffffu, vs);
         mn = __reduce_min_sync(0xffffffffu, vmn);
         mx = __reduce_max_sync(0xffffffffu, vmx);
+    }
+    // BLOCK only: exclusive prefix sum of x over the group's threads (one barrier).
+    __device__ __forceinline__ int exclusive_scan(int x) {
+        const int lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
+        int incl = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const uint32_t r = red + parity * 384;
+        parity ^= 1;
+        if (lane == 31) sts32(r + warp * 4, (uint32_t)incl);
+        __syncthreads();
+        int vs = (lane < nw) ? (int)lds32(r + lane * 4) : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, vs, d);
+            if (lane >= d) vs += y;
+        }
+        const int below = __shfl_sync(0xffffffffu, vs, (warp > 0) ? warp - 1 : 0);
+        return ((warp > 0) ? below : 0) + incl - x;
     }
     __device__ __forceinline__ void sync() {
         if (BLOCK) __syncthreads(); else __syncwarp();
@@ -566,12 +589,19 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     }
 
     // ---- bisection on the 16-bit keys (each thread reads only its own quads)
+    // Warp groups narrow the key bracket down to <= kRankCap candidates.  CTA groups stop
+    // at <= P.block_stop (a key pass over the whole population costs far more there than a
+    // pass over a short list of re-materialised values) and finish the bisection on the
+    // full float32 patterns of the list (below).
     uint32_t lo = kmin, hi = (kmax < kmin) ? kmin : kmax;
     int cb = 0, ch = d.keep * P.nstruct;
-    while (lo < hi && (ch - cb) > kRankCap) {
+    const int stop = BLOCK ? P.block_stop : kRankCap;
+    int cl_lo = 0, cl_hi = -1;             // BLOCK: this thread's own #{key < lo}, #{key <= hi}
+    while (lo < hi && (ch - cb) > stop) {
         const uint32_t mid = (lo + hi) >> 1;
-        const int c = g.sum(count_le(g.kscr, g.kstride, nq, mid | (mid << 16)));
-        if (c > o) { hi = mid; ch = c; } else { lo = mid + 1; cb = c; }
+        const int cl = count_le(g.kscr, g.kstride, nq, mid | (mid << 16));
+        const int c = g.sum(cl);
+        if (c > o) { hi = mid; ch = c; cl_hi = cl; } else { lo = mid + 1; cb = c; cl_lo = cl; }
     }
     const uint32_t lo2 = lo | (lo << 16), hi2 = hi | (hi << 16);
     int n_list;
@@ -579,11 +609,22 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     if ((ch - cb) <= g.cap) {
         // ---- compact the candidates' locations, then re-materialise them in
         // full precision with the whole group in parallel
-        g.sync();                               // counter = 0 visible
-        scan_range(g.kscr, g.kstride, nq, lo2, hi2, [&](int e) {
-            const uint32_t slot = atoms_inc(g.ctl);
-            if (slot < (uint32_t)g.cap) sts32(g.list + slot * 4, ((uint32_t)g.tid << 16) | (uint32_t)e);
-        });
+        if (BLOCK) {
+            // no atomics: every thread knows how many candidates it owns from the passes
+            // that set the bracket, so an exclusive scan gives it a private list range
+            if (cl_hi < 0) cl_hi = count_le(g.kscr, g.kstride, nq, hi2);     // hi never moved (uniform)
+            uint32_t pos = (uint32_t)g.exclusive_scan(cl_hi - cl_lo);
+            scan_range(g.kscr, g.kstride, nq, lo2, hi2, [&](int e) {
+                if (pos < (uint32_t)g.cap) sts32(g.list + pos * 4, ((uint32_t)g.tid << 16) | (uint32_t)e);
+                ++pos;
+            });
+        } else {
+            g.sync();                               // counter = 0 visible
+            scan_range(g.kscr, g.kstride, nq, lo2, hi2, [&](int e) {
+                const uint32_t slot = atoms_inc(g.ctl);
+                if (slot < (uint32_t)g.cap) sts32(g.list + slot * 4, ((uint32_t)g.tid << 16) | (uint32_t)e);
+            });
+        }
         g.sync();
         n_list = ch - cb;
         for (int t = g.tid; t < n_list; t += g.nthr) {
@@ -625,9 +666,47 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
         n_list = ch - cb;
     }
 
-    // ---- exact rank inside one warp: the (o - cb)-th smallest candidate
+    int r = o - cb;                        // rank of the answer inside the list
+    uint32_t sel = g.list;
+    if (BLOCK && n_list > kRankCap) {
+        // ---- CTA groups: bisection on the full 32-bit patterns of the list (a pass reads
+        // n_list / nthr words per thread) until <= kRankCap values remain
+        uint32_t vlo = 0u, vhi = 0x7f800000u;
+        int nb = 0, nh = n_list;
+        // all list values lie in [lo << 16, hi << 16 | 0xffff] except in the fat-key branch,
+        // where the bracket is narrower still; the key bracket is a valid start for both
+        vlo = lo << 16; vhi = (hi << 16) | 0xffffu;
+        while (vlo < vhi && (nh - nb) > kRankCap) {
+            const uint32_t mid = vlo + ((vhi - vlo) >> 1);
+            int c = 0;
+            for (int t = g.tid; t < n_list; t += g.nthr) c += (lds32(g.list + t * 4) <= mid) ? 1 : 0;
+            c = g.sum(c);
+            if (c > r) { vhi = mid; nh = c; } else { vlo = mid + 1; nb = c; }
+        }
+        if ((nh - nb) > kRankCap) {
+            // vlo == vhi: every remaining value has the same bit pattern
+            emit_result(P, g.tid, pair, d, vlo, cnt, o_rep, p, extra);
+            return;
+        }
+        // survivors -> short list (<= kRankCap shared atomics)
+        if (g.tid == 0) sts32(g.ctl, 0u);
+        g.sync();
+        for (int t = g.tid; t < n_list; t += g.nthr) {
+            const uint32_t x = lds32(g.list + t * 4);
+            if (x >= vlo && x <= vhi) {
+                const uint32_t slot = atoms_inc(g.ctl);
+                if (slot < (uint32_t)kRankCap) sts32(g.list2 + slot * 4, x);
+            }
+        }
+        g.sync();
+        sel = g.list2;
+        r -= nb;
+        n_list = nh - nb;
+    }
+
+    // ---- exact rank inside one warp: the r-th smallest candidate
     if (g.leader_warp()) {
-        const uint32_t ans = warp_select(g.list, n_list, o - cb, g.tid & 31);
+        const uint32_t ans = warp_select(sel, n_list, r, g.tid & 31);
         emit_result(P, g.tid, pair, d, ans, cnt, o_rep, p, extra);
     }
 }
@@ -663,6 +742,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     g.kscr = smem_addr(s_keys) + (uint32_t)(warp * 2 * V * 32 + g.tid) * 16u;
     g.kstride = 32u * 16u;
     g.red = 0u;
+    g.list2 = 0u;
     g.parity = 0;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = smem_addr(s_slot); tile.nslots = P.tile_slots;
@@ -711,6 +791,7 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     __shared__ uint32_t s_list[kBlockListCap];
     __shared__ uint32_t s_cnt;
     __shared__ uint32_t s_red[2 * 96];
+    __shared__ uint32_t s_list2[kRankCap];
     Group<true> g;
     g.tid = threadIdx.x;
     g.nthr = blockDim.x;
@@ -720,6 +801,7 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     g.kscr = smem_addr(s_keys) + (uint32_t)threadIdx.x * 16u;
     g.kstride = (uint32_t)blockDim.x * 16u;
     g.red = smem_addr(s_red);
+    g.list2 = smem_addr(s_list2);
     g.parity = 0;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;

@@ -155,6 +155,59 @@ def test_jblock_order_and_locus_tile(nstruct, tile_block, monkeypatch):
             _check_against_details(res, dets)
 
 
+@pytest.mark.parametrize("block_stop", [32, 100, 512, 1024])
+@pytest.mark.parametrize("nstruct", [1500, 10000])
+def test_block_stop_variants(nstruct, block_stop, monkeypatch):
+    """CTA groups: the key bisection stops at <= IGMK_BLOCK_STOP candidates, which are then
+    compacted without atomics and bisected on their full float32 patterns."""
+    from igm_b200 import synthetic
+    monkeypatch.setenv("IGMK_BLOCK_STOP", str(block_stop))
+    pop = synthetic.make_population(2_000_000, nstruct, seed=900 + nstruct, genome_scale=0.004)
+    rng = np.random.default_rng(nstruct + block_stop)
+    nh = pop.n_hap
+    ii = rng.integers(0, nh, 150)
+    jj = rng.integers(0, nh, 150)
+    k = ii < jj
+    ii, jj = ii[k].astype(np.int32), jj[k].astype(np.int32)
+    pw = np.concatenate([rng.uniform(0.0005, 1.0, len(ii) - 3), [1.0, 0.9999, 1e-4]])
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, 0, 2.0, MODES[mode])
+            res = eng.actdist(ii, jj, pw, pl, 2.0, 0, mode, 0)
+            _check_against_details(res, dets)
+
+
+@pytest.mark.parametrize("nconf", [1, 3, 40])
+def test_block_groups_many_equal_distances(nconf, monkeypatch):
+    """CTA groups on populations whose structures are copies of a few conformations: every
+    distance value occurs hundreds of times (fat keys, lists full of duplicates, the
+    all-equal exits of both bisections)."""
+    from igm_b200.population import Population
+    from igm_b200 import synthetic
+    nstruct = 2100
+    bins = np.array([6, 5, 3])
+    chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins, n_diploid_chroms=2)
+    nbead = len(chrom_bead)
+    rng = np.random.default_rng(nconf)
+    conf = (rng.standard_normal((nbead, nconf, 3)) * 300.0).astype(np.float32)
+    crd = np.ascontiguousarray(conf[:, rng.integers(0, nconf, nstruct), :])
+    pop = Population(crd, np.full(nbead, 50.0, np.float32), chrom_bead, ci, copy_bead)
+    ii, jj = np.triu_indices(pop.n_hap, 1)
+    ii, jj = ii.astype(np.int32), jj.astype(np.int32)
+    pw = rng.uniform(0.001, 1.0, len(ii))
+    pl = np.zeros(len(ii))
+    for stop in ("64", "1024"):
+        monkeypatch.setenv("IGMK_BLOCK_STOP", stop)
+        with _engine(pop) as eng:
+            for mode in ("lb", "gp"):
+                _, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(),
+                                        pop.copy_index, 0, 2.0, MODES[mode])
+                res = eng.actdist(ii, jj, pw, pl, 2.0, 0, mode, 0)
+                _check_against_details(res, dets)
+
+
 def test_degenerate_inputs():
     """Identical coordinates (all distances equal), empty and i == j inputs."""
     from igm_b200.population import CopyIndex, Population
