@@ -30,10 +30,14 @@
 
 namespace igmk {
 
+#ifndef IGMK_STAGE_J
+#define IGMK_STAGE_J 0
+#endif
 constexpr int kRankCap = 32;        // bisection stops at <= kRankCap candidates
 constexpr int kWarpListCap = 64;    // candidate list words per warp group
 constexpr int kBlockListCap = 1024; // candidate list words per CTA group
 constexpr int kMaxQuads = 64;       // key quads per thread: bf16 pass counters stay exact
+constexpr bool kStageJ = IGMK_STAGE_J != 0;   // warp groups: locus-j rows staged one chunk ahead (cp.async)
 
 // ------------------------------------------------------------------ groups
 // Shared scratch is addressed through 32-bit shared-window addresses.
@@ -48,6 +52,7 @@ struct Group {
     int cap;            // list capacity
     uint32_t red;       // BLOCK: [2][3][32] words
     uint32_t list2;     // BLOCK: short list of the final <= kRankCap candidates
+    uint32_t bbuf;      // warp groups with kStageJ: this thread's slot of the locus-j staging buffer
     int parity;
 
     __device__ __forceinline__ int sum(int x) {
@@ -146,10 +151,15 @@ __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const Pair
 
 // AS: the rows of locus i come from the CTA's shared-memory tile (as0 / as1 =
 // shared addresses of the a0 / a1 rows, same layout as in HBM).
-template <int SH, bool AS>
+// BS: the rows of locus j are staged one chunk ahead through shared memory (`bbuf`: six
+// 16-byte slots of this thread, 512 bytes apart: b0 x / y / z, b1 x / y / z) with
+// asynchronous copies, so their L2 latency overlaps the arithmetic of the previous chunk
+// without costing registers.  Warp groups only (slot stride 512 bytes = 32 lanes).
+template <int SH, bool AS, bool BS>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
                                           const PairPtrs& pp, int tid, int nthr, int V,
                                           uint32_t kscr, uint32_t kstride, uint32_t as0, uint32_t as1,
+                                          uint32_t bbuf,
                                           int& cnt, uint32_t& mn2, uint32_t& mx2) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
@@ -169,6 +179,18 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
     // in generic pairs only NH is not known at compile time
     const int nh = (NS == 4) ? ((d.keep > 2) ? 2 : 1) : 1;
     uint32_t dst = kscr;
+    // BS: the staging slots are this thread's LAST six key-quad slots, which the keys
+    // themselves only reach at the end of the fill: chunk k may be staged while
+    // nh * k <= 2 V - 6 (the keys of chunks < k occupy slots 0 .. nh k - 1); later
+    // chunks are loaded directly.  Shapes with one quad per chunk stage every chunk.
+    const int vlast = (BS && 2 * V >= 6) ? (2 * V - 6) / nh : -1;
+    if (BS && vlast >= 0) {
+        if (tid < P.nchunks) {             // chunk 0
+            cp_async_row(bbuf, pb0);
+            cp_async_row(bbuf + 1536u, pb1);
+        }
+        cp_async_commit();
+    }
 
     // The chunk loop is deliberately NOT unrolled (instruction-cache footprint and
     // register pressure: 48 registers of loaded coordinates are live here).
@@ -190,7 +212,17 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
         }
         {
             float s[4][NS];   // [q][slot]
-            b0 = load_row6<LD_STREAM>(pb0); b1 = load_row6<LD_STREAM>(pb1);
+            if (BS && v <= vlast) {            // uniform
+                cp_async_wait_all();           // this thread's own copies of chunk v have landed
+                b0 = load_row6_shared(bbuf); b1 = load_row6_shared(bbuf + 1536u);
+                if (v < vlast && c + nthr < P.nchunks) {   // chunk v + 1 -> the same slots (read above, program order)
+                    cp_async_row(bbuf, pb0 + vstride);
+                    cp_async_row(bbuf + 1536u, pb1 + vstride);
+                }
+                cp_async_commit();
+            } else {
+                b0 = load_row6<LD_STREAM>(pb0); b1 = load_row6<LD_STREAM>(pb1);
+            }
             if (AS) {
                 a0 = load_row6_shared(sa0); a1 = load_row6_shared(sa1);
             } else {
@@ -544,18 +576,18 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
         const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
         const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
         switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  fill_keys<SH_FULL4, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
-            case SH_INTRA2: fill_keys<SH_INTRA2, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
-            case SH_GP4:    fill_keys<SH_GP4, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
-            default:        fill_keys<SH_GENERIC, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            case SH_FULL4:  fill_keys<SH_FULL4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
         }
         tile_release(tile, tslot, g.tid);
     } else {
         switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  fill_keys<SH_FULL4, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
-            case SH_INTRA2: fill_keys<SH_INTRA2, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
-            case SH_GP4:    fill_keys<SH_GP4, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
-            default:        fill_keys<SH_GENERIC, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            case SH_FULL4:  fill_keys<SH_FULL4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
         }
     }
     const int nh = (d.keep > 2) ? 2 : 1;
@@ -743,6 +775,9 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     g.kstride = 32u * 16u;
     g.red = 0u;
     g.list2 = 0u;
+    g.bbuf = 0u;
+    if (kStageJ && !DAMID && 2 * V >= 6)          // the thread's last six key-quad slots
+        g.bbuf = g.kscr + (uint32_t)(2 * V - 6) * 512u;
     g.parity = 0;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = smem_addr(s_slot); tile.nslots = P.tile_slots;
@@ -802,6 +837,7 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     g.kstride = (uint32_t)blockDim.x * 16u;
     g.red = smem_addr(s_red);
     g.list2 = smem_addr(s_list2);
+    g.bbuf = 0u;
     g.parity = 0;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;

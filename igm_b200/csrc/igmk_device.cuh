@@ -428,6 +428,18 @@ __device__ __forceinline__ Row6 load_row6_shared(uint32_t addr) {   // same layo
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+1024];" : "=l"(r.z01), "=l"(r.z23) : "r"(addr) : "memory");
     return r;
 }
+// Asynchronous 16-byte copies global -> shared (LDGSTS, L2 only): the rows of locus j of
+// the NEXT chunk travel while the current chunk is being computed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_row(uint32_t dst, const float* p) {     // x / y / z of one row chunk
+    cp_async16(dst, p);
+    cp_async16(dst + 512u, p + kSeg);
+    cp_async16(dst + 1024u, p + 2 * kSeg);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 template <int HINT>
 __device__ __forceinline__ Row6 load_row6(const float* p) {
     Row6 r;
