@@ -446,6 +446,30 @@ def main():
             line["cpu_baseline"] = cpu_baseline(sub, radii[beads], chrom_hap, _CI2(), ii[:nb * 8],
                                                 jj[:nb * 8], pw[:nb * 8], args.it_corr, args.mode,
                                                 args.cpu_seconds)
+            # second CPU figure and a much larger parity gate: the plain-C oracle (OpenMP,
+            # all host threads) over the same sample, compared with the GPU results of the
+            # last timed step pair by pair
+            from oracle import c_oracle
+            if c_oracle.available():
+                n_c = int(min(len(ii), nb * 8, 1_000_000))
+                t0 = time.perf_counter()
+                exp_c = c_oracle.run_pairs(ii[:n_c], jj[:n_c], pw[:n_c], np.zeros(n_c), sub, radii[beads],
+                                           chrom_hap, ci.ptr, remap[ci.beads].astype(np.int32),
+                                           args.it_corr, 2.0, 0 if args.mode == "LB" else 1)
+                dt_c = time.perf_counter() - t0
+                got_c = last[rank][:n_c].cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)
+                ok = exp_c["o"] >= 0
+                equal = bool(np.array_equal(got_c["d2_sel_bits"][ok], exp_c["d2_sel_bits"][ok])
+                             and np.array_equal(got_c["contact_count"], exp_c["contact_count"])
+                             and np.array_equal(got_c["o"], exp_c["o"])
+                             and np.array_equal(got_c["p"].view(np.uint64), exp_c["p"].view(np.uint64))
+                             and np.array_equal(got_c["nrec"], exp_c["nrec"]))
+                line["cpu_baseline"]["c_port"] = {
+                    "value": n_c / dt_c, "unit": UNIT, "cores": os.cpu_count() or 1,
+                    "sample": "first %d pairs, oracle/actdist_oracle.c with OpenMP; %.1f s" % (n_c, dt_c),
+                    "gpu_results_equal": equal}
+                line["config"]["parity_c_oracle_pairs"] = n_c
+                line["config"]["parity_c_oracle_ok"] = equal
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
