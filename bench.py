@@ -514,6 +514,20 @@ def run_reference_arm(args, rank, world):
             per_step.append(info["value"])
             per_ms.append((time.perf_counter() - t0) * 1e3)
     value = float(np.mean(per_step))
+    # for context: the plain-C oracle (OpenMP) on the same sample
+    c_port = None
+    try:
+        from oracle import c_oracle
+        if c_oracle.available():
+            n_c = int(min(len(si), 400000))
+            t0 = time.perf_counter()
+            c_oracle.run_pairs(si[:n_c], sj[:n_c], spw[:n_c], np.zeros(n_c), sub, radii, chrom_hap, ci.ptr,
+                               remap[ci.beads].astype(np.int32), args.it_corr, 2.0,
+                               0 if args.mode == "LB" else 1)
+            c_port = {"value": n_c / (time.perf_counter() - t0), "unit": UNIT, "cores": cores,
+                      "sample": "first %d pairs, oracle/actdist_oracle.c with OpenMP" % n_c}
+    except Exception as e:          # the C oracle is optional here
+        c_port = {"unavailable": str(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(per_ms)),
@@ -526,7 +540,7 @@ def run_reference_arm(args, rank, world):
                                                                 nbead, args.mode, args.sigma),
                    "nstruct": args.nstruct, "nbead": nbead},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
-                         "sample": info["sample"]},
+                         "sample": info["sample"], "c_port": c_port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -132,6 +132,14 @@ class ActdistEngine:
         self.n_hap = n_hap
         self._ncopies = np.diff(copy_ptr)
         self._chrom_hap = chrom_hap
+        # whole-chromosome ploidy (igm/_preprocess.py:66-86): every locus of a chromosome
+        # has the same number of copies, so no intra-chromosomal pair can violate q5
+        nchrom = int(chrom_hap.max()) + 1 if n_hap else 0
+        lo = np.full(nchrom, np.iinfo(np.int32).max, np.int64)
+        hi = np.full(nchrom, -1, np.int64)
+        np.minimum.at(lo, chrom_hap, self._ncopies)
+        np.maximum.at(hi, chrom_hap, self._ncopies)
+        self._uniform_ploidy = bool(np.all((lo == hi) | (hi < 0))) and (n_hap == 0 or int(chrom_hap.min()) >= 0)
 
     # -- A-step ----------------------------------------------------------
     def _validate_pairs(self, i, j, mode):
@@ -139,7 +147,7 @@ class ActdistEngine:
             return
         if i.min() < 0 or j.min() < 0 or i.max() >= self.n_hap or j.max() >= self.n_hap:
             raise ValueError("pair index out of range [0, %d)" % self.n_hap)
-        if mode == MODE_LB:
+        if mode == MODE_LB and not getattr(self, "_uniform_ploidy", False):
             # quirk q5: the reference's intra branch reads uninitialised
             # memory when the two loci have different copy counts - refuse instead.
             bad = (self._chrom_hap[i] == self._chrom_hap[j]) & (self._ncopies[i] != self._ncopies[j]) & (i != j)

@@ -626,13 +626,19 @@ class _Writer:
     GROUP_INTERNAL_K = 16  # B-tree node holds up to 2K children
 
     def __init__(self):
-        self.buf = bytearray()
+        # the image is kept as a list of byte blocks and streamed to the file at the
+        # end: large datasets are written straight from the arrays' own memory
+        self.parts = []
+        self.pos = 0
 
-    def alloc(self, data: bytes) -> int:
-        if len(self.buf) % 8:
-            self.buf += b"\0" * (-len(self.buf) % 8)
-        addr = len(self.buf)
-        self.buf += data
+    def alloc(self, data) -> int:
+        pad = -self.pos % 8
+        if pad:
+            self.parts.append(b"\0" * pad)
+            self.pos += pad
+        addr = self.pos
+        self.parts.append(data)
+        self.pos += len(data)
         return addr
 
     def write_dataset(self, arr: np.ndarray, attrs: Optional[dict] = None) -> int:
@@ -641,8 +647,8 @@ class _Writer:
             arr = arr.astype(arr.dtype.newbyteorder("<"))
         if arr.dtype.kind == "U":
             arr = arr.astype("S")
-        raw = arr.tobytes()
-        daddr = self.alloc(raw) if raw else _UNDEF
+        raw = memoryview(arr.reshape(-1).view(np.uint8)) if arr.size else b""
+        daddr = self.alloc(raw) if len(raw) else _UNDEF
         msgs = [
             _message(0x01, _dataspace_message(arr.shape)),
             _message(0x03, _dtype_message(arr.dtype), flags=1),
@@ -734,13 +740,15 @@ def write_h5(path: str, datasets: Dict[str, Any], attrs: Optional[dict] = None) 
         hdr, _, _ = w.write_group(links)
         root_links[g] = hdr
     root_hdr, bt, heap = w.write_group(root_links, attrs)
-    eof = len(w.buf) + (-len(w.buf) % 8)
-    w.buf += b"\0" * (eof - len(w.buf))
+    eof = w.pos + (-w.pos % 8)
+    if eof > w.pos:
+        w.parts.append(b"\0" * (eof - w.pos))
     sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0,
                             _Writer.GROUP_LEAF_K, _Writer.GROUP_INTERNAL_K, 0)
     sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
     sb += struct.pack("<QQII", 0, root_hdr, 1, 0) + struct.pack("<QQ", bt, heap)
     assert len(sb) == 96
-    w.buf[0:96] = sb
+    w.parts[0] = sb
     with open(path, "wb") as fh:
-        fh.write(bytes(w.buf))
+        for part in w.parts:
+            fh.write(part)

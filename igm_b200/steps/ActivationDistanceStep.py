@@ -47,19 +47,34 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
     NumPy >= 2 happens in float32.  ``i == j`` entries are
     dropped (they never produce a record, :379-380).  Returns (i, j, pwish64).
     """
-    rows = pm.rows().astype(np.int64)
-    cols = pm.indices.astype(np.int64)
     dt = np.dtype(compare_dtype)
-    pw = pm.data.astype(dt)
-    intra = pm.chrom[rows] == pm.chrom[cols]
-    keep = np.zeros(len(rows), dtype=bool)
-    if intra_sigma is not False and intra_sigma is not None:
-        keep |= intra & (pw >= dt.type(intra_sigma))
-    if inter_sigma is not False and inter_sigma is not None:
-        keep |= (~intra) & (pw >= dt.type(inter_sigma))
-    keep &= rows != cols
-    return (rows[keep].astype(np.int32), cols[keep].astype(np.int32),
-            pm.data[keep].astype(np.float64))
+    pw = pm.data.astype(dt, copy=False)
+    use_intra = intra_sigma is not False and intra_sigma is not None
+    use_inter = inter_sigma is not False and inter_sigma is not None
+    if not (use_intra or use_inter):
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), np.zeros(0, np.float64)
+    # first cut on the probability alone (the smaller threshold), then the intra / inter
+    # distinction on the survivors only
+    lo = min([dt.type(x) for x, u in ((intra_sigma, use_intra), (inter_sigma, use_inter)) if u])
+    idx = np.flatnonzero(pw >= lo)
+    rows = pm.rows()[idx]
+    cols = pm.indices[idx].astype(np.int32, copy=False)
+    pk = pw[idx]
+    if not (use_intra and use_inter and dt.type(intra_sigma) == dt.type(inter_sigma)):
+        intra = pm.chrom[rows] == pm.chrom[cols]
+        keep = np.zeros(len(idx), dtype=bool)
+        if use_intra:
+            keep |= intra & (pk >= dt.type(intra_sigma))
+        if use_inter:
+            keep |= (~intra) & (pk >= dt.type(inter_sigma))
+        keep &= rows != cols
+    else:
+        keep = rows != cols
+    if not keep.all():
+        idx, rows, cols = idx[keep], rows[keep], cols[keep]
+    return (np.ascontiguousarray(rows), np.ascontiguousarray(cols),
+            pm.data[idx].astype(np.float64))
 
 
 def lookup_plast(last_actdist_file, n, ii, jj):
@@ -78,17 +93,58 @@ def lookup_plast(last_actdist_file, n, ii, jj):
     val = prob[m].astype(np.float32)
     if len(key) == 0:
         return out
-    order = np.argsort(key, kind="stable")
-    key, val = key[order], val[order]
-    # duplicates (none in files this step writes) are summed, as coo -> lil does
-    uk, start = np.unique(key, return_index=True)
-    sums = np.add.reduceat(val, start).astype(np.float32)
+    if len(key) > 1 and not np.all(key[1:] > key[:-1]):
+        order = np.argsort(key, kind="stable")
+        key, val = key[order], val[order]
+        # duplicates (none in files this step writes) are summed, as coo -> lil does
+        uk, start = np.unique(key, return_index=True)
+        sums = np.add.reduceat(val, start).astype(np.float32)
+    else:
+        # files written by this step list the records in candidate (CSR) order: the
+        # copy-0 x copy-0 keys are already strictly increasing
+        uk, sums = key, val
     q = ii.astype(np.int64) * n + jj.astype(np.int64)
+    if len(q) > 1 and len(uk) < len(q) and np.all(q[1:] > q[:-1]):
+        # sorted candidate list (CSR order) and fewer stored records than candidates (the
+        # usual case: the previous sigma was larger): look the records up in the list
+        pos = np.searchsorted(q, uk)
+        pos_c = np.minimum(pos, len(q) - 1)
+        hit = q[pos_c] == uk
+        out[pos_c[hit]] = sums[hit].astype(np.float64)
+        return out
     pos = np.searchsorted(uk, q)
     pos_c = np.minimum(pos, len(uk) - 1)
     hit = uk[pos_c] == q
     out[hit] = sums[pos_c[hit]].astype(np.float64)
     return out
+
+
+def pack_records(row, col, dist, prob):
+    """Task output: the four record columns as the rows of one (4, n) 32-bit array
+    (columnar, so reduce() hands them to the HDF5 writer without re-interleaving)."""
+    out = np.empty((4, len(row)), dtype=np.uint32)
+    out[0] = np.asarray(row, np.int32).view(np.uint32)
+    out[1] = np.asarray(col, np.int32).view(np.uint32)
+    out[2] = np.asarray(dist, np.float32).view(np.uint32)
+    out[3] = np.asarray(prob, np.float32).view(np.uint32)
+    return out
+
+
+def unpack_records(parts):
+    """Columns {row, col: int32; dist, prob: float32} of the concatenated task outputs
+    (:246-257).  Accepts the columnar arrays of pack_records and structured
+    ``actdist_shape`` arrays (what np.genfromtxt yields in the reference)."""
+    cols = []
+    for a in parts:
+        if a.dtype.names:
+            cols.append(pack_records(a["row"], a["col"], a["dist"], a["prob"]))
+        elif a.size == 0:
+            cols.append(np.zeros((4, 0), np.uint32))
+        else:
+            cols.append(a)
+    rec = cols[0] if len(cols) == 1 else (np.concatenate(cols, axis=1) if cols else np.zeros((4, 0), np.uint32))
+    return {"row": rec[0].view(np.int32), "col": rec[1].view(np.int32),
+            "dist": rec[2].view(np.float32), "prob": rec[3].view(np.float32)}
 
 
 _engine_cache = {}
@@ -169,7 +225,7 @@ class ActivationDistanceStep(Step):
         params = np.load(os.path.join(tmp_dir, "%d.in.npy" % batch_id))
         out_name = os.path.join(tmp_dir, "%d.out.npy" % batch_id)
         if params.size == 0:
-            np.save(out_name, np.zeros(0, dtype=actdist_shape))
+            np.save(out_name, np.zeros((4, 0), dtype=np.uint32))
             return
         import torch  # device enumeration only
         ndev = torch.cuda.device_count() if torch.cuda.is_available() else 0
@@ -182,9 +238,7 @@ class ActivationDistanceStep(Step):
                           it_corr=1 if it_corr == 1 else 0,
                           mode=dictHiC.get("gpu_mode", "LB"))
         row, col, dist, prob = eng.expand_records(ii, jj, res)
-        rec = np.empty(len(row), dtype=actdist_shape)
-        rec["row"], rec["col"], rec["dist"], rec["prob"] = row, col, dist, prob
-        np.save(out_name, rec)
+        np.save(out_name, pack_records(row, col, dist, prob))
         if dictHiC.get("write_text_tmp", False):
             # the reference's own wire format (:228-230), for byte-level comparison
             ad = np.repeat(np.sqrt(res["d2_sel_bits"].view(np.float32).astype(np.float64)), res["nrec"])
@@ -196,8 +250,8 @@ class ActivationDistanceStep(Step):
     def reduce(self):
         actdist_file = os.path.join(self.tmp_dir, "actdist.hdf5")
         last_actdist_file = self.cfg["runtime"]["Hi-C"].get("actdist_file", None)
-        parts = [np.load(os.path.join(self.tmp_dir, "%d.out.npy" % i)) for i in self.argument_list]
-        rec = np.concatenate(parts) if parts else np.zeros(0, dtype=actdist_shape)
+        columns = unpack_records([np.load(os.path.join(self.tmp_dir, "%d.out.npy" % i))
+                                  for i in self.argument_list])
 
         additional_data = []
         if "Hi-C" in self.cfg["runtime"]:
@@ -207,9 +261,7 @@ class ActivationDistanceStep(Step):
             additional_data.append("iter_{}".format(self.cfg["runtime"]["opt_iter"] - 1))
 
         tmp_actdist_file = actdist_file + ".tmp"
-        hdf5.write_h5(tmp_actdist_file, {
-            "row": np.ascontiguousarray(rec["row"]), "col": np.ascontiguousarray(rec["col"]),
-            "dist": np.ascontiguousarray(rec["dist"]), "prob": np.ascontiguousarray(rec["prob"])})
+        hdf5.write_h5(tmp_actdist_file, columns)
 
         swapfile = os.path.realpath(".".join([actdist_file, ] + additional_data))
         if last_actdist_file is not None:

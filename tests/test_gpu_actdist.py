@@ -289,6 +289,38 @@ def test_full_demo_sha(sigma):
                 assert np.array_equal(prob.view(np.uint32), orc.text_roundtrip(p_r).view(np.uint32))
 
 
+def test_mixed_ploidy_inside_a_chromosome_is_refused_in_lb_mode():
+    """the reference's LB intra branch reads uninitialised memory when the two loci
+    of one chromosome have different copy counts; the engine refuses such pairs (GP mode and
+    inter-chromosomal pairs are well defined and still match the oracle)."""
+    from igm_b200.population import CopyIndex, Population
+    rng = np.random.default_rng(12)
+    # loci 0..3 on chromosome 0 (locus 1 has a single copy), loci 4..5 on chromosome 1
+    ptr = np.array([0, 2, 3, 5, 7, 9, 10], np.int32)
+    beads = np.array([0, 6, 1, 2, 7, 3, 8, 4, 9, 5], np.int32)
+    chrom_hap = np.array([0, 0, 0, 0, 1, 1], np.int32)
+    nbead, nstruct = 10, 64
+    crd = (rng.standard_normal((nbead, nstruct, 3)) * 400).astype(np.float32)
+    chrom_bead = np.zeros(nbead, np.int32)
+    for h in range(6):
+        chrom_bead[beads[ptr[h]:ptr[h + 1]]] = chrom_hap[h]
+    pop = Population(crd, np.full(nbead, 60.0, np.float32), chrom_bead, CopyIndex(ptr, beads))
+    with _engine(pop) as eng:
+        with pytest.raises(ValueError):
+            eng.actdist(np.array([0], np.int32), np.array([1], np.int32), np.array([0.5]), None, 2.0, 0, "lb")
+        ii = np.array([0, 0, 1, 1, 2], np.int32)
+        jj = np.array([2, 4, 4, 5, 5], np.int32)          # equal-count intra pair and inter pairs
+        pw = np.array([0.5, 0.2, 0.9, 0.05, 1.0])
+        for mode in ("lb", "gp"):
+            _, dets = orc.run_pairs(ii, jj, pw, np.zeros(5), pop.coordinates, pop.radii, pop.chrom_hap(),
+                                    pop.copy_index, 0, 2.0, MODES[mode])
+            _check_against_details(eng.actdist(ii, jj, pw, None, 2.0, 0, mode), dets)
+        _, dets = orc.run_pairs(np.array([0], np.int32), np.array([1], np.int32), np.array([0.5]), np.zeros(1),
+                                pop.coordinates, pop.radii, pop.chrom_hap(), pop.copy_index, 0, 2.0, orc.MODE_GP)
+        _check_against_details(eng.actdist(np.array([0], np.int32), np.array([1], np.int32), np.array([0.5]),
+                                           None, 2.0, 0, "gp"), dets)
+
+
 def test_round4_random():
     """round4_to_f32 on device == float32(float('%.4f' % x)) incl. exact ties."""
     from igm_b200.population import Population

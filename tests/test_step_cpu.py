@@ -80,6 +80,32 @@ def test_lookup_plast_matches_coo_lil(tmp_path):
     assert np.array_equal(S.lookup_plast(None, n, ii, jj), np.zeros(300))
 
 
+@pytest.mark.parametrize("frac", [0.0, 0.3, 1.0])
+def test_lookup_plast_sorted_fast_paths(tmp_path, frac):
+    """Files this step writes list their records in candidate order (strictly increasing
+    copy-0 keys) and usually hold fewer pairs than the next, smaller sigma selects: both
+    shortcuts must give what the coo -> lil lookup of the reference gives (:145-156,177)."""
+    rng = np.random.default_rng(int(frac * 10))
+    n = 80
+    ii, jj = np.triu_indices(n, 1)
+    keep = np.sort(rng.choice(len(ii), 900, replace=False))
+    ii, jj = ii[keep].astype(np.int32), jj[keep].astype(np.int32)        # sorted candidate list
+    prev = np.sort(rng.choice(len(ii), int(frac * len(ii)), replace=False))
+    # previous file: per pair one copy-0 record followed by a copy-1 record (row, col >= n)
+    row = np.repeat(ii[prev], 2); col = np.repeat(jj[prev], 2)
+    row[1::2] += n; col[1::2] += n
+    prob = orc.text_roundtrip(rng.uniform(0, 1, len(row)))
+    f = str(tmp_path / "actdist.hdf5")
+    hdf5.write_h5(f, {"row": row.astype(np.int32), "col": col.astype(np.int32),
+                      "dist": np.zeros(len(row), np.float32), "prob": prob})
+    exp = np.zeros(len(ii))
+    exp[prev] = prob[0::2].astype(np.float64)
+    assert np.array_equal(S.lookup_plast(f, n, ii, jj), exp)
+    # an unsorted candidate list takes the general path
+    perm = rng.permutation(len(ii))
+    assert np.array_equal(S.lookup_plast(f, n, ii[perm], jj[perm]), exp[perm])
+
+
 def _cfg(tmp_path, hcs, hss, **hic):
     d = {"restraints": {"Hi-C": dict({"input_matrix": hcs, "intra_sigma_list": [0.2, 0.05],
                                       "inter_sigma_list": [0.2, 0.05], "contact_range": 2.0,
