@@ -91,6 +91,34 @@ def test_fullsize_sample_against_oracle(cfg2):
     assert np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))
 
 
+def _check_against_c_oracle(cfg, sel, it_corr, fast):
+    """GPU results of the pairs `sel` against the plain-C oracle (OpenMP, all host threads)."""
+    from oracle import c_oracle
+    ii, jj, pw, ci = cfg["ii"], cfg["jj"], cfg["pw"], cfg["ci"]
+    coords = cfg["coords"].cpu().numpy()
+    exp = c_oracle.run_pairs(ii[sel], jj[sel], pw[sel], np.zeros(len(sel)), coords, cfg["radii"],
+                             cfg["chrom_hap"], ci.ptr, ci.beads, it_corr, 2.0, 0)
+    got = fast[sel]
+    ok = exp["o"] >= 0
+    assert np.array_equal(got["contact_count"], exp["contact_count"])
+    assert np.array_equal(got["o"], exp["o"])
+    assert np.array_equal(got["nrec"], exp["nrec"])
+    assert np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))
+    assert np.array_equal(got["d2_sel_bits"][ok], exp["d2_sel_bits"][ok])
+    return int(ok.sum())
+
+
+def test_fullsize_every_13th_pair_against_c_oracle(cfg2):
+    """304 k pairs spread over the whole config-2 list, bit for bit against the C oracle."""
+    from oracle import c_oracle
+    if not c_oracle.available():
+        pytest.skip("oracle/_ref/libactdist_oracle.so not built")
+    eng, ii, jj, pw = cfg2["eng"], cfg2["ii"], cfg2["jj"], cfg2["pw"]
+    fast = eng.actdist(ii, jj, pw, None, 2.0, 0, "LB", 0)
+    sel = np.arange(5, len(ii), 13)
+    assert _check_against_c_oracle(cfg2, sel, 0, fast) == len(sel)
+
+
 # ---------------------------------------------------------------- config 5
 @pytest.fixture(scope="module")
 def cfg5():
@@ -133,6 +161,11 @@ def test_config5_stress(cfg5):
     simple = eng.actdist(ii[sub], jj[sub], pw[sub], None, 2.0, 0, "LB", 1)
     assert simple.tobytes() == fast[sub].tobytes()
 
+    from oracle import c_oracle
+    if c_oracle.available():                                    # 210 k pairs against the C oracle
+        big = np.arange(11, len(ii), 80)
+        assert _check_against_c_oracle(cfg5, big, 0, fast) == len(big)
+
     sel = np.sort(np.random.default_rng(5).choice(len(ii), 300, replace=False))
     hap = np.unique(np.concatenate([ii[sel], jj[sel]]))
     beads = np.unique(np.concatenate([ci[h] for h in hap]))
@@ -151,3 +184,38 @@ def test_config5_stress(cfg5):
     assert np.array_equal(got["contact_count"], exp["contact_count"])
     assert np.array_equal(got["o"], exp["o"])
     assert np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))
+
+
+# ---------------------------------------------------------------- config 3
+def test_config3_population_block_kernel_against_c_oracle():
+    """Config 3 of BASELINE.json: the 10 000-structure population at 200 kb (3.58 GB of
+    coordinates, CTA-per-pair kernel).  Every 20th pair of the sigma = 0.01 list (198 k pairs,
+    one GPU's share of a sharded run in miniature) runs on the GPU; 40 k of them are
+    compared bit for bit with the C oracle, and the iterative-correction variant on 8 k."""
+    import torch
+    from oracle import c_oracle
+    from igm_b200 import synthetic
+    from igm_b200.engine import ActdistEngine
+    from igm_b200.steps.ActivationDistanceStep import filter_candidates
+    if not c_oracle.available():
+        pytest.skip("oracle/_ref/libactdist_oracle.so not built")
+    dev = torch.device("cuda:0")
+    bins = synthetic.genome_bins(200_000)
+    chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins)
+    nbead = len(chrom_bead)
+    radius = float(synthetic.bead_radius(nbead))
+    coords = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, 10000, radius, 20261020, dev)
+    radii = np.full(nbead, radius, np.float32)
+    pm = synthetic.make_prob_matrix(chrom_hap, seed=20261018)
+    ii, jj, pw = filter_candidates(pm, 0.01, 0.01)
+    ii, jj, pw = ii[7::20], jj[7::20], pw[7::20]
+    with ActdistEngine(nbead=nbead, nstruct=10000, device=0) as eng:
+        eng.upload_coordinates(coords)
+        eng.set_index(ci.ptr, ci.beads, chrom_hap, radii)
+        fast = eng.actdist(ii, jj, pw, None, 2.0, 0, "LB", 0)
+        corr = eng.actdist(ii[:8000], jj[:8000], pw[:8000], None, 2.0, 1, "LB", 0)
+    assert int((fast["nrec"] > 0).sum()) == len(ii)
+    cfg = dict(ii=ii, jj=jj, pw=pw, ci=ci, coords=coords, radii=radii, chrom_hap=chrom_hap)
+    sel = np.arange(2, len(ii), 5)
+    assert _check_against_c_oracle(cfg, sel, 0, fast) == len(sel)
+    _check_against_c_oracle(cfg, np.arange(8000), 1, corr)
