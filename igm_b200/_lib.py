@@ -37,7 +37,7 @@ EXPORTS = (
     "igmk_contact_counts_device", "igmk_contact_counts_host",
     "igmk_contact_counts_haploid_device", "igmk_contact_counts_haploid_host",
     "igmk_set_bead_chrom", "igmk_restraint_words", "igmk_restraint_select_device",
-    "igmk_restraint_select_host", "igmk_sprite_rg2_host",
+    "igmk_restraint_select_host", "igmk_sprite_rg2_host", "igmk_sprite_cluster_rg2_host",
     "igmk_rank_match_device", "igmk_rank_match_host",
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms",
 )
@@ -86,6 +86,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.igmk_restraint_select_device.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int, vp, vp, vp]
     lib.igmk_restraint_select_host.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int, vp, vp]
     lib.igmk_sprite_rg2_host.argtypes = [vp, C.c_int, i32p, i32p, i32p, f32p, i32p, i32p]
+    lib.igmk_sprite_cluster_rg2_host.argtypes = [vp, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p, f32p]
     lib.igmk_rank_match_device.argtypes = [vp, C.c_int64, i32p, i32p, C.c_int, f32p, C.c_int64, vp, vp, vp, vp]
     lib.igmk_rank_match_host.argtypes = [vp, C.c_int64, i32p, i32p, C.c_int, f32p, C.c_int64, vp, vp, vp]
     lib.igmk_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_int64]

@@ -722,6 +722,70 @@ extern "C" int igmk_restraint_select_host(igmk_ctx* c, int64_t n_rec, const int3
 }
 
 // ------------------------------------------------------------- K4 (next row f3)
+extern "C" int igmk_sprite_cluster_rg2_host(igmk_ctx* c, int n_clusters, const int32_t* seg_ptr,
+                                            const int32_t* loc_ptr, const int32_t* beads,
+                                            const int32_t* seg_group, const int32_t* group_ptr,
+                                            const int32_t* sel, float* rg2s) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: NULL context");
+    if (!c->have_coords) return fail(IGMK_ESTATE, "igmk_sprite_cluster_rg2: upload coordinates first");
+    if (n_clusters < 0) return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: negative n_clusters");
+    if (n_clusters == 0) return IGMK_OK;
+    if (!seg_ptr || !loc_ptr || !beads || !seg_group || !group_ptr || !sel || !rg2s)
+        return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: NULL buffer");
+    if (seg_ptr[0] != 0 || loc_ptr[0] != 0 || group_ptr[0] != 0)
+        return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: CSR arrays must start at 0");
+    const int nseg_tot = seg_ptr[n_clusters], ngrp_tot = group_ptr[n_clusters];
+    const int nloc_tot = loc_ptr[nseg_tot];
+    for (int k = 0; k < n_clusters; ++k) {
+        const int ng = group_ptr[k + 1] - group_ptr[k];
+        if (seg_ptr[k + 1] <= seg_ptr[k] || ng <= 0)
+            return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: cluster %d is empty", k);
+        for (int i = seg_ptr[k]; i < seg_ptr[k + 1]; ++i) {
+            if (loc_ptr[i + 1] <= loc_ptr[i]) return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: segment %d has no location", i);
+            if (seg_group[i] < 0 || seg_group[i] >= ng) return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: segment %d: selection column out of range", i);
+        }
+    }
+    for (int b = 0; b < nloc_tot; ++b)
+        if (beads[b] < 0 || beads[b] >= c->nbead) return fail(IGMK_EINVAL, "igmk_sprite_cluster_rg2: bead id out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t N = (size_t)c->nstruct;
+    const size_t o_lp = up((size_t)(n_clusters + 1) * 4), o_b = o_lp + up((size_t)(nseg_tot + 1) * 4);
+    const size_t o_sg = o_b + up((size_t)nloc_tot * 4), o_gp = o_sg + up((size_t)nseg_tot * 4);
+    const size_t o_sel = o_gp + up((size_t)(n_clusters + 1) * 4), o_rg = o_sel + up((size_t)ngrp_tot * N * 4);
+    const size_t total = o_rg + up((size_t)n_clusters * N * 4);
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, seg_ptr, (size_t)(n_clusters + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_lp, loc_ptr, (size_t)(nseg_tot + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_b, beads, (size_t)nloc_tot * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_sg, seg_group, (size_t)nseg_tot * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_gp, group_ptr, (size_t)(n_clusters + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + o_sel, sel, (size_t)ngrp_tot * N * 4, cudaMemcpyHostToDevice, c->stream));
+    SpriteClusterParams P;
+    P.coords = c->d_coords; P.seg_ptr = (const int32_t*)base; P.loc_ptr = (const int32_t*)(base + o_lp);
+    P.beads = (const int32_t*)(base + o_b); P.seg_group = (const int32_t*)(base + o_sg);
+    P.group_ptr = (const int32_t*)(base + o_gp); P.sel = (const int32_t*)(base + o_sel);
+    P.rg2s = (float*)(base + o_rg);
+    P.n_clusters = n_clusters; P.nstruct = c->nstruct; P.npad = c->npad;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    for (int k0 = 0; k0 < n_clusters; k0 += 65535) {        // gridDim.y limit
+        SpriteClusterParams Q = P;
+        const int nk = (n_clusters - k0 < 65535) ? n_clusters - k0 : 65535;
+        Q.seg_ptr = P.seg_ptr + k0; Q.group_ptr = P.group_ptr + k0; Q.rg2s = P.rg2s + (size_t)k0 * N; Q.n_clusters = nk;
+        dim3 grid((c->nstruct + 127) / 128, nk);
+        sprite_cluster_rg2_kernel<<<grid, 128, 0, c->stream>>>(Q);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(rg2s, base + o_rg, (size_t)n_clusters * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
+    return IGMK_OK;
+}
+
 extern "C" int igmk_sprite_rg2_host(igmk_ctx* c, int n_clusters, const int32_t* region_ptr,
                                     const int32_t* copy_ptr, const int32_t* beads,
                                     float* rg2s, int32_t* copy_idx, int32_t* min_struct) {

@@ -96,6 +96,66 @@ sprite_rg2_kernel(const SpriteParams P) {
     }
 }
 
+// K4b: Rg^2 of a WHOLE cluster under a per-structure choice of chromosome copies - the
+// second half of compute_gyration_radius (igm/cython_compiled/sprite.pyx:238-283): every
+// segment of the cluster follows the copy that stage one (K4 on one representative segment
+// per chromosome) selected for its chromosome in that structure, and get_rgs2 is evaluated
+// on the selected beads with one location per segment (:279-282).  Also serves the
+// single-chromosome branch (:200-215) with a constant selection per copy.
+//
+// Same float32 arithmetic as above (gyration_radius_sq, cpp:49-61), segments in the order
+// given (all_segments of :243); with one combination the reference reports
+// min(Rg^2, INF) (cpp:104-131: `if (rg2 < best)` from best = INF).  A negative selection
+// (stage one found nothing below INF) indexes from the end, as NumPy does at :270-271.
+//
+// One thread per (cluster, structure), two passes over the segments; the coordinate reads
+// are coalesced over structures (both passes hit the same rows, the second from L1 / L2).
+struct SpriteClusterParams {
+    const float*   coords;
+    const int32_t* seg_ptr;      // [n_clusters + 1] -> segments
+    const int32_t* loc_ptr;      // [n_segments_total + 1] -> beads (the copies of each segment)
+    const int32_t* beads;
+    const int32_t* seg_group;    // [n_segments_total] selection column of the segment within its cluster
+    const int32_t* group_ptr;    // [n_clusters + 1] -> selection columns
+    const int32_t* sel;          // [group_ptr[c] * nstruct + s * ngroups(c) + g]  (K4's copy_idx layout)
+    float* rg2s;                 // [n_clusters][nstruct]
+    int n_clusters, nstruct, npad;
+};
+
+__global__ void __launch_bounds__(128)
+sprite_cluster_rg2_kernel(const SpriteClusterParams P) {
+    const int c = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.nstruct) return;
+    const int s0 = __ldg(P.seg_ptr + c), nseg = __ldg(P.seg_ptr + c + 1) - s0;
+    const int g0 = __ldg(P.group_ptr + c), ngrp = __ldg(P.group_ptr + c + 1) - g0;
+    const int32_t* sel = P.sel + (size_t)g0 * P.nstruct + (size_t)s * ngrp;
+    const size_t rowf = (size_t)3 * P.npad;
+    const size_t so = coord_off(s);
+    auto point = [&](int i) -> const float* {
+        const int l0 = __ldg(P.loc_ptr + s0 + i), nl = __ldg(P.loc_ptr + s0 + i + 1) - l0;
+        int k = __ldg(sel + __ldg(P.seg_group + s0 + i));
+        if (k < 0) k += nl;
+        k = (k < 0) ? 0 : (k >= nl ? nl - 1 : k);           // (never out of range for valid input)
+        return P.coords + (size_t)__ldg(P.beads + l0 + k) * rowf + so;
+    };
+    const float fn = (float)nseg;
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    for (int i = 0; i < nseg; ++i) {
+        const float* p = point(i);
+        mx = __fadd_rn(mx, __ldg(p)); my = __fadd_rn(my, __ldg(p + kSeg)); mz = __fadd_rn(mz, __ldg(p + 2 * kSeg));
+    }
+    mx = __fdiv_rn(mx, fn); my = __fdiv_rn(my, fn); mz = __fdiv_rn(mz, fn);
+    float rg = 0.f;
+    for (int i = 0; i < nseg; ++i) {
+        const float* p = point(i);
+        const float dx = __fsub_rn(__ldg(p), mx), dy = __fsub_rn(__ldg(p + kSeg), my), dz = __fsub_rn(__ldg(p + 2 * kSeg), mz);
+        rg = __fadd_rn(rg, __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    }
+    const float rg2 = __fdiv_rn(rg, fn);
+    P.rg2s[(size_t)c * P.nstruct + s] = (rg2 < kSpInf) ? rg2 : kSpInf;
+}
+
 // first structure with the strictly smallest Rg^2 below INF (one CTA per cluster)
 __global__ void __launch_bounds__(256)
 sprite_argmin_kernel(const float* __restrict__ rg2s, int nstruct, int32_t* __restrict__ min_struct) {

@@ -295,6 +295,39 @@ class ActdistEngine:
             out.append((rg2s[k], int(ms[k]), cidx[lo:lo + m * self.nstruct].reshape(self.nstruct, m)))
         return out
 
+    def sprite_cluster_rg2(self, clusters):
+        """Rg^2 of whole clusters under a per-structure choice of copies (K4b) - the second
+        half of compute_gyration_radius (igm/cython_compiled/sprite.pyx:238-283).
+
+        clusters: list of ``(segments, groups, sel)``: ``segments`` a list of bead-id lists
+        (the copies of each segment, in the reference's concatenation order), ``groups`` the
+        selection column each segment follows, ``sel`` an int array (nstruct, n_columns) of
+        chosen copies (get_rgs2's copy_idxs; negative = from the end).  Returns a float32
+        array (n_clusters, nstruct)."""
+        seg_ptr, loc_ptr, beads, seg_group, group_ptr, sels = [0], [0], [], [], [0], []
+        for segments, groups, sel in clusters:
+            sel = np.ascontiguousarray(sel, dtype=np.int32)
+            if sel.ndim != 2 or sel.shape[0] != self.nstruct:
+                raise ValueError("sel must have shape (nstruct, n_columns)")
+            if len(groups) != len(segments):
+                raise ValueError("one selection column per segment is required")
+            for reg in segments:
+                beads.extend(int(b) for b in reg)
+                loc_ptr.append(len(beads))
+            seg_group.extend(int(g) for g in groups)
+            seg_ptr.append(len(loc_ptr) - 1)
+            group_ptr.append(group_ptr[-1] + sel.shape[1])
+            sels.append(sel.reshape(-1))
+        n = len(clusters)
+        rg2s = np.zeros((n, self.nstruct), np.float32)
+        if n == 0:
+            return rg2s
+        a = [np.asarray(x, np.int32) for x in (seg_ptr, loc_ptr, beads, seg_group, group_ptr)]
+        sel_all = np.ascontiguousarray(np.concatenate(sels), dtype=np.int32)
+        check(self._lib.igmk_sprite_cluster_rg2_host(self._ctx, n, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]),
+                                                     ptr(a[4]), ptr(sel_all), ptr(rg2s)))
+        return rg2s
+
     # -- DamID ----------------------------------------------------------
     def damid_actdist(self, loci, p_exp, plast=None, nucleus_radius: float = 5000.0,
                       contact_range: float = 0.05, it_corr: int = 0) -> np.ndarray:

@@ -4,6 +4,7 @@ from .HicEvaluationStep import HicEvaluationStep
 from .DamidActivationDistanceStep import DamidActivationDistanceStep, NuclDamidActivationDistanceStep
 from .FishAssignmentStep import FishAssignmentStep
 from .PolymerAssignmentStep import PolymerAssignmentStep
+from .SpriteAssignmentStep import SpriteAssignmentStep
 
 __all__ = ["ActivationDistanceStep", "HicEvaluationStep", "DamidActivationDistanceStep",
-           "NuclDamidActivationDistanceStep", "FishAssignmentStep", "PolymerAssignmentStep"]
+           "NuclDamidActivationDistanceStep", "FishAssignmentStep", "PolymerAssignmentStep", "SpriteAssignmentStep"]

@@ -210,6 +210,23 @@ int igmk_sprite_rg2_host(igmk_ctx* ctx, int n_clusters, const int32_t* region_pt
                          const int32_t* copy_ptr, const int32_t* beads,
                          float* rg2s, int32_t* copy_idx, int32_t* min_struct);
 
+/* Rg^2 of whole SPRITE clusters under a per-structure choice of chromosome copies - the
+ * second half of compute_gyration_radius (igm/cython_compiled/sprite.pyx:238-283: the copies
+ * selected on one representative segment per chromosome are applied to every segment of the
+ * cluster and get_rgs2 is evaluated on the selected beads) and its single-chromosome branch
+ * (:200-215, one constant selection per copy).  Cluster k has the segments
+ * seg_ptr[k] .. seg_ptr[k+1]-1 in the order the reference concatenates them (:243); segment
+ * i has the copies beads[loc_ptr[i] .. loc_ptr[i+1]-1] and follows selection column
+ * seg_group[i] (0 .. G_k-1, G_k = group_ptr[k+1] - group_ptr[k]);
+ * sel[group_ptr[k] * nstruct + s * G_k + g] is the copy chosen in structure s (the layout of
+ * igmk_sprite_rg2_host's copy_idx; negative values index from the end as NumPy does).
+ * Out: rg2s[k * nstruct + s] = min(Rg^2, 1e8).  No limit on the segments per cluster.
+ * Host pointers. */
+int igmk_sprite_cluster_rg2_host(igmk_ctx* ctx, int n_clusters, const int32_t* seg_ptr,
+                                 const int32_t* loc_ptr, const int32_t* beads,
+                                 const int32_t* seg_group, const int32_t* group_ptr,
+                                 const int32_t* sel, float* rg2s);
+
 /* Population rank matching - the arithmetic of the FISH and polymer assignment steps
  * (igm/steps/FishAssignmentStep.py:23-79 get_pair_dists / get_rad_dists /
  * get_min_max_and_idx and task :189-193, :214-219; igm/steps/PolymerAssignmentStep.py:24-33

@@ -37,3 +37,22 @@ def test_port_equals_compiled_reference():
         r2, b2, c2 = so.get_rgs2_port(crd, copies)
         assert np.array_equal(r1.view(np.uint32), r2.view(np.uint32))
         assert b1 == b2 and np.array_equal(c1, c2)
+
+
+def test_compute_gyration_radius_port_equals_reference_golden():
+    """The cluster-level driver against what the reference's own compiled
+    compute_gyration_radius returned (tests/golden/make_golden_sprite.py), with the global
+    NumPy random stream seeded as it was there; both get_rgs2 oracles."""
+    from tests import helpers as H
+    fns = [so.get_rgs2_port] + ([so.ref_get_rgs2] if so.ref_available() else [])
+    n = 0
+    for name, crd, chrom, ci, clusters, rg2s, best, sel, seed0, _ in H.sprite_golden_cases():
+        for k, cl in enumerate(clusters):
+            for fn in fns:
+                np.random.seed(seed0 + k)
+                r, b, s = so.compute_gyration_radius_port(crd, cl, chrom, ci, get_rgs2=fn)
+                assert np.array_equal(np.asarray(r, np.float32).view(np.uint32), rg2s[k].view(np.uint32)), (name, k)
+                assert int(b) == int(best[k])
+                assert np.array_equal(np.asarray(s), sel[k])
+            n += 1
+    assert n == 54

@@ -176,3 +176,51 @@ def test_hdf5_writer_roundtrip_and_layout(tmp_path):
         assert h.attrs["nbead"] == 3
     raw = open(f, "rb").read()
     assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0     # classic superblock v0
+
+
+def test_sprite_step_setup_and_reduce_host_logic(tmp_path):
+    """SpriteAssignmentStep without a GPU: batch layout of setup, and reduce (Gibbs draw with
+    occupancy penalty, igm/steps/SpriteAssignmentStep.py:166-259) on task files produced by
+    the oracle-driven restatement - same seed, same assignment."""
+    from igm_b200 import synthetic
+    from igm_b200.steps import SpriteAssignmentStep
+    pop = synthetic.make_population(2_000_000, 60, seed=5, genome_scale=0.02)
+    hss = str(tmp_path / "p.hss")
+    pop.save_hss(hss)
+    rng = np.random.default_rng(9)
+    chrom_hap, n_hap = pop.chrom_hap(), pop.n_hap
+    clusters = []
+    for k in range(11):
+        cs = rng.choice(np.unique(chrom_hap), size=int(rng.integers(1, 6)), replace=False)
+        pool = np.nonzero(np.isin(chrom_hap, cs))[0]
+        clusters.append(np.sort(rng.choice(pool, size=int(min(len(pool), rng.integers(2, 9))), replace=False)).astype(np.int32))
+    indptr = np.concatenate([[0], np.cumsum([len(c) for c in clusters])]).astype(np.int32)
+    clf = str(tmp_path / "clusters.h5")
+    hdf5.write_h5(clf, {"indptr": indptr, "data": np.concatenate(clusters).astype(np.int32)})
+    cfg = Config({"parameters": {"workdir": str(tmp_path), "tmp_dir": str(tmp_path / "tmp")},
+                           "optimization": {"structure_output": hss},
+                           "restraints": {"sprite": {"clusters": clf, "volume_fraction_list": [0.5, 0.2],
+                                                     "batch_size": 4, "keep_best": 10, "max_chrom_in_cluster": 3}},
+                           "runtime": {"sprite": {}}})
+    step = SpriteAssignmentStep(cfg)
+    assert cfg.get("runtime/sprite/volume_fraction") == 0.5 and cfg.get("runtime/sprite/volume_fraction_list") == [0.2]
+    assert step.name() == "SpriteAssignmentStep (volume_fraction=0.5%, iter=N/A)"
+    step.setup()
+    assert list(step.argument_list) == [0, 1, 2] and step.n_clusters == 11 and step.n_struct == 60
+    assert step.tmp_extensions == [".npy", ".npz"]
+    cidict = {i: pop.copy_index[i] for i in range(n_hap)}
+    np.random.seed(31)
+    batches = [H.sprite_reference_task(pop.coordinates, pop.chrom, cidict, clusters[b * 4:(b + 1) * 4], 10, 3)
+               for b in range(3)]
+    for b, (sel, idx, val) in enumerate(batches):          # the files task() writes (:155-161)
+        np.savez(os.path.join(step.tmp_dir, 'tmp.%d.selected.npz' % b), *sel)
+        np.save(os.path.join(step.tmp_dir, 'tmp.%d.idx.npy' % b), idx)
+        np.save(os.path.join(step.tmp_dir, 'tmp.%d.values.npy' % b), val)
+    np.random.seed(77)
+    step.reduce()
+    np.random.seed(77)
+    exp_assign, exp_sel = H.sprite_reference_reduce(batches, indptr, 60, 4, 100.0)
+    with hdf5.open_h5(os.path.join(step.tmp_dir, "assignment.h5")) as f:
+        assert np.array_equal(np.asarray(f["assignment"][()]), exp_assign)
+        assert np.array_equal(np.asarray(f["selected"][()]), exp_sel)
+    assert (exp_assign >= 0).any()
