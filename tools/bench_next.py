@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput of the "next" kernels on the config-2 population (synthetic, 1000
 structures x 29 838 beads): K3 restraint selection over the records of an A-step,
-K4 SPRITE Rg^2 over random clusters, K5 rank matching of every polymer bond, DamID activation distances of every locus,
+K4 / K4b SPRITE Rg^2 over random clusters, K5 rank matching of every polymer bond, DamID activation distances of every locus,
 haploid contact map.  Kernel-only times (CUDA events inside the library)."""
 import argparse
 import json
@@ -55,6 +55,21 @@ def main():
     eng.sprite_rg2(clusters)
     ms = eng.last_kernel_ms()
     out["K4"] = {"clusters": len(clusters), "ms": ms, "cluster_structs_per_s": len(clusters) * args.nstruct / (ms * 1e-3)}
+    # K4b: whole-cluster Rg^2 under a per-structure copy choice: 2 000 clusters of 20..200 segments
+    full, nseg_tot = [], 0
+    for _ in range(2000):
+        loci = rng.choice(len(chrom_hap), size=int(rng.integers(20, 201)), replace=False)
+        groups = (np.arange(len(loci)) % 4).tolist()
+        sel = rng.integers(0, 2, (args.nstruct, 4)).astype(np.int32)
+        # haploid loci have one copy: selection 1 would be out of range -> use the last copy (-1)
+        sel[sel == 1] = -1
+        full.append(([ci[int(l)] for l in loci], groups, sel))
+        nseg_tot += len(loci)
+    eng.sprite_cluster_rg2(full)
+    ms = eng.last_kernel_ms()
+    out["K4b"] = {"clusters": len(full), "segments": nseg_tot, "ms": ms,
+                  "segment_structs_per_s": nseg_tot * args.nstruct / (ms * 1e-3),
+                  "GBps_algorithmic": nseg_tot * 12.0 * args.nstruct / (ms * 1e-3) / 1e9}
     # DamID: every locus
     nh = len(chrom_hap)
     pe = rng.uniform(0.05, 1, nh).astype(np.float32)
