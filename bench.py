@@ -151,15 +151,16 @@ class ClockSampler(threading.Thread):
                 "power_w_max": max(pw) if pw else None}
 
 
-def measured_traffic(nstruct, n_pairs, mode):
+def measured_traffic(nstruct, n_pairs, mode, key="dram_bytes_per_launch"):
     """DRAM bytes (read + write) of ONE launch of the dominant kernel on this
     workload, from the committed `ncu --set full` capture (profiles/traffic.json,
-    written by profiles/summarize.py --traffic); None when no capture matches."""
+    written by profiles/update_traffic.py); None when no capture matches.  ``key`` selects
+    another per-launch counter of the same capture (warp instructions)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         for e in json.load(open(p))["captures"]:
             if e["nstruct"] == nstruct and e["n_pairs"] == n_pairs and e["mode"] == mode:
-                return float(e["dram_bytes_per_launch"])
+                return float(e[key])
     except Exception:
         pass
     return None
@@ -428,6 +429,18 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
+        # what actually limits the kernel: the issue slots it uses,
+        # from the warp-instruction count of the committed ncu capture and the live kernel time
+        winst = measured_traffic(args.nstruct, n_pairs, args.mode, "warp_instructions_per_launch")
+        sm_mhz = line["clocks"].get("sm_mhz") or 1965.0
+        if winst:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            line["roofline"]["issue"] = {
+                "warp_instructions_per_launch": winst,
+                "achieved_winst_per_s": winst / (k_ms * 1e-3),
+                "peak_winst_per_s": sms * 4 * sm_mhz * 1e6,
+                "frac": winst / (k_ms * 1e-3) / (sms * 4 * sm_mhz * 1e6),
+                "note": "issue slots used (4 schedulers per SM at the sampled SM clock); the kernel is latency-bound"}
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline:

@@ -34,6 +34,8 @@ def main():
                  "dram_bytes_per_launch": tot, "kernel_ms_under_ncu": float(row[ix["gpu__time_duration.sum"]]) *
                  {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[units[ix["gpu__time_duration.sum"]]],
                  "report": os.path.basename(rep)}
+        if "smsp__inst_executed.sum" in ix:
+            entry["warp_instructions_per_launch"] = float(row[ix["smsp__inst_executed.sum"]])
         path = os.path.join(HERE, "traffic.json")
         data = json.load(open(path)) if os.path.exists(path) else {"captures": []}
         data["captures"] = [e for e in data["captures"]
