@@ -74,6 +74,7 @@ struct igmk_ctx {
     void* d_order = nullptr; size_t order_bytes = 0;    // keys / values / cub temp of order_pairs()
     int tile_block = 512;        // IGMK_TILE_BLOCK (0: no shared-memory locus-i tile)
     int tile_slots = 1;          // IGMK_TILE_SLOTS (2 slots shrink L1 to 15 KB at N = 1000: slower)
+    int warp_specialised = 0;    // IGMK_WS: experimental warp-specialised K1 (fill / select warps, setmaxnreg)
     int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
 };
 
@@ -135,6 +136,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov && atoll(ov) > 0) c->host_slice_pairs = atoll(ov);
     ov = getenv("IGMK_WARPS_PER_CTA");
     if (ov) c->warps_per_cta = atoi(ov);
+    ov = getenv("IGMK_WS");
+    if (ov) c->warp_specialised = atoi(ov);
     ov = getenv("IGMK_BLOCK_STOP");
     if (ov) c->block_stop = atoi(ov);
     if (c->block_stop < kRankCap) c->block_stop = kRankCap;
@@ -261,6 +264,22 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     if (warps < 1) return fail(IGMK_ELIMIT, "actdist_warp_kernel: nstruct = %d is too large for one warp per pair", c->nstruct);
     P.tile_block = tile_bytes ? c->tile_block : 0;
     P.tile_slots = slots;
+    if (c->warp_specialised && !DAMID && tile_bytes && slots == 1) {
+        // experimental: fill and select halves on different warps (IGMK_WS=1)
+        const size_t buf_bytes = (size_t)2 * V * 32 * 16;
+        int nbuf = (int)((budget - tile_bytes) / buf_bytes);
+        if (nbuf > 32) nbuf = 32;
+        if (nbuf >= kWsFill + 4) {
+            const size_t smem_ws = (size_t)nbuf * buf_bytes + tile_bytes;
+            CUDA_TRY(cudaFuncSetAttribute(actdist_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+            long long want_ws = (P.n_pairs + P.tile_block - 1) / P.tile_block;
+            const int grid_ws = (int)((want_ws < c->sm_count) ? want_ws : c->sm_count);
+            actdist_ws_kernel<<<grid_ws, 32 * (kWsFill + kWsSel), smem_ws, st>>>(P, V, nbuf);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            return launch_finish(P, st);
+        }
+    }
     int per_sm = 0;
     const size_t smem = (size_t)warps * 2 * V * 32 * 16 + tile_bytes;
     CUDA_TRY(cudaFuncSetAttribute(actdist_warp_kernel<DAMID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -155,7 +155,7 @@ __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const Pair
 // 16-byte slots of this thread, 512 bytes apart: b0 x / y / z, b1 x / y / z) with
 // asynchronous copies, so their L2 latency overlaps the arithmetic of the previous chunk
 // without costing registers.  Warp groups only (slot stride 512 bytes = 32 lanes).
-template <int SH, bool AS, bool BS>
+template <int SH, bool AS, bool BS, bool PIPE_REQ = false>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
                                           const PairPtrs& pp, int tid, int nthr, int V,
                                           uint32_t kscr, uint32_t kstride, uint32_t as0, uint32_t as1,
@@ -197,11 +197,22 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
     // (Software-pipelining the locus-j loads of chunk v + 1 over the arithmetic of
     // chunk v was tried for the shared-tile path: at 96 registers it spills and
     // loses 12 %, at 118 registers / 16 warps it only reaches parity.)
+    // PIPE (fill warps of the warp-specialised kernel, shared-tile path, the two
+    // straight-line shapes): the rows of locus j are loop-carried - the b0 row of chunk
+    // v + 1 is requested right after the last use of b0 in chunk v (half a chunk of
+    // arithmetic before the loop comes round), b1 likewise, and every distance is counted
+    // and packed as soon as it exists.  Needs the larger register budget of those warps.
+    constexpr bool PIPE = PIPE_REQ && AS && !BS && (SH == SH_FULL4 || SH == SH_INTRA2);
+    Row6 b0, b1;
+    if (PIPE && tid < P.nchunks) {
+        b0 = load_row6_stream_pinned(pb0);
+        b1 = load_row6_stream_pinned(pb1);
+    }
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
         const int c = tid + v * nthr;
         uint32_t nk[NS][2];
-        Row6 a0, a1, b0, b1;
+        Row6 a0, a1;
         if (c >= P.nchunks) {              // padding chunk: NaN keys, nothing to load
             sts128(dst, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
             if (NS == 4) {
@@ -210,7 +221,43 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
             dst += (uint32_t)nh * kstride;
             continue;                      // (pointers are not used again: c only grows)
         }
-        {
+        if (PIPE) {
+            const bool tail = 4 * c + 4 > P.nstruct;
+            // slot k of structures 4c .. 4c+3: count, keep the high halves, track min / max
+            auto consume = [&](int k, u64 d01, u64 d23) {
+                float v0, v1, v2, v3;
+                f2split(d01, v0, v1);
+                f2split(d23, v2, v3);
+                if (tail) {                      // tail chunk of the population (one thread)
+                    if (4 * c + 1 >= P.nstruct) v1 = qnan;
+                    if (4 * c + 2 >= P.nstruct) v2 = qnan;
+                    if (4 * c + 3 >= P.nstruct) v3 = qnan;
+                }
+                c_local = f2add(c_local, f2pack(f_le_one(v0, rc), f_le_one(v1, rc)));
+                c_local = f2add(c_local, f2pack(f_le_one(v2, rc), f_le_one(v3, rc)));
+                nk[k][0] = __byte_perm(__float_as_uint(v0), __float_as_uint(v1), 0x7632);
+                nk[k][1] = __byte_perm(__float_as_uint(v2), __float_as_uint(v3), 0x7632);
+                lmn = bf2_min(lmn, bf2_min(nk[k][0], nk[k][1]));
+                lmx = bf2_max(lmx, bf2_max(nk[k][0], nk[k][1]));
+            };
+            // a lane without a next chunk re-reads its own rows (no branch around the loads)
+            const size_t nxt = (c + nthr < P.nchunks) ? vstride : (size_t)0;
+            a0 = load_row6_shared(sa0);
+            a1 = load_row6_shared(sa1);
+            if (SH == SH_INTRA2) {
+                consume(0, d2pair<0>(a0, b0, nz), d2pair<1>(a0, b0, nz));
+                b0 = load_row6_stream_pinned(pb0 + nxt);
+                consume(1, d2pair<0>(a1, b1, nz), d2pair<1>(a1, b1, nz));
+                b1 = load_row6_stream_pinned(pb1 + nxt);
+            } else {
+                consume(0, d2pair<0>(a0, b0, nz), d2pair<1>(a0, b0, nz));
+                consume(NS == 4 ? 2 : 0, d2pair<0>(a1, b0, nz), d2pair<1>(a1, b0, nz));
+                b0 = load_row6_stream_pinned(pb0 + nxt);
+                consume(1, d2pair<0>(a0, b1, nz), d2pair<1>(a0, b1, nz));
+                consume(NS == 4 ? 3 : 1, d2pair<0>(a1, b1, nz), d2pair<1>(a1, b1, nz));
+                b1 = load_row6_stream_pinned(pb1 + nxt);
+            }
+        } else {
             float s[4][NS];   // [q][slot]
             if (BS && v <= vlast) {            // uniform
                 cp_async_wait_all();           // this thread's own copies of chunk v have landed
@@ -548,59 +595,15 @@ __device__ __forceinline__ void tile_release(const TileCtl& tile, int slot, int 
         asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(tile.words + 4u * slot), "r"(0xffffffffu) : "memory");
 }
 
-// DAMID: the same machinery computes the lamina-DamID activation distance of one
-// locus (igm/steps/DamidActivationDistanceStep.py:375-470, spherical envelope): the
-// "pair" is (locus, origin) - the partner row is the all-zero bead kept behind the
-// population, so d2 is the float32 sum of squares of the coordinates, exactly
-// np.sum(np.square(x), axis=1) - the order statistic is taken in descending order and
-// the probability arithmetic is float32 (see compute_p_o_damid).
+// Second half of a pair: p and o, bisection on the parked keys, candidate list, exact
+// rank, result.  `cnt`, `kmin`, `kmax` are the group-wide values of the fill; the group's
+// candidate counter (g.ctl) must be zero.
 template <bool BLOCK, bool DAMID>
-__device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK>& g, int V,
-                                             long long slot, const TileCtl& tile) {
-    // slot = position in processing order; perm maps it to the pair's index in the
-    // caller's list (results stay in input order)
-    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-    const int i = __ldg(P.pi + pair);
-    double extra = 0.0;                    // DAMID: (R - r)^2, handed to the finish pass
-    const PairDesc d = DAMID ? make_damid_desc(P, i, extra) : make_pair_desc(P, i, __ldg(P.pj + pair));
-    if (!d.valid) {                        // uniform over the group
-        emit_empty(P, g.tid, pair);
-        return;
-    }
-    const PairPtrs pp = pair_ptrs(P, d);
-
-    int cnt;
-    uint32_t mn2, mx2;
-    const int tslot = (!BLOCK && !DAMID && tile.base) ? tile_acquire(P, tile, i, d, pp, g.tid) : -1;
-    if (tslot >= 0) {
-        const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
-        const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
-        switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  fill_keys<SH_FULL4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-            case SH_INTRA2: fill_keys<SH_INTRA2, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-            case SH_GP4:    fill_keys<SH_GP4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-            default:        fill_keys<SH_GENERIC, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-        }
-        tile_release(tile, tslot, g.tid);
-    } else {
-        switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  fill_keys<SH_FULL4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-            case SH_INTRA2: fill_keys<SH_INTRA2, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-            case SH_GP4:    fill_keys<SH_GP4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-            default:        fill_keys<SH_GENERIC, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-        }
-    }
+__device__ __forceinline__ void select_part(const ActdistParams& P, Group<BLOCK>& g, int V,
+                                            long long pair, const PairDesc& d, const PairPtrs& pp,
+                                            double extra, int cnt, uint32_t kmin, uint32_t kmax) {
     const int nh = (d.keep > 2) ? 2 : 1;
     const int nq = V * nh;
-
-    uint32_t kmin = min(mn2 & 0xffffu, mn2 >> 16);
-    uint32_t mxl = mx2 & 0xffffu, mxh = mx2 >> 16;
-    mxl = (mxl > 0x7f80u) ? 0u : mxl;
-    mxh = (mxh > 0x7f80u) ? 0u : mxh;
-    uint32_t kmax = max(mxl, mxh);
-    if (g.tid == 0) sts32(g.ctl, 0u);
-    g.sum_min_max(cnt, kmin, kmax);
-
     double p;
     int o;                                 // ascending index of the element to select
     int o_rep;                             // index reported to the caller
@@ -743,6 +746,58 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
     }
 }
 
+// DAMID: the same machinery computes the lamina-DamID activation distance of one
+// locus (igm/steps/DamidActivationDistanceStep.py:375-470, spherical envelope): the
+// "pair" is (locus, origin) - the partner row is the all-zero bead kept behind the
+// population, so d2 is the float32 sum of squares of the coordinates, exactly
+// np.sum(np.square(x), axis=1) - the order statistic is taken in descending order and
+// the probability arithmetic is float32 (see compute_p_o_damid).
+template <bool BLOCK, bool DAMID>
+__device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK>& g, int V,
+                                             long long slot, const TileCtl& tile) {
+    // slot = position in processing order; perm maps it to the pair's index in the
+    // caller's list (results stay in input order)
+    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
+    const int i = __ldg(P.pi + pair);
+    double extra = 0.0;                    // DAMID: (R - r)^2, handed to the finish pass
+    const PairDesc d = DAMID ? make_damid_desc(P, i, extra) : make_pair_desc(P, i, __ldg(P.pj + pair));
+    if (!d.valid) {                        // uniform over the group
+        emit_empty(P, g.tid, pair);
+        return;
+    }
+    const PairPtrs pp = pair_ptrs(P, d);
+
+    int cnt;
+    uint32_t mn2, mx2;
+    const int tslot = (!BLOCK && !DAMID && tile.base) ? tile_acquire(P, tile, i, d, pp, g.tid) : -1;
+    if (tslot >= 0) {
+        const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
+        const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
+        switch (pair_shape(d, P.mode)) {       // uniform over the group
+            case SH_FULL4:  fill_keys<SH_FULL4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+        }
+        tile_release(tile, tslot, g.tid);
+    } else {
+        switch (pair_shape(d, P.mode)) {       // uniform over the group
+            case SH_FULL4:  fill_keys<SH_FULL4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+        }
+    }
+    uint32_t kmin = min(mn2 & 0xffffu, mn2 >> 16);
+    uint32_t mxl = mx2 & 0xffffu, mxh = mx2 >> 16;
+    mxl = (mxl > 0x7f80u) ? 0u : mxl;
+    mxh = (mxh > 0x7f80u) ? 0u : mxh;
+    uint32_t kmax = max(mxl, mxh);
+    if (g.tid == 0) sts32(g.ctl, 0u);
+    g.sum_min_max(cnt, kmin, kmax);
+    select_part<BLOCK, DAMID>(P, g, V, pair, d, pp, extra, cnt, kmin, kmax);
+}
+
 // ---------------------------------------------------------------- kernels
 // G = 32: one pair per warp, kWarpsPerBlock independent warps per CTA, no CTA
 // barrier anywhere.  Consecutive pairs (CSR order: same locus i) go to the warps
@@ -813,6 +868,172 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
          pair += stride) {
         process_pair<false, DAMID>(P, g, V, pair, tile);
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------- warp-specialised variant (experimental)
+// Same per-pair algorithm, but the two halves of a pair run on different warps: kWsFill
+// "fill" warps (register budget raised with setmaxnreg) stream coordinates and park keys
+// in a ring of shared-memory key arrays; kWsSel "select" warps (budget lowered) take the
+// arrays in the same order, bisect, rank and emit.  Hand-over: one state word per array,
+// 2 g = free for generation g, 2 g + 1 = filled; tickets from two shared counters keep both
+// sides in list order, so the ring can never dead-lock; every wait is bounded and traps.
+#ifndef IGMK_WS_FILL
+#define IGMK_WS_FILL 8
+#endif
+#ifndef IGMK_WS_SEL
+#define IGMK_WS_SEL 12
+#endif
+#ifndef IGMK_WS_FILL_REGS
+#define IGMK_WS_FILL_REGS 144
+#endif
+#ifndef IGMK_WS_SEL_REGS
+#define IGMK_WS_SEL_REGS 64
+#endif
+#ifndef IGMK_WS_PIPE
+#define IGMK_WS_PIPE 0
+#endif
+#ifndef IGMK_WS_SLEEP
+#define IGMK_WS_SLEEP 200
+#endif
+constexpr int kWsFill = IGMK_WS_FILL;          // multiples of 4 (setmaxnreg is warpgroup-wide)
+constexpr int kWsSel = IGMK_WS_SEL;
+constexpr int kWsFillRegs = IGMK_WS_FILL_REGS; // 32 (kWsFill Rf + kWsSel Rs) <= threads x launch registers
+constexpr int kWsSelRegs = IGMK_WS_SEL_REGS;
+constexpr bool kWsPipe = IGMK_WS_PIPE != 0;
+struct WsMeta { long long pair; int cnt; uint32_t kmin, kmax; int pad; };
+
+__device__ __forceinline__ void ws_wait(uint32_t addr, uint32_t want, int lane) {
+    if (lane == 0) {
+        int spins = 0;
+        while (lds32_volatile(addr) != want) {
+            __nanosleep(IGMK_WS_SLEEP);
+            if (++spins > (1 << 24)) __trap();          // never hang the GPU on a protocol error
+        }
+    }
+    __syncwarp();
+    __threadfence_block();
+}
+
+__global__ void __launch_bounds__(32 * (kWsFill + kWsSel), 1)
+actdist_ws_kernel(const ActdistParams P, const int V, const int nbuf) {
+    extern __shared__ uint4 s_keys[];             // [nbuf][2 V][32] key quads, then the locus-i tile
+    __shared__ uint32_t s_list[kWsSel][kWarpListCap];
+    __shared__ uint32_t s_cnt[kWsSel];
+    __shared__ WsMeta s_meta[32];
+    __shared__ uint32_t s_state[32];
+    __shared__ uint32_t s_slot[2];
+    __shared__ unsigned int s_ticket[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) s_state[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) {
+        s_slot[0] = (0xfffffu << 12) | (TS_EMPTY << 10);
+        s_slot[1] = (0xfffffu << 12) | (TS_EMPTY << 10);
+        s_ticket[0] = 0u; s_ticket[1] = 0u;
+    }
+    __syncthreads();
+    const unsigned int B = (unsigned int)P.tile_block;
+    const uint32_t keys0 = smem_addr(s_keys);
+    const uint32_t buf_bytes = 2u * (uint32_t)V * 512u;
+    Group<false> g;
+    g.tid = lane; g.nthr = 32; g.kstride = 512u; g.red = 0u; g.list2 = 0u; g.bbuf = 0u; g.parity = 0;
+    g.cap = kWarpListCap;
+    if (warp < kWsFill) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kWsFillRegs));
+        TileCtl tile;
+        tile.base = keys0 + (uint32_t)nbuf * buf_bytes;
+        tile.slot_bytes = 24u * (uint32_t)P.npad;
+        tile.words = smem_addr(s_slot);
+        tile.nslots = 1;
+        g.list = 0u; g.ctl = 0u;
+        for (;;) {
+            unsigned int t = 0u;
+            if (lane == 0) t = atomicAdd(&s_ticket[0], 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const unsigned int k = t / B, r = t - k * B;
+            const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
+            if (base >= P.n_pairs) break;
+            if (base + r >= P.n_pairs) continue;            // trailing tickets of the last block
+            const int b = (int)(t % (unsigned int)nbuf);
+            const uint32_t gen = t / (unsigned int)nbuf;
+            ws_wait(smem_addr(&s_state[b]), 2u * gen, lane);
+            g.kscr = keys0 + (uint32_t)b * buf_bytes + (uint32_t)lane * 16u;
+            // ---- first half of process_pair
+            const long long slot = base + r;
+            const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
+            const int i = __ldg(P.pi + pair);
+            const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
+            int cnt = -1;
+            uint32_t kmin = 0u, kmax = 0u;
+            if (d.valid) {
+                const PairPtrs pp = pair_ptrs(P, d);
+                uint32_t mn2, mx2;
+                const int tslot = tile_acquire(P, tile, i, d, pp, lane);
+                if (tslot >= 0) {
+                    const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
+                    const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
+                    switch (pair_shape(d, P.mode)) {
+                        case SH_FULL4:  fill_keys<SH_FULL4, true, false, kWsPipe>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
+                        case SH_INTRA2: fill_keys<SH_INTRA2, true, false, kWsPipe>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
+                        case SH_GP4:    fill_keys<SH_GP4, true, false>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
+                        default:        fill_keys<SH_GENERIC, true, false>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
+                    }
+                    tile_release(tile, tslot, lane);
+                } else {
+                    switch (pair_shape(d, P.mode)) {
+                        case SH_FULL4:  fill_keys<SH_FULL4, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
+                        case SH_INTRA2: fill_keys<SH_INTRA2, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
+                        case SH_GP4:    fill_keys<SH_GP4, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
+                        default:        fill_keys<SH_GENERIC, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
+                    }
+                }
+                kmin = min(mn2 & 0xffffu, mn2 >> 16);
+                uint32_t mxl = mx2 & 0xffffu, mxh = mx2 >> 16;
+                mxl = (mxl > 0x7f80u) ? 0u : mxl;
+                mxh = (mxh > 0x7f80u) ? 0u : mxh;
+                kmax = max(mxl, mxh);
+                g.sum_min_max(cnt, kmin, kmax);
+            }
+            if (lane == 0) {
+                s_meta[b].pair = pair; s_meta[b].cnt = cnt; s_meta[b].kmin = kmin; s_meta[b].kmax = kmax;
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) sts32(smem_addr(&s_state[b]), 2u * gen + 1u);
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kWsSelRegs));
+        const int sw = warp - kWsFill;
+        g.list = smem_addr(&s_list[sw][0]);
+        g.ctl = smem_addr(&s_cnt[sw]);
+        for (;;) {
+            unsigned int t = 0u;
+            if (lane == 0) t = atomicAdd(&s_ticket[1], 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const unsigned int k = t / B, r = t - k * B;
+            const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
+            if (base >= P.n_pairs) break;
+            if (base + r >= P.n_pairs) continue;
+            const int b = (int)(t % (unsigned int)nbuf);
+            const uint32_t gen = t / (unsigned int)nbuf;
+            ws_wait(smem_addr(&s_state[b]), 2u * gen + 1u, lane);
+            const long long pair = s_meta[b].pair;
+            const int cnt = s_meta[b].cnt;
+            const uint32_t kmin = s_meta[b].kmin, kmax = s_meta[b].kmax;
+            if (cnt < 0) {
+                emit_empty(P, lane, pair);
+            } else {
+                const int i = __ldg(P.pi + pair);
+                const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
+                const PairPtrs pp = pair_ptrs(P, d);
+                g.kscr = keys0 + (uint32_t)b * buf_bytes + (uint32_t)lane * 16u;
+                if (lane == 0) sts32(g.ctl, 0u);
+                __syncwarp();
+                select_part<false, false>(P, g, V, pair, d, pp, 0.0, cnt, kmin, kmax);
+            }
+            __syncwarp();
+            if (lane == 0) sts32(smem_addr(&s_state[b]), 2u * (gen + 1u));
+        }
     }
 }
 

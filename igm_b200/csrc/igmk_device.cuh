@@ -448,6 +448,15 @@ __device__ __forceinline__ Row6 load_row6(const float* p) {
     ldg_v2b64<HINT>(p + 2 * kSeg, r.z01, r.z23);
     return r;
 }
+// Same loads pinned in program order (software-pipelined fill of the warp-specialised
+// kernel: issued half a chunk before their first use, which lies in the NEXT iteration).
+__device__ __forceinline__ Row6 load_row6_stream_pinned(const float* p) {
+    Row6 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.x01), "=l"(r.x23) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.y01), "=l"(r.y23) : "l"(p + kSeg));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.z01), "=l"(r.z23) : "l"(p + 2 * kSeg));
+    return r;
+}
 // d2 of structures (4c+2h, 4c+2h+1), h = 0 / 1
 template <int H>
 __device__ __forceinline__ u64 d2pair(const Row6& a, const Row6& b, u64 nz) {

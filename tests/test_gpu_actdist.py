@@ -208,6 +208,31 @@ def test_block_groups_many_equal_distances(nconf, monkeypatch):
                 _check_against_details(res, dets)
 
 
+def test_warp_specialised_variant_matches(monkeypatch):
+    """IGMK_WS=1: the experimental kernel that runs the fill and select halves of a pair on
+    different warps (setmaxnreg, ring of key arrays) gives byte-identical results."""
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, 700, seed=41, genome_scale=0.05)
+    rng = np.random.default_rng(8)
+    nh = pop.n_hap
+    ii = rng.integers(0, nh, 70000)
+    jj = rng.integers(0, nh, 70000)
+    k = ii < jj
+    ii, jj = ii[k].astype(np.int32), jj[k].astype(np.int32)
+    order = np.lexsort((jj, ii))
+    ii, jj = ii[order], jj[order]
+    pw = rng.uniform(0.001, 1.0, len(ii))
+    with _engine(pop) as eng:
+        base = eng.actdist(ii, jj, pw, None, 2.0, 1, "lb", 0)
+        base_gp = eng.actdist(ii, jj, pw, None, 2.0, 0, "gp", 0)
+    monkeypatch.setenv("IGMK_WS", "1")
+    with _engine(pop) as eng:
+        ws = eng.actdist(ii, jj, pw, None, 2.0, 1, "lb", 0)
+        ws_gp = eng.actdist(ii, jj, pw, None, 2.0, 0, "gp", 0)
+    assert ws.tobytes() == base.tobytes()
+    assert ws_gp.tobytes() == base_gp.tobytes()
+
+
 def test_degenerate_inputs():
     """Identical coordinates (all distances equal), empty and i == j inputs."""
     from igm_b200.population import CopyIndex, Population
