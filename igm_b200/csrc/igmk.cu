@@ -91,6 +91,8 @@ extern "C" int igmk_version(void) { return IGMK_VERSION; }
 extern "C" const char* igmk_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t igmk_launch_count(void) { return (int64_t)g_launches.load(); }
 
+extern "C" int igmk_destroy(igmk_ctx* c);
+
 extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (!out) return fail(IGMK_EINVAL, "igmk_create: out is NULL");
     *out = nullptr;
@@ -102,26 +104,32 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
                     cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(IGMK_EINVAL, "igmk_create: device %d out of range", device);
     CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     igmk_ctx* c = new igmk_ctx();
     c->device = device;
     c->nbead = nbead;
     c->nstruct = nstruct;
     c->npad = (nstruct + kSeg - 1) / kSeg * kSeg;
     c->nchunks = (nstruct + 3) / 4;
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     // one extra all-zero row behind the population: the "origin bead" of the DamID path
     const size_t bytes = (size_t)(nbead + 1) * 3 * c->npad * sizeof(float);
     e = cudaMalloc(&c->d_coords, bytes);
     if (e != cudaSuccess) { delete c; return fail(IGMK_ECUDA, "igmk_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
-    cudaMemset(c->d_coords, 0, bytes);
-    cudaMalloc(&c->d_radii, (size_t)nbead * sizeof(float));
-    cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
-    cudaEventCreate(&c->ev0);
-    cudaEventCreate(&c->ev1);
+    // every further resource is checked; a failure releases what exists so far
+    e = cudaMemset(c->d_coords, 0, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_radii, (size_t)nbead * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        const int rc = fail(IGMK_ECUDA, "igmk_create: device resources: %s", cudaGetErrorString(e));
+        igmk_destroy(c);
+        return rc;
+    }
     const char* ov = getenv("IGMK_GROUP_THREADS");
     if (ov) c->group_threads = atoi(ov);
     ov = getenv("IGMK_L2_BUDGET");
