@@ -32,7 +32,7 @@ EXPORTS = (
     "igmk_version", "igmk_last_error", "igmk_launch_count", "igmk_create", "igmk_destroy",
     "igmk_upload_coords", "igmk_upload_coords_range", "igmk_set_index",
     "igmk_actdist_device", "igmk_actdist_host", "igmk_actdist_device_peers",
-    "igmk_finish_results_device", "igmk_expand_records",
+    "igmk_finish_results_device", "igmk_expand_records", "igmk_filter_candidates", "igmk_join_plast",
     "igmk_damid_actdist_device", "igmk_damid_actdist_host",
     "igmk_contact_counts_device", "igmk_contact_counts_host",
     "igmk_contact_counts_haploid_device", "igmk_contact_counts_haploid_host",
@@ -85,6 +85,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.igmk_restraint_words.argtypes = [vp]
     lib.igmk_restraint_select_device.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int, vp, vp, vp]
     lib.igmk_restraint_select_host.argtypes = [vp, C.c_int64, i32p, i32p, f32p, C.c_int, vp, vp]
+    lib.igmk_filter_candidates.restype = C.c_int64
+    lib.igmk_filter_candidates.argtypes = [C.c_int64, vp, i32p, f32p, i32p, C.c_int, C.c_float, C.c_int, C.c_float,
+                                           i32p, i32p, f64p, C.c_int64]
+    lib.igmk_join_plast.argtypes = [C.c_int64, i32p, i32p, f32p, C.c_int32, C.c_int64, i32p, i32p, f64p]
     lib.igmk_sprite_rg2_host.argtypes = [vp, C.c_int, i32p, i32p, i32p, f32p, i32p, i32p]
     lib.igmk_sprite_cluster_rg2_host.argtypes = [vp, C.c_int, i32p, i32p, i32p, i32p, i32p, i32p, f32p]
     lib.igmk_rank_match_device.argtypes = [vp, C.c_int64, i32p, i32p, C.c_int, f32p, C.c_int64, vp, vp, vp, vp]

@@ -589,6 +589,69 @@ extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
 
 extern "C" float igmk_last_kernel_ms(igmk_ctx* c) { return c ? c->last_kernel_ms : 0.f; }
 
+// ---------------------------------------------------------------- host phases of setup()
+// Candidate filter of the reference's setup loop (ActivationDistanceStep.py:166-178) over
+// a strict-upper-triangle CSR matrix: entry (r, c, p) is kept if r != c and
+// p >= intra_sigma (same chromosome) / p >= inter_sigma (different chromosomes), the
+// comparison in float32 as NumPy >= 2 evaluates `float32 >= python float`.  Pure host
+// code (no device needed).  Returns the number of candidates, or -1 - needed when
+// `capacity` is too small (nothing is written beyond capacity).
+extern "C" int64_t igmk_filter_candidates(int64_t n_rows, const int64_t* indptr, const int32_t* indices,
+                                          const float* data, const int32_t* chrom,
+                                          int use_intra, float intra_sigma, int use_inter, float inter_sigma,
+                                          int32_t* out_i, int32_t* out_j, double* out_p, int64_t capacity) {
+    if (n_rows < 0 || !indptr || (indptr[n_rows] > 0 && (!indices || !data || !chrom))) return -1;
+    int64_t k = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int cr = chrom[r];
+        for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+            const int32_t c = indices[e];
+            const float p = data[e];
+            const bool intra = chrom[c] == cr;
+            const bool keep = (intra ? (use_intra && p >= intra_sigma) : (use_inter && p >= inter_sigma)) && c != (int32_t)r;
+            if (!keep) continue;
+            if (k < capacity) { out_i[k] = (int32_t)r; out_j[k] = c; out_p[k] = (double)p; }
+            ++k;
+        }
+    }
+    return (k <= capacity) ? k : -1 - k;
+}
+
+// plast[i, j] of setup (:144-160, :177) as a merge join: the stored records (row, col, prob)
+// restricted to row < n and col < n, against the candidate list (ii, jj), both in strictly
+// increasing (row, col) order - what files written by this step and CSR-ordered candidate
+// lists are.  Returns 1 when done, 0 when either side is not strictly increasing (the caller
+// then takes the general path), -1 on bad arguments.
+extern "C" int igmk_join_plast(int64_t n_rec, const int32_t* row, const int32_t* col, const float* prob,
+                               int32_t n, int64_t n_pairs, const int32_t* ii, const int32_t* jj,
+                               double* out) {
+    if (n_rec < 0 || n_pairs < 0 || (n_rec > 0 && (!row || !col || !prob)) || (n_pairs > 0 && (!ii || !jj || !out)))
+        return -1;
+    auto key = [n](int32_t a, int32_t b) { return (int64_t)a * n + b; };
+    int64_t last = -1;
+    for (int64_t t = 0; t < n_pairs; ++t) {
+        const int64_t kq = key(ii[t], jj[t]);
+        if (kq <= last) return 0;
+        last = kq;
+    }
+    last = -1;
+    for (int64_t e = 0; e < n_rec; ++e) {
+        if (row[e] >= n || col[e] >= n) continue;
+        const int64_t kr = key(row[e], col[e]);
+        if (kr <= last) return 0;
+        last = kr;
+    }
+    for (int64_t t = 0; t < n_pairs; ++t) out[t] = 0.0;
+    int64_t t = 0;
+    for (int64_t e = 0; e < n_rec && t < n_pairs; ++e) {
+        if (row[e] >= n || col[e] >= n) continue;
+        const int64_t kr = key(row[e], col[e]);
+        while (t < n_pairs && key(ii[t], jj[t]) < kr) ++t;
+        if (t < n_pairs && key(ii[t], jj[t]) == kr) out[t] = (double)prob[e];
+    }
+    return 1;
+}
+
 // Record expansion, host side: task() flattening + get_actdist's result lists
 // (ActivationDistanceStep.py:221-222, 476-483).
 extern "C" int igmk_expand_records(igmk_ctx* c, int64_t n_pairs,

@@ -28,7 +28,7 @@ import shutil
 
 import numpy as np
 
-from .. import hdf5
+from .. import _lib, hdf5
 from ..engine import ActdistEngine
 from ..population import Population, ProbMatrix
 from ._compat import Step, logger, make_absolute_path
@@ -38,7 +38,7 @@ actdist_shape = [("row", "int32"), ("col", "int32"), ("dist", "float32"), ("prob
 actdist_fmt_str = "%6d %6d %10.4f %.4f"
 
 
-def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np.float32):
+def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np.float32, native=True):
     """Candidate filter of the reference's setup loop (:166-178), vectorised.
 
     Stored non-zeros are visited in CSR row-major order (what ``coo_generator``
@@ -46,14 +46,28 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
     reference compares a float32 matrix value with a Python float, which under
     NumPy >= 2 happens in float32.  ``i == j`` entries are
     dropped (they never produce a record, :379-380).  Returns (i, j, pwish64).
+    ``native=False`` (or a compare dtype other than float32) takes the NumPy form.
     """
     dt = np.dtype(compare_dtype)
-    pw = pm.data.astype(dt, copy=False)
     use_intra = intra_sigma is not False and intra_sigma is not None
     use_inter = inter_sigma is not False and inter_sigma is not None
     if not (use_intra or use_inter):
         z = np.zeros(0, np.int32)
         return z, z.copy(), np.zeros(0, np.float64)
+    if dt == np.float32 and native:
+        # one pass over the CSR arrays in the C library (igmk_filter_candidates)
+        lib = _lib.load()
+        cap = int(len(pm.indices))
+        oi, oj, op = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float64)
+        k = lib.igmk_filter_candidates(pm.n, _lib.ptr(pm.indptr), _lib.ptr(pm.indices), _lib.ptr(pm.data),
+                                       _lib.ptr(pm.chrom), int(use_intra),
+                                       float(np.float32(intra_sigma)) if use_intra else 0.0, int(use_inter),
+                                       float(np.float32(inter_sigma)) if use_inter else 0.0,
+                                       _lib.ptr(oi), _lib.ptr(oj), _lib.ptr(op), cap)
+        if k < 0:
+            raise RuntimeError("igmk_filter_candidates failed (%d)" % k)
+        return oi[:k].copy(), oj[:k].copy(), op[:k].copy()
+    pw = pm.data.astype(dt, copy=False)
     # first cut on the probability alone (the smaller threshold), then the intra / inter
     # distinction on the survivors only
     lo = min([dt.type(x) for x, u in ((intra_sigma, use_intra), (inter_sigma, use_inter)) if u])
@@ -77,7 +91,7 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
             pm.data[idx].astype(np.float64))
 
 
-def lookup_plast(last_actdist_file, n, ii, jj):
+def lookup_plast(last_actdist_file, n, ii, jj, native=True):
     """``plast[i, j]`` of setup (:144-160,177): the previous iteration's stored
     ``prob`` of the record whose (row, col) are the haploid indices themselves
     (only records with row < n and col < n survive the mask, quirk q7)."""
@@ -88,6 +102,18 @@ def lookup_plast(last_actdist_file, n, ii, jj):
         row = np.asarray(h5f["row"][()])
         col = np.asarray(h5f["col"][()])
         prob = np.asarray(h5f["prob"][()])
+    if native and len(ii) and n < 2 ** 31:
+        # both sides in (row, col) order - the usual case: one merge pass in the C library
+        r32, c32 = np.ascontiguousarray(row, np.int32), np.ascontiguousarray(col, np.int32)
+        p32 = np.ascontiguousarray(prob, np.float32)
+        i32, j32 = np.ascontiguousarray(ii, np.int32), np.ascontiguousarray(jj, np.int32)
+        rc = _lib.load().igmk_join_plast(len(r32), _lib.ptr(r32), _lib.ptr(c32), _lib.ptr(p32), int(n), len(i32),
+                                         _lib.ptr(i32), _lib.ptr(j32), _lib.ptr(out))
+        if rc == 1:
+            return out
+        if rc < 0:
+            raise RuntimeError("igmk_join_plast: bad arguments")
+        out[:] = 0.0
     m = np.logical_and(row < n, col < n)
     key = row[m].astype(np.int64) * n + col[m].astype(np.int64)
     val = prob[m].astype(np.float32)

@@ -152,6 +152,25 @@ int igmk_expand_records(igmk_ctx* ctx, int64_t n_pairs,
                         int32_t* row, int32_t* col, float* dist, float* prob,
                         int64_t capacity, int64_t* n_records);
 
+/* Host phases of setup() (pure host code, no device needed).
+ * igmk_filter_candidates: the candidate filter of the reference's setup loop
+ * (igm/steps/ActivationDistanceStep.py:166-178) over the strict-upper-triangle CSR matrix of
+ * the .hcs file: entry (r, c, p) is kept if r != c and p >= intra_sigma (chrom[r] == chrom[c])
+ * or p >= inter_sigma (otherwise), compared in float32; use_intra / use_inter = 0 disables a
+ * class (the reference's `False` sigma).  Writes (i, j, pwish as float64) in CSR order and
+ * returns their number, or -1 - needed when capacity is too small.
+ * igmk_join_plast: plast[i, j] of :144-160,177 - the stored `prob` of the previous
+ * iteration's record whose (row, col) are the haploid indices (records with row >= n or
+ * col >= n are skipped, quirk q7) - as a merge join for inputs in strictly increasing
+ * (row, col) order.  Returns 1 when done, 0 when an input is not in that order (nothing
+ * useful written; the caller takes its general path), -1 on bad arguments. */
+int64_t igmk_filter_candidates(int64_t n_rows, const int64_t* indptr, const int32_t* indices,
+                               const float* data, const int32_t* chrom,
+                               int use_intra, float intra_sigma, int use_inter, float inter_sigma,
+                               int32_t* out_i, int32_t* out_j, double* out_p, int64_t capacity);
+int igmk_join_plast(int64_t n_rec, const int32_t* row, const int32_t* col, const float* prob,
+                    int32_t n, int64_t n_pairs, const int32_t* ii, const int32_t* jj, double* out);
+
 /* Population contact-frequency counts for a tile of bead pairs
  * (HssFile.buildContactMap as used by igm/steps/HicEvaluationStep.py:107-112
  * and igm/report/hic.py:51; in-tree statement of the formula:

@@ -224,3 +224,35 @@ def test_sprite_step_setup_and_reduce_host_logic(tmp_path):
         assert np.array_equal(np.asarray(f["assignment"][()]), exp_assign)
         assert np.array_equal(np.asarray(f["selected"][()]), exp_sel)
     assert (exp_assign >= 0).any()
+
+
+@pytest.mark.parametrize("sig", [(0.2, 0.2), (0.05, 0.3), (0.3, 0.05), (False, 0.1), (0.1, False), (None, None)])
+def test_native_filter_equals_numpy_form(sig):
+    """igmk_filter_candidates (C) against the vectorised NumPy form, every sigma combination."""
+    pm = _small_matrix(seed=4)
+    a = S.filter_candidates(pm, sig[0], sig[1], native=True)
+    b = S.filter_candidates(pm, sig[0], sig[1], native=False)
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    if sig[0] and sig[1]:
+        assert len(a[0]) > 0
+
+
+def test_native_plast_join_equals_general_path(tmp_path):
+    rng = np.random.default_rng(1)
+    n = 120
+    ii, jj = np.triu_indices(n, 1)
+    keep = np.sort(rng.choice(len(ii), 2500, replace=False))
+    ii, jj = ii[keep].astype(np.int32), jj[keep].astype(np.int32)
+    prev = np.sort(rng.choice(len(ii), 1400, replace=False))
+    row = np.repeat(ii[prev], 2); col = np.repeat(jj[prev], 2)
+    row[1::2] += n
+    prob = orc.text_roundtrip(rng.uniform(0, 1, len(row)))
+    f = str(tmp_path / "actdist.hdf5")
+    hdf5.write_h5(f, {"row": row.astype(np.int32), "col": col.astype(np.int32),
+                      "dist": np.zeros(len(row), np.float32), "prob": prob})
+    a = S.lookup_plast(f, n, ii, jj, native=True)
+    b = S.lookup_plast(f, n, ii, jj, native=False)
+    assert np.array_equal(a, b) and (a > 0).sum() > 1000
+    perm = rng.permutation(len(ii))                      # unsorted candidates: the C join declines
+    assert np.array_equal(S.lookup_plast(f, n, ii[perm], jj[perm], native=True), b[perm])
