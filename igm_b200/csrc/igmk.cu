@@ -272,6 +272,16 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     if (warps < 1) return fail(IGMK_ELIMIT, "actdist_warp_kernel: nstruct = %d is too large for one warp per pair", c->nstruct);
     P.tile_block = tile_bytes ? c->tile_block : 0;
     P.tile_slots = slots;
+    if (P.tile_block > 0) {
+        // short lists: blocks are dealt to the CTAs round-robin, so keep about eight blocks
+        // per CTA (a list of 229 k pairs in blocks of 512 gives most CTAs 3 blocks and some 4)
+        const long long per_cta = (P.n_pairs + c->sm_count - 1) / c->sm_count;
+        if (per_cta < 8LL * P.tile_block) {
+            long long b = ((per_cta + 7) / 8 + 31) / 32 * 32;
+            if (b < 32) b = 32;
+            if (b < P.tile_block) P.tile_block = (int)b;
+        }
+    }
     if (c->warp_specialised && !DAMID && tile_bytes && slots == 1) {
         // experimental: fill and select halves on different warps (IGMK_WS=1)
         const size_t buf_bytes = (size_t)2 * V * 32 * 16;
