@@ -74,6 +74,9 @@ struct igmk_ctx {
     void* d_order = nullptr; size_t order_bytes = 0;    // keys / values / cub temp of order_pairs()
     int tile_block = 512;        // IGMK_TILE_BLOCK (0: no shared-memory locus-i tile)
     int tile_slots = 1;          // IGMK_TILE_SLOTS (2 slots shrink L1 to 15 KB at N = 1000: slower)
+    unsigned int* d_blockctr = nullptr;   // ring of 64 block counters (one per launch in flight)
+    unsigned int ctr_next = 0;
+    int dynamic_blocks = 0;      // IGMK_DYNAMIC_BLOCKS: pair blocks handed out by a device-wide counter (config 2: -1 %, config 5: +3.5 %)
     int warp_specialised = 0;    // IGMK_WS: experimental warp-specialised K1 (fill / select warps, setmaxnreg)
     int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
 };
@@ -120,6 +123,7 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     // every further resource is checked; a failure releases what exists so far
     e = cudaMemset(c->d_coords, 0, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_radii, (size_t)nbead * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_blockctr, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
@@ -144,6 +148,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov && atoll(ov) > 0) c->host_slice_pairs = atoll(ov);
     ov = getenv("IGMK_WARPS_PER_CTA");
     if (ov) c->warps_per_cta = atoi(ov);
+    ov = getenv("IGMK_DYNAMIC_BLOCKS");
+    if (ov) c->dynamic_blocks = atoi(ov);
     ov = getenv("IGMK_WS");
     if (ov) c->warp_specialised = atoi(ov);
     ov = getenv("IGMK_BLOCK_STOP");
@@ -159,6 +165,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_coords);
     cudaFree(c->d_radii);
+    cudaFree(c->d_blockctr);
     cudaFree(c->d_chrom);
     cudaFree(c->d_hap);
     cudaFree(c->d_stage);
@@ -297,6 +304,12 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
             CUDA_TRY(cudaGetLastError());
             return launch_finish(P, st);
         }
+    }
+    P.block_counter = nullptr;
+    if (P.tile_block > 0 && c->dynamic_blocks && c->d_blockctr) {
+        igmk_ctx* cm = const_cast<igmk_ctx*>(c);
+        P.block_counter = c->d_blockctr + (cm->ctr_next++ & 63u);
+        CUDA_TRY(cudaMemsetAsync(P.block_counter, 0, sizeof(unsigned int), st));
     }
     int per_sm = 0;
     const size_t smem = (size_t)warps * 2 * V * 32 * 16 + tile_bytes;

@@ -818,6 +818,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     __shared__ uint32_t s_cnt[kWarpsPerBlock];
     __shared__ uint32_t s_slot[2];
     __shared__ unsigned int s_ticket;
+    __shared__ unsigned long long s_gblock[8];
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;           // <= kWarpsPerBlock (fewer when V is large)
     Group<false> g;
@@ -844,12 +845,48 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
             s_slot[1] = (0xfffffu << 12) | (TS_EMPTY << 10);
             s_ticket = 0u;
         }
+        if (threadIdx.x < 8) s_gblock[threadIdx.x] = 0ull;
         __syncthreads();
         // CTA-contiguous blocks of tile_block pairs (block k of this CTA = list block
         // blockIdx + k * gridDim), handed to the warps one pair at a time by a
         // shared ticket counter: consecutive pairs share locus i, and fast / slow
         // pairs balance out across the warps.
         const unsigned int B = (unsigned int)P.tile_block;
+        if (P.block_counter) {
+            // dynamic variant: the CTA's k-th block is whatever list block the device-wide
+            // counter hands out next (fetched by the warp that draws the block's first
+            // ticket, published to the other warps through one 64-bit word per slot:
+            // (k + 1) << 32 | block), so CTAs that drew cheap blocks simply take more of them
+            for (;;) {
+                unsigned int t = 0u;
+                if (g.tid == 0) t = atomicAdd(&s_ticket, 1u);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                const unsigned int k = t / B, r = t - k * B;
+                unsigned int gb = 0u;
+                if (g.tid == 0) {
+                    volatile unsigned long long* w = &s_gblock[k & 7u];
+                    if (r == 0u) {
+                        gb = atomicAdd(P.block_counter, 1u);
+                        *w = ((unsigned long long)(k + 1u) << 32) | gb;
+                    } else {
+                        unsigned long long x;
+                        int spins = 0;
+                        while ((unsigned int)((x = *w) >> 32) != k + 1u) {
+                            __nanosleep(20);
+                            if (++spins > (1 << 24)) __trap();      // protocol error: never hang the GPU
+                        }
+                        gb = (unsigned int)x;
+                    }
+                }
+                gb = __shfl_sync(0xffffffffu, gb, 0);
+                const long long base = (long long)gb * B;
+                if (base >= P.n_pairs) break;
+                const long long pair = base + r;
+                if (pair < P.n_pairs) process_pair<false, DAMID>(P, g, V, pair, tile);
+                __syncwarp();
+            }
+            return;
+        }
         for (;;) {
             unsigned int t = 0u;
             if (g.tid == 0) t = atomicAdd(&s_ticket, 1u);

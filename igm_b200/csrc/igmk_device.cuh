@@ -64,6 +64,7 @@ struct ActdistParams {
     const int32_t* perm;      // processing order (NULL: input order), see igmk.cu order_pairs()
     int   tile_slots;         // 1 or 2 locus-i tiles per CTA
     int   tile_block;         // warp kernel: pairs per CTA-contiguous block; 0 = no locus-i tile in shared memory
+    unsigned int* block_counter;  // warp kernel: device-wide counter handing out pair blocks (NULL: static round-robin)
     int   block_stop;         // CTA groups: the key bisection stops at <= block_stop candidates (<= kBlockListCap)
     u64   negzero2;           // {-0.0f, -0.0f}: opaque addend of the packed squares (igmk_actdist.cuh)
 };

@@ -231,6 +231,12 @@ def test_warp_specialised_variant_matches(monkeypatch):
         ws_gp = eng.actdist(ii, jj, pw, None, 2.0, 0, "gp", 0)
     assert ws.tobytes() == base.tobytes()
     assert ws_gp.tobytes() == base_gp.tobytes()
+    # pair blocks handed out by a device-wide counter instead of round-robin
+    monkeypatch.delenv("IGMK_WS")
+    monkeypatch.setenv("IGMK_DYNAMIC_BLOCKS", "1")
+    with _engine(pop) as eng:
+        dyn = eng.actdist(ii, jj, pw, None, 2.0, 1, "lb", 0)
+    assert dyn.tobytes() == base.tobytes()
 
 
 def test_degenerate_inputs():
