@@ -256,3 +256,36 @@ def test_native_plast_join_equals_general_path(tmp_path):
     assert np.array_equal(a, b) and (a > 0).sum() > 1000
     perm = rng.permutation(len(ii))                      # unsorted candidates: the C join declines
     assert np.array_equal(S.lookup_plast(f, n, ii[perm], jj[perm], native=True), b[perm])
+
+
+def test_hdf5_writer_roundtrip_property(tmp_path):
+    """The streaming writer against the reader over random dataset sets: dtypes, shapes
+    (incl. empty and 2-D), one group level, attributes; every dataset is 8-byte aligned."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    dtypes = [np.int32, np.int64, np.float32, np.float64, np.uint8, np.int16]
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(st.tuples(st.sampled_from(range(len(dtypes))), st.integers(0, 3000), st.integers(1, 3),
+                              st.booleans()), min_size=1, max_size=7),
+           st.integers(0, 2 ** 31 - 1))
+    def run(spec, seed):
+        rng = np.random.default_rng(seed)
+        data = {}
+        for k, (di, n, cols, grouped) in enumerate(spec):
+            shape = (n,) if cols == 1 else (n, cols)
+            a = (rng.integers(-1000, 1000, size=shape)).astype(dtypes[di])
+            data[("g/" if grouped else "") + "d%d" % k] = a
+        f = str(tmp_path / "p.h5")
+        hdf5.write_h5(f, data, attrs={"n": np.int64(len(data))})
+        with hdf5.open_h5(f) as h:
+            assert h.attrs["n"] == len(data)
+            for name, a in data.items():
+                node = h
+                for part in name.split("/"):
+                    node = node[part]
+                got = node[()]
+                assert got.dtype == a.dtype and got.shape == a.shape and np.array_equal(got, a)
+                if a.size:
+                    assert np.array_equal(node[:max(1, a.shape[0] // 2)], a[:max(1, a.shape[0] // 2)])
+    run()
