@@ -76,7 +76,9 @@ struct igmk_ctx {
     int tile_slots = 1;          // IGMK_TILE_SLOTS (2 slots shrink L1 to 15 KB at N = 1000: slower)
     unsigned int* d_blockctr = nullptr;   // ring of 64 block counters (one per launch in flight)
     unsigned int ctr_next = 0;
-    int dynamic_blocks = 0;      // IGMK_DYNAMIC_BLOCKS: pair blocks handed out by a device-wide counter (config 2: -1 %, config 5: +3.5 %)
+    int dynamic_blocks = -1;     // IGMK_DYNAMIC_BLOCKS: pair blocks handed out by a device-wide counter; -1 = for lists of
+                                 // more than 8 M pairs (CTAs drift apart over a long list and lose the J-block's L2
+                                 // residency: config 5 +4 %; config 2 -1 %)
     int warp_specialised = 0;    // IGMK_WS: experimental warp-specialised K1 (fill / select warps, setmaxnreg)
     int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
 };
@@ -306,7 +308,8 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
         }
     }
     P.block_counter = nullptr;
-    if (P.tile_block > 0 && c->dynamic_blocks && c->d_blockctr) {
+    const bool dyn = (c->dynamic_blocks < 0) ? (P.n_pairs > (8LL << 20)) : (c->dynamic_blocks != 0);
+    if (P.tile_block > 0 && dyn && c->d_blockctr) {
         igmk_ctx* cm = const_cast<igmk_ctx*>(c);
         P.block_counter = c->d_blockctr + (cm->ctr_next++ & 63u);
         CUDA_TRY(cudaMemsetAsync(P.block_counter, 0, sizeof(unsigned int), st));
