@@ -329,7 +329,14 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
 }
 
 template <int MAXT, bool DAMID>
-static int launch_block(const igmk_ctx* c, const ActdistParams& P, int threads, cudaStream_t st) {
+static int launch_block(const igmk_ctx* c, const ActdistParams& Pin, int threads, cudaStream_t st) {
+    ActdistParams P = Pin;
+    P.block_counter = nullptr;
+    if (c->dynamic_blocks > 0 && c->d_blockctr && P.n_pairs < 0xffffffffLL) {      // IGMK_DYNAMIC_BLOCKS=1
+        igmk_ctx* cm = const_cast<igmk_ctx*>(c);
+        P.block_counter = c->d_blockctr + (cm->ctr_next++ & 63u);
+        CUDA_TRY(cudaMemsetAsync(P.block_counter, 0, sizeof(unsigned int), st));
+    }
     const int V = (c->nchunks + threads - 1) / threads;
     int per_sm = 0;
     const size_t smem = (size_t)2 * V * threads * 16;

@@ -1099,6 +1099,20 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     g.parity = 0;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;
+    if (P.block_counter) {
+        // pairs handed out by a device-wide counter (list order): the CTAs stay together in
+        // the list and share the J-block's L2 residency instead of drifting apart
+        __shared__ unsigned int s_next;
+        for (;;) {
+            if (threadIdx.x == 0) s_next = atomicAdd(P.block_counter, 1u);
+            __syncthreads();
+            const long long pair = (long long)s_next;
+            if (pair >= P.n_pairs) break;
+            process_pair<true, DAMID>(P, g, V, pair, tile);
+            __syncthreads();
+        }
+        return;
+    }
     for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
         process_pair<true, DAMID>(P, g, V, pair, tile);
         __syncthreads();
