@@ -183,8 +183,11 @@ def _get_engine(hss_path, device):
     key = (os.path.abspath(hss_path), st.st_mtime_ns, st.st_size, device)
     eng = _engine_cache.get(key)
     if eng is None:
+        # a new population (or a rewritten file) replaces everything that was staged; engines
+        # of the SAME file on other devices stay (gpu_shards > 1: one shard per device)
         for k in list(_engine_cache):
-            _engine_cache.pop(k).close()
+            if k[:3] != key[:3] or k[3] == device:
+                _engine_cache.pop(k).close()
         eng = ActdistEngine.from_hss(hss_path, device)     # chunk-wise staging, no host copy
         _engine_cache[key] = eng
     return eng

@@ -289,3 +289,28 @@ def test_hdf5_writer_roundtrip_property(tmp_path):
                 if a.size:
                     assert np.array_equal(node[:max(1, a.shape[0] // 2)], a[:max(1, a.shape[0] // 2)])
     run()
+
+
+def test_engine_cache_keeps_one_engine_per_device(tmp_path, monkeypatch):
+    """_get_engine: shards of one A-step on different devices keep their staged populations;
+    a rewritten or different .hss replaces all of them."""
+    made, closed = [], []
+
+    class FakeEngine:
+        def __init__(self, path, device):
+            self.tag = (path, device)
+            made.append(self.tag)
+
+        def close(self):
+            closed.append(self.tag)
+
+    monkeypatch.setattr(S, "ActdistEngine", type("E", (), {"from_hss": staticmethod(lambda p, d: FakeEngine(p, d))}))
+    monkeypatch.setattr(S, "_engine_cache", {})
+    a, b = str(tmp_path / "a.hss"), str(tmp_path / "b.hss")
+    open(a, "wb").write(b"x" * 10)
+    open(b, "wb").write(b"y" * 20)
+    e0 = S._get_engine(a, 0)
+    e1 = S._get_engine(a, 1)
+    assert S._get_engine(a, 0) is e0 and S._get_engine(a, 1) is e1 and not closed
+    S._get_engine(b, 0)                                   # another population: both are released
+    assert sorted(closed) == [(a, 0), (a, 1)] and len(S._engine_cache) == 1
