@@ -476,7 +476,7 @@ def main():
                 "note": "issue slots used (4 schedulers per SM at the sampled SM clock); the kernel is latency-bound"}
         if e2e is not None:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
             # bounded CPU sample (about --cpu-seconds of work on all host cores):
             # needs host copies of the beads the sample touches
             nb = 320000
