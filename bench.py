@@ -474,6 +474,16 @@ def main():
                 "peak_winst_per_s": sms * 4 * sm_mhz * 1e6,
                 "frac": winst / (k_ms * 1e-3) / (sms * 4 * sm_mhz * 1e6),
                 "note": "issue slots used (4 schedulers per SM at the sampled SM clock); the kernel is latency-bound"}
+        # ... and the unit it keeps busiest: the L1 / shared-memory data pipe (LSU wavefronts,
+        # 128 bytes per clock per SM) - ncu figure of the committed capture, rescaled to the
+        # live kernel time
+        l1pct = measured_traffic(args.nstruct, n_pairs, args.mode, "l1tex_lsu_data_pipe_pct")
+        ms_ncu = measured_traffic(args.nstruct, n_pairs, args.mode, "kernel_ms_under_ncu")
+        if l1pct and ms_ncu:
+            line["roofline"]["l1tex"] = {
+                "lsu_data_pipe_frac": l1pct / 100.0 * ms_ncu / k_ms,
+                "lsu_data_pipe_frac_under_ncu": l1pct / 100.0, "kernel_ms_under_ncu": ms_ncu,
+                "note": "l1tex__data_pipe_lsu_wavefronts: coordinate loads, tile and key-array traffic"}
         if e2e is not None:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only

@@ -34,6 +34,9 @@ def main():
                  "dram_bytes_per_launch": tot, "kernel_ms_under_ncu": float(row[ix["gpu__time_duration.sum"]]) *
                  {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[units[ix["gpu__time_duration.sum"]]],
                  "report": os.path.basename(rep)}
+        k = "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"
+        if k in ix:
+            entry["l1tex_lsu_data_pipe_pct"] = float(row[ix[k]])
         if "smsp__inst_executed.sum" in ix:
             entry["warp_instructions_per_launch"] = float(row[ix["smsp__inst_executed.sum"]])
         path = os.path.join(HERE, "traffic.json")
