@@ -329,6 +329,7 @@ def main():
     if world > 1:
         dist.barrier()
     launches = launch_count() - l0
+    redo_pairs = eng.last_redo_count()
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -451,6 +452,7 @@ def main():
                 "l2": "inputs larger than L2 (coordinates %.0f MB, pair list %.0f MB)" % (
                     nbead * 3 * eng.nstruct * 4 / 1e6, n_pairs * 24 / 1e6),
                 "parity_sample_ok": parity,
+                "list_form_redo_pairs": redo_pairs,
                 "sigma_sweep": sweep,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

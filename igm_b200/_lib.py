@@ -39,7 +39,7 @@ EXPORTS = (
     "igmk_set_bead_chrom", "igmk_restraint_words", "igmk_restraint_select_device",
     "igmk_restraint_select_host", "igmk_sprite_rg2_host", "igmk_sprite_cluster_rg2_host",
     "igmk_rank_match_device", "igmk_rank_match_host",
-    "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms",
+    "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms", "igmk_last_redo_count",
 )
 
 
@@ -97,6 +97,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.igmk_host_free.argtypes = [vp]
     lib.igmk_last_kernel_ms.argtypes = [vp]
     lib.igmk_last_kernel_ms.restype = C.c_float
+    lib.igmk_last_redo_count.argtypes = [vp]
+    lib.igmk_last_redo_count.restype = C.c_int64
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("igmk_version",):

@@ -18,6 +18,7 @@
 
 #include "../../include/igmk.h"
 #include "igmk_actdist.cuh"
+#include "igmk_actdist_list.cuh"
 #include "igmk_contact.cuh"
 #include "igmk_restraint.cuh"
 #include "igmk_sprite.cuh"
@@ -79,7 +80,12 @@ struct igmk_ctx {
     int dynamic_blocks = -1;     // IGMK_DYNAMIC_BLOCKS: pair blocks handed out by a device-wide counter; -1 = for lists of
                                  // more than 8 M pairs (CTAs drift apart over a long list and lose the J-block's L2
                                  // residency: config 5 +4 %; config 2 -1 %)
-    int warp_specialised = 0;    // IGMK_WS: experimental warp-specialised K1 (fill / select warps, setmaxnreg)
+    int list_form = 1;           // IGMK_LIST: 1 = list form first, key-array kernels for what it hands back; 0 = key arrays only
+    float list_z = 2.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
+    float list_budget = 12.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
+    void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
+    unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
+    bool redo_pending = false;
     int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
 };
 
@@ -152,8 +158,12 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov) c->warps_per_cta = atoi(ov);
     ov = getenv("IGMK_DYNAMIC_BLOCKS");
     if (ov) c->dynamic_blocks = atoi(ov);
-    ov = getenv("IGMK_WS");
-    if (ov) c->warp_specialised = atoi(ov);
+    ov = getenv("IGMK_LIST");
+    if (ov) c->list_form = atoi(ov);
+    ov = getenv("IGMK_LIST_Z");
+    if (ov) c->list_z = (float)atof(ov);
+    ov = getenv("IGMK_LIST_BUDGET");
+    if (ov) c->list_budget = (float)atof(ov);
     ov = getenv("IGMK_BLOCK_STOP");
     if (ov) c->block_stop = atoi(ov);
     if (c->block_stop < kRankCap) c->block_stop = kRankCap;
@@ -173,6 +183,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_stage);
     cudaFree(c->d_pairs);
     cudaFree(c->d_order);
+    cudaFree(c->d_redo);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
@@ -267,13 +278,14 @@ static int launch_finish(const ActdistParams& P, cudaStream_t st) {
 }
 
 template <bool DAMID>
-static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
+static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st, bool redo = false) {
     const int V = (c->nchunks + 31) / 32;
     // one CTA per SM: two locus-i tiles (2 rows of 12 * npad bytes each) plus as many
     // warps as the key arrays (V KiB per warp) leave room for
     const size_t budget = 208 * 1024;
     const int slots = (c->tile_slots == 1) ? 1 : 2;
-    size_t tile_bytes = (!DAMID && c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)slots * 24 * c->npad : 0;
+    // (a redo launch works through an unordered list of unknown length: no locus-i tile)
+    size_t tile_bytes = (!DAMID && !redo && c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)slots * 24 * c->npad : 0;
     if (tile_bytes + (size_t)8 * 2 * V * 32 * 16 > budget) tile_bytes = 0;     // keep >= 8 warps
     int warps = (int)((budget - tile_bytes) / ((size_t)2 * V * 32 * 16));
     if (warps > kWarpsPerBlock) warps = kWarpsPerBlock;
@@ -289,22 +301,6 @@ static int launch_warp(const igmk_ctx* c, ActdistParams P, cudaStream_t st) {
             long long b = ((per_cta + 7) / 8 + 31) / 32 * 32;
             if (b < 32) b = 32;
             if (b < P.tile_block) P.tile_block = (int)b;
-        }
-    }
-    if (c->warp_specialised && !DAMID && tile_bytes && slots == 1) {
-        // experimental: fill and select halves on different warps (IGMK_WS=1)
-        const size_t buf_bytes = (size_t)2 * V * 32 * 16;
-        int nbuf = (int)((budget - tile_bytes) / buf_bytes);
-        if (nbuf > 32) nbuf = 32;
-        if (nbuf >= kWsFill + 4) {
-            const size_t smem_ws = (size_t)nbuf * buf_bytes + tile_bytes;
-            CUDA_TRY(cudaFuncSetAttribute(actdist_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
-            long long want_ws = (P.n_pairs + P.tile_block - 1) / P.tile_block;
-            const int grid_ws = (int)((want_ws < c->sm_count) ? want_ws : c->sm_count);
-            actdist_ws_kernel<<<grid_ws, 32 * (kWsFill + kWsSel), smem_ws, st>>>(P, V, nbuf);
-            g_launches++;
-            CUDA_TRY(cudaGetLastError());
-            return launch_finish(P, st);
         }
     }
     P.block_counter = nullptr;
@@ -351,6 +347,72 @@ static int launch_block(const igmk_ctx* c, const ActdistParams& Pin, int threads
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return launch_finish(P, st);
+}
+
+
+// ------------------------------------------------------------- K1, list form
+// First launch: igmk_actdist_list.cuh over the whole list; second launch: the key-array
+// kernels over the pairs the first one handed back (count and order live on the device).
+static int list_prepare(igmk_ctx* c, ActdistParams& P, cudaStream_t st, int group_threads) {
+    int rc = ensure(&c->d_redo, &c->redo_bytes, 256 + (size_t)P.n_pairs * sizeof(int32_t));
+    if (rc) return rc;
+    P.redo_count = (unsigned int*)c->d_redo;
+    P.redo = (int32_t*)((char*)c->d_redo + 256);
+    P.n_pairs_dev = nullptr;
+    P.list_z = c->list_z;
+    P.list_budget = c->list_budget * (float)group_threads;
+    CUDA_TRY(cudaMemsetAsync(P.redo_count, 0, sizeof(unsigned int), st));
+    return IGMK_OK;
+}
+
+static int launch_list_warp(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
+    const int V = (c->nchunks + 31) / 32;
+    int rc = list_prepare(c, P, st, 32);
+    if (rc) return rc;
+    const size_t budget = 224 * 1024;
+    const size_t per_warp = (size_t)kRing * kStageBytes + (size_t)kListSlots * 128;
+    size_t tile_bytes = (c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)24 * c->npad : 0;
+    if (tile_bytes + 8 * per_warp > budget) tile_bytes = 0;             // keep >= 8 warps
+    int warps = (int)((budget - tile_bytes) / per_warp);
+    if (warps > kListWarps) warps = kListWarps;
+    if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
+    P.tile_block = c->tile_block > 0 ? c->tile_block : 512;
+    P.tile_slots = tile_bytes ? 1 : 0;
+    {
+        // short lists: blocks are dealt to the CTAs round-robin, so keep about eight per CTA
+        const long long per_cta = (P.n_pairs + c->sm_count - 1) / c->sm_count;
+        if (per_cta < 8LL * P.tile_block) {
+            long long b = ((per_cta + 7) / 8 + 31) / 32 * 32;
+            if (b < 32) b = 32;
+            if (b < P.tile_block) P.tile_block = (int)b;
+        }
+    }
+    const size_t smem = (size_t)warps * per_warp + tile_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(actdist_list_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long want = (P.n_pairs + P.tile_block - 1) / P.tile_block;
+    const int grid = (int)((want < c->sm_count) ? want : c->sm_count);
+    actdist_list_warp_kernel<<<grid, 32 * warps, smem, st>>>(P, V);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+static int launch_list_block(igmk_ctx* c, ActdistParams P, int threads, cudaStream_t st) {
+    if (threads > kListBlockThreads) threads = kListBlockThreads;
+    const int V = (c->nchunks + threads - 1) / threads;
+    int rc = list_prepare(c, P, st, threads);
+    if (rc) return rc;
+    const size_t smem = (size_t)(threads / 32) * kRing * kStageBytes + (size_t)kListSlots * threads * 4;
+    int per_sm = 0;
+    CUDA_TRY(cudaFuncSetAttribute(actdist_list_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_list_block_kernel, threads, smem));
+    if (per_sm < 1) return fail(IGMK_ECUDA, "actdist_list_block_kernel cannot run (shared memory %zu)", smem);
+    long long cap = (long long)c->sm_count * per_sm;
+    const int grid = (int)((P.n_pairs < cap) ? P.n_pairs : cap);
+    actdist_list_block_kernel<<<grid, threads, smem, st>>>(P, V);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
 }
 
 static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
@@ -417,8 +479,7 @@ static int order_pairs(igmk_ctx* c, int64_t n_pairs, const int32_t* d_j, cudaStr
     return IGMK_OK;
 }
 
-template <bool DAMID>
-static int dispatch_groups(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
+static int group_threads_for(const igmk_ctx* c) {
     int T = c->group_threads;
     if (T == 0) {
         if (c->nchunks <= 32 * 8) T = 32;
@@ -428,7 +489,13 @@ static int dispatch_groups(const igmk_ctx* c, const ActdistParams& P, cudaStream
             if (T > 320) T = ((c->nchunks + 319) / 320 <= 12) ? 320 : 512;
         }
     }
-    if (T == 32 && c->nchunks <= 32 * 32) return launch_warp<DAMID>(c, P, st);
+    return T;
+}
+
+template <bool DAMID>
+static int dispatch_groups(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st, bool redo = false) {
+    int T = group_threads_for(c);
+    if (T == 32 && c->nchunks <= 32 * 32) return launch_warp<DAMID>(c, P, st, redo);
     if (T < 64) T = 64;
     if (T > 512) T = 512;
     T = (T + 31) / 32 * 32;
@@ -463,6 +530,8 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     P.pexp32 = nullptr; P.plast32 = nullptr; P.damid_R = 0.0; P.zero_bead = c->nbead;
     P.tile_block = 0;
     P.tile_slots = 0;
+    P.redo = nullptr; P.redo_count = nullptr; P.n_pairs_dev = nullptr; P.list_z = 0.f; P.list_budget = 0.f;
+    c->redo_pending = false;
 
     if (algo == IGMK_ALGO_SIMPLE) return launch_simple(c, P, st);
     if (algo != IGMK_ALGO_FAST) return fail(IGMK_EINVAL, "igmk_actdist: bad algo %d", algo);
@@ -478,7 +547,34 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     //                    (T = 512 beyond nstruct = 15360)
     // IGMK_GROUP_THREADS (tuning knob): 0 = default, 32 = force one warp per pair
     // (nstruct <= 4096), otherwise the CTA size to use.
+    // List form first (igmk_actdist_list.cuh); the key-array kernels then redo what it
+    // handed back, in the order it was handed back.  Forced group sizes and IGMK_LIST=0
+    // keep the key-array kernels alone (cross-check).
+    if (c->list_form && c->group_threads == 0 && n_pairs <= 0x7fffffffLL) {
+        const int T = group_threads_for(c);
+        int rc = (T == 32) ? launch_list_warp(c, P, st) : launch_list_block(c, P, (T + 31) / 32 * 32, st);
+        if (rc) return rc;
+        ActdistParams R = P;
+        R.redo_count = (unsigned int*)c->d_redo;
+        R.redo = (int32_t*)((char*)c->d_redo + 256);
+        R.perm = R.redo;
+        R.n_pairs_dev = R.redo_count;
+        c->redo_pending = true;
+        return dispatch_groups<false>(c, R, st, true);
+    }
     return dispatch_groups<false>(c, P, st);
+}
+
+// Pairs the list form handed to the key-array kernels in the most recent launch on this
+// context (diagnostic; synchronises the device).
+extern "C" int64_t igmk_last_redo_count(igmk_ctx* c) {
+    if (!c) return -1;
+    if (!c->redo_pending || !c->d_redo) return 0;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
+    unsigned int v = 0;
+    if (cudaMemcpy(&v, c->d_redo, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    c->last_redo = v;
+    return (int64_t)v;
 }
 
 extern "C" int igmk_actdist_device(igmk_ctx* c, int64_t n_pairs,

@@ -30,14 +30,10 @@
 
 namespace igmk {
 
-#ifndef IGMK_STAGE_J
-#define IGMK_STAGE_J 0
-#endif
 constexpr int kRankCap = 32;        // bisection stops at <= kRankCap candidates
 constexpr int kWarpListCap = 64;    // candidate list words per warp group
 constexpr int kBlockListCap = 1024; // candidate list words per CTA group
 constexpr int kMaxQuads = 64;       // key quads per thread: bf16 pass counters stay exact
-constexpr bool kStageJ = IGMK_STAGE_J != 0;   // warp groups: locus-j rows staged one chunk ahead (cp.async)
 
 // ------------------------------------------------------------------ groups
 // Shared scratch is addressed through 32-bit shared-window addresses.
@@ -52,7 +48,6 @@ struct Group {
     int cap;            // list capacity
     uint32_t red;       // BLOCK: [2][3][32] words
     uint32_t list2;     // BLOCK: short list of the final <= kRankCap candidates
-    uint32_t bbuf;      // warp groups with kStageJ: this thread's slot of the locus-j staging buffer
     int parity;
 
     __device__ __forceinline__ int sum(int x) {
@@ -149,17 +144,56 @@ __device__ __forceinline__ PairPtrs pair_ptrs(const ActdistParams& P, const Pair
     return pp;
 }
 
+// Four structures (4c .. 4c+3) x the kept copy-combination values of one pair shape,
+// from the four coordinate row chunks: s[q][slot], NaN where nothing is kept.
+template <int SH, int NS>
+__device__ __forceinline__ void chunk_values(const PairDesc& d, int mode, const Row6& a0, const Row6& a1,
+                                             const Row6& b0, const Row6& b1, u64 nz, float (&s)[4][NS]) {
+    const float qnan = __int_as_float(0x7fffffff);
+    if (SH == SH_INTRA2) {
+        f2split(d2pair<0>(a0, b0, nz), s[0][0], s[1][0]);
+        f2split(d2pair<1>(a0, b0, nz), s[2][0], s[3][0]);
+        f2split(d2pair<0>(a1, b1, nz), s[0][1], s[1][1]);
+        f2split(d2pair<1>(a1, b1, nz), s[2][1], s[3][1]);
+    } else {
+        float e[4][4];   // [q][combination d0..d3]
+        f2split(d2pair<0>(a0, b0, nz), e[0][0], e[1][0]);
+        f2split(d2pair<1>(a0, b0, nz), e[2][0], e[3][0]);
+        f2split(d2pair<0>(a0, b1, nz), e[0][1], e[1][1]);
+        f2split(d2pair<1>(a0, b1, nz), e[2][1], e[3][1]);
+        f2split(d2pair<0>(a1, b0, nz), e[0][2], e[1][2]);
+        f2split(d2pair<1>(a1, b0, nz), e[2][2], e[3][2]);
+        f2split(d2pair<0>(a1, b1, nz), e[0][3], e[1][3]);
+        f2split(d2pair<1>(a1, b1, nz), e[2][3], e[3][3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (SH == SH_FULL4) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) s[q][k] = e[q][k];
+            } else if (SH == SH_GP4) {
+                const float lo1 = fminf(e[q][0], e[q][1]), hi1 = fmaxf(e[q][0], e[q][1]);
+                const float lo2 = fminf(e[q][2], e[q][3]), hi2 = fmaxf(e[q][2], e[q][3]);
+                s[q][0] = fminf(lo1, lo2);
+                s[q][1] = fminf(fmaxf(lo1, lo2), fminf(hi1, hi2));
+            } else {
+                const float e1 = (d.cmask & CM_D1) ? e[q][1] : qnan;
+                const float e2 = (d.cmask & CM_D2) ? e[q][2] : qnan;
+                const float e3 = (d.cmask & CM_D3) ? e[q][3] : qnan;
+                float t[4];
+                pack_slots(d, mode, e[q][0], e1, e2, e3, t);
+#pragma unroll
+                for (int k = 0; k < NS; ++k) s[q][k] = t[k];
+            }
+        }
+    }
+}
+
 // AS: the rows of locus i come from the CTA's shared-memory tile (as0 / as1 =
 // shared addresses of the a0 / a1 rows, same layout as in HBM).
-// BS: the rows of locus j are staged one chunk ahead through shared memory (`bbuf`: six
-// 16-byte slots of this thread, 512 bytes apart: b0 x / y / z, b1 x / y / z) with
-// asynchronous copies, so their L2 latency overlaps the arithmetic of the previous chunk
-// without costing registers.  Warp groups only (slot stride 512 bytes = 32 lanes).
-template <int SH, bool AS, bool BS, bool PIPE_REQ = false>
+template <int SH, bool AS>
 __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc& d,
                                           const PairPtrs& pp, int tid, int nthr, int V,
                                           uint32_t kscr, uint32_t kstride, uint32_t as0, uint32_t as1,
-                                          uint32_t bbuf,
                                           int& cnt, uint32_t& mn2, uint32_t& mx2) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
@@ -179,40 +213,13 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
     // in generic pairs only NH is not known at compile time
     const int nh = (NS == 4) ? ((d.keep > 2) ? 2 : 1) : 1;
     uint32_t dst = kscr;
-    // BS: the staging slots are this thread's LAST six key-quad slots, which the keys
-    // themselves only reach at the end of the fill: chunk k may be staged while
-    // nh * k <= 2 V - 6 (the keys of chunks < k occupy slots 0 .. nh k - 1); later
-    // chunks are loaded directly.  Shapes with one quad per chunk stage every chunk.
-    const int vlast = (BS && 2 * V >= 6) ? (2 * V - 6) / nh : -1;
-    if (BS && vlast >= 0) {
-        if (tid < P.nchunks) {             // chunk 0
-            cp_async_row(bbuf, pb0);
-            cp_async_row(bbuf + 1536u, pb1);
-        }
-        cp_async_commit();
-    }
 
     // The chunk loop is deliberately NOT unrolled (instruction-cache footprint and
     // register pressure: 48 registers of loaded coordinates are live here).
-    // (Software-pipelining the locus-j loads of chunk v + 1 over the arithmetic of
-    // chunk v was tried for the shared-tile path: at 96 registers it spills and
-    // loses 12 %, at 118 registers / 16 warps it only reaches parity.)
-    // PIPE (fill warps of the warp-specialised kernel, shared-tile path, the two
-    // straight-line shapes): the rows of locus j are loop-carried - the b0 row of chunk
-    // v + 1 is requested right after the last use of b0 in chunk v (half a chunk of
-    // arithmetic before the loop comes round), b1 likewise, and every distance is counted
-    // and packed as soon as it exists.  Needs the larger register budget of those warps.
-    constexpr bool PIPE = PIPE_REQ && AS && !BS && (SH == SH_FULL4 || SH == SH_INTRA2);
-    Row6 b0, b1;
-    if (PIPE && tid < P.nchunks) {
-        b0 = load_row6_stream_pinned(pb0);
-        b1 = load_row6_stream_pinned(pb1);
-    }
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
         const int c = tid + v * nthr;
         uint32_t nk[NS][2];
-        Row6 a0, a1;
         if (c >= P.nchunks) {              // padding chunk: NaN keys, nothing to load
             sts128(dst, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu, 0x7fff7fffu);
             if (NS == 4) {
@@ -221,121 +228,41 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
             dst += (uint32_t)nh * kstride;
             continue;                      // (pointers are not used again: c only grows)
         }
-        if (PIPE) {
-            const bool tail = 4 * c + 4 > P.nstruct;
-            // slot k of structures 4c .. 4c+3: count, keep the high halves, track min / max
-            auto consume = [&](int k, u64 d01, u64 d23) {
-                float v0, v1, v2, v3;
-                f2split(d01, v0, v1);
-                f2split(d23, v2, v3);
-                if (tail) {                      // tail chunk of the population (one thread)
-                    if (4 * c + 1 >= P.nstruct) v1 = qnan;
-                    if (4 * c + 2 >= P.nstruct) v2 = qnan;
-                    if (4 * c + 3 >= P.nstruct) v3 = qnan;
-                }
-                c_local = f2add(c_local, f2pack(f_le_one(v0, rc), f_le_one(v1, rc)));
-                c_local = f2add(c_local, f2pack(f_le_one(v2, rc), f_le_one(v3, rc)));
-                nk[k][0] = __byte_perm(__float_as_uint(v0), __float_as_uint(v1), 0x7632);
-                nk[k][1] = __byte_perm(__float_as_uint(v2), __float_as_uint(v3), 0x7632);
-                lmn = bf2_min(lmn, bf2_min(nk[k][0], nk[k][1]));
-                lmx = bf2_max(lmx, bf2_max(nk[k][0], nk[k][1]));
-            };
-            // a lane without a next chunk re-reads its own rows (no branch around the loads)
-            const size_t nxt = (c + nthr < P.nchunks) ? vstride : (size_t)0;
-            a0 = load_row6_shared(sa0);
-            a1 = load_row6_shared(sa1);
-            if (SH == SH_INTRA2) {
-                consume(0, d2pair<0>(a0, b0, nz), d2pair<1>(a0, b0, nz));
-                b0 = load_row6_stream_pinned(pb0 + nxt);
-                consume(1, d2pair<0>(a1, b1, nz), d2pair<1>(a1, b1, nz));
-                b1 = load_row6_stream_pinned(pb1 + nxt);
-            } else {
-                consume(0, d2pair<0>(a0, b0, nz), d2pair<1>(a0, b0, nz));
-                consume(NS == 4 ? 2 : 0, d2pair<0>(a1, b0, nz), d2pair<1>(a1, b0, nz));
-                b0 = load_row6_stream_pinned(pb0 + nxt);
-                consume(1, d2pair<0>(a0, b1, nz), d2pair<1>(a0, b1, nz));
-                consume(NS == 4 ? 3 : 1, d2pair<0>(a1, b1, nz), d2pair<1>(a1, b1, nz));
-                b1 = load_row6_stream_pinned(pb1 + nxt);
-            }
-        } else {
-            float s[4][NS];   // [q][slot]
-            if (BS && v <= vlast) {            // uniform
-                cp_async_wait_all();           // this thread's own copies of chunk v have landed
-                b0 = load_row6_shared(bbuf); b1 = load_row6_shared(bbuf + 1536u);
-                if (v < vlast && c + nthr < P.nchunks) {   // chunk v + 1 -> the same slots (read above, program order)
-                    cp_async_row(bbuf, pb0 + vstride);
-                    cp_async_row(bbuf + 1536u, pb1 + vstride);
-                }
-                cp_async_commit();
-            } else {
-                b0 = load_row6<LD_STREAM>(pb0); b1 = load_row6<LD_STREAM>(pb1);
-            }
+        float s[4][NS];   // [q][slot]
+        {
+            Row6 a0, a1;
+            const Row6 b0 = load_row6<LD_STREAM>(pb0), b1 = load_row6<LD_STREAM>(pb1);
             if (AS) {
                 a0 = load_row6_shared(sa0); a1 = load_row6_shared(sa1);
             } else {
                 a0 = load_row6<LD_KEEP>(pa0); a1 = load_row6<LD_KEEP>(pa1);
             }
-            if (SH == SH_INTRA2) {
-                f2split(d2pair<0>(a0, b0, nz), s[0][0], s[1][0]);
-                f2split(d2pair<1>(a0, b0, nz), s[2][0], s[3][0]);
-                f2split(d2pair<0>(a1, b1, nz), s[0][1], s[1][1]);
-                f2split(d2pair<1>(a1, b1, nz), s[2][1], s[3][1]);
-            } else {
-                float e[4][4];   // [q][combination d0..d3]
-                f2split(d2pair<0>(a0, b0, nz), e[0][0], e[1][0]);
-                f2split(d2pair<1>(a0, b0, nz), e[2][0], e[3][0]);
-                f2split(d2pair<0>(a0, b1, nz), e[0][1], e[1][1]);
-                f2split(d2pair<1>(a0, b1, nz), e[2][1], e[3][1]);
-                f2split(d2pair<0>(a1, b0, nz), e[0][2], e[1][2]);
-                f2split(d2pair<1>(a1, b0, nz), e[2][2], e[3][2]);
-                f2split(d2pair<0>(a1, b1, nz), e[0][3], e[1][3]);
-                f2split(d2pair<1>(a1, b1, nz), e[2][3], e[3][3]);
+            chunk_values<SH, NS>(d, P.mode, a0, a1, b0, b1, nz, s);
+        }
+        if (4 * c + 4 > P.nstruct) {        // tail chunk of the population (one thread)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (SH == SH_FULL4) {
+            for (int q = 1; q < 4; ++q)
+                if (4 * c + q >= P.nstruct) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) s[q][k] = e[q][k];
-                    } else if (SH == SH_GP4) {
-                        const float lo1 = fminf(e[q][0], e[q][1]), hi1 = fmaxf(e[q][0], e[q][1]);
-                        const float lo2 = fminf(e[q][2], e[q][3]), hi2 = fmaxf(e[q][2], e[q][3]);
-                        s[q][0] = fminf(lo1, lo2);
-                        s[q][1] = fminf(fmaxf(lo1, lo2), fminf(hi1, hi2));
-                    } else {
-                        const float e1 = (d.cmask & CM_D1) ? e[q][1] : qnan;
-                        const float e2 = (d.cmask & CM_D2) ? e[q][2] : qnan;
-                        const float e3 = (d.cmask & CM_D3) ? e[q][3] : qnan;
-                        float t[4];
-                        pack_slots(d, P.mode, e[q][0], e1, e2, e3, t);
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) s[q][k] = t[k];
-                    }
+                    for (int k = 0; k < NS; ++k) s[q][k] = qnan;
                 }
+        }
+        // contact count: 1.0 / 0.0 flags accumulated two per FADD2 (exact: < 2^24)
+#pragma unroll
+        for (int q = 0; q < 4; q += 2)
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                c_local = f2add(c_local, f2pack(f_le_one(s[q][k], rc), f_le_one(s[q + 1][k], rc)));
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+#pragma unroll
+            for (int qh = 0; qh < 2; ++qh) {
+                // {hi16(s[2qh]), hi16(s[2qh+1])}: bytes 2,3 of each -> one PRMT
+                nk[k][qh] = __byte_perm(__float_as_uint(s[2 * qh][k]),
+                                        __float_as_uint(s[2 * qh + 1][k]), 0x7632);
             }
-            if (4 * c + 4 > P.nstruct) {        // tail chunk of the population (one thread)
-#pragma unroll
-                for (int q = 1; q < 4; ++q)
-                    if (4 * c + q >= P.nstruct) {
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) s[q][k] = qnan;
-                    }
-            }
-            // contact count: 1.0 / 0.0 flags accumulated two per FADD2 (exact: < 2^24)
-#pragma unroll
-            for (int q = 0; q < 4; q += 2)
-#pragma unroll
-                for (int k = 0; k < NS; ++k)
-                    c_local = f2add(c_local, f2pack(f_le_one(s[q][k], rc), f_le_one(s[q + 1][k], rc)));
-#pragma unroll
-            for (int k = 0; k < NS; ++k) {
-#pragma unroll
-                for (int qh = 0; qh < 2; ++qh) {
-                    // {hi16(s[2qh]), hi16(s[2qh+1])}: bytes 2,3 of each -> one PRMT
-                    nk[k][qh] = __byte_perm(__float_as_uint(s[2 * qh][k]),
-                                            __float_as_uint(s[2 * qh + 1][k]), 0x7632);
-                }
-                lmn = bf2_min(lmn, bf2_min(nk[k][0], nk[k][1]));   // NaN halves are ignored
-                lmx = bf2_max(lmx, bf2_max(nk[k][0], nk[k][1]));
-            }
+            lmn = bf2_min(lmn, bf2_min(nk[k][0], nk[k][1]));   // NaN halves are ignored
+            lmx = bf2_max(lmx, bf2_max(nk[k][0], nk[k][1]));
         }
         sts128(dst, nk[0][0], nk[0][1], nk[1][0], nk[1][1]);
         if (NS == 4) {
@@ -774,18 +701,18 @@ __device__ __forceinline__ void process_pair(const ActdistParams& P, Group<BLOCK
         const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
         const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
         switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  fill_keys<SH_FULL4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-            case SH_INTRA2: fill_keys<SH_INTRA2, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-            case SH_GP4:    fill_keys<SH_GP4, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
-            default:        fill_keys<SH_GENERIC, true, kStageJ && !BLOCK>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, g.bbuf, cnt, mn2, mx2); break;
+            case SH_FULL4:  fill_keys<SH_FULL4, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, true>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, as0, as1, cnt, mn2, mx2); break;
         }
         tile_release(tile, tslot, g.tid);
     } else {
         switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  fill_keys<SH_FULL4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-            case SH_INTRA2: fill_keys<SH_INTRA2, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-            case SH_GP4:    fill_keys<SH_GP4, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
-            default:        fill_keys<SH_GENERIC, false, kStageJ && !BLOCK && !DAMID>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, g.bbuf, cnt, mn2, mx2); break;
+            case SH_FULL4:  fill_keys<SH_FULL4, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            case SH_INTRA2: fill_keys<SH_INTRA2, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            case SH_GP4:    fill_keys<SH_GP4, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
+            default:        fill_keys<SH_GENERIC, false>(P, d, pp, g.tid, g.nthr, V, g.kscr, g.kstride, 0u, 0u, cnt, mn2, mx2); break;
         }
     }
     uint32_t kmin = min(mn2 & 0xffffu, mn2 >> 16);
@@ -821,6 +748,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     __shared__ unsigned long long s_gblock[8];
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;           // <= kWarpsPerBlock (fewer when V is large)
+    const long long n_pairs = P.n_pairs_dev ? (long long)__ldg(P.n_pairs_dev) : P.n_pairs;   // redo launch: count on the device
     Group<false> g;
     g.tid = threadIdx.x & 31;
     g.nthr = 32;
@@ -831,9 +759,6 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     g.kstride = 32u * 16u;
     g.red = 0u;
     g.list2 = 0u;
-    g.bbuf = 0u;
-    if (kStageJ && !DAMID && 2 * V >= 6)          // the thread's last six key-quad slots
-        g.bbuf = g.kscr + (uint32_t)(2 * V - 6) * 512u;
     g.parity = 0;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = smem_addr(s_slot); tile.nslots = P.tile_slots;
@@ -880,9 +805,9 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
                 }
                 gb = __shfl_sync(0xffffffffu, gb, 0);
                 const long long base = (long long)gb * B;
-                if (base >= P.n_pairs) break;
+                if (base >= n_pairs) break;
                 const long long pair = base + r;
-                if (pair < P.n_pairs) process_pair<false, DAMID>(P, g, V, pair, tile);
+                if (pair < n_pairs) process_pair<false, DAMID>(P, g, V, pair, tile);
                 __syncwarp();
             }
             return;
@@ -893,184 +818,18 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
             t = __shfl_sync(0xffffffffu, t, 0);
             const unsigned int k = t / B, r = t - k * B;
             const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
-            if (base >= P.n_pairs) break;
+            if (base >= n_pairs) break;
             const long long pair = base + r;
-            if (pair < P.n_pairs) process_pair<false, DAMID>(P, g, V, pair, tile);
+            if (pair < n_pairs) process_pair<false, DAMID>(P, g, V, pair, tile);
             __syncwarp();
         }
         return;
     }
     const long long stride = (long long)gridDim.x * nwarps;
-    for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < P.n_pairs;
+    for (long long pair = (long long)blockIdx.x * nwarps + warp; pair < n_pairs;
          pair += stride) {
         process_pair<false, DAMID>(P, g, V, pair, tile);
         __syncwarp();
-    }
-}
-
-// ------------------------------------------------- warp-specialised variant (experimental)
-// Same per-pair algorithm, but the two halves of a pair run on different warps: kWsFill
-// "fill" warps (register budget raised with setmaxnreg) stream coordinates and park keys
-// in a ring of shared-memory key arrays; kWsSel "select" warps (budget lowered) take the
-// arrays in the same order, bisect, rank and emit.  Hand-over: one state word per array,
-// 2 g = free for generation g, 2 g + 1 = filled; tickets from two shared counters keep both
-// sides in list order, so the ring can never dead-lock; every wait is bounded and traps.
-#ifndef IGMK_WS_FILL
-#define IGMK_WS_FILL 8
-#endif
-#ifndef IGMK_WS_SEL
-#define IGMK_WS_SEL 12
-#endif
-#ifndef IGMK_WS_FILL_REGS
-#define IGMK_WS_FILL_REGS 144
-#endif
-#ifndef IGMK_WS_SEL_REGS
-#define IGMK_WS_SEL_REGS 64
-#endif
-#ifndef IGMK_WS_PIPE
-#define IGMK_WS_PIPE 0
-#endif
-#ifndef IGMK_WS_SLEEP
-#define IGMK_WS_SLEEP 200
-#endif
-constexpr int kWsFill = IGMK_WS_FILL;          // multiples of 4 (setmaxnreg is warpgroup-wide)
-constexpr int kWsSel = IGMK_WS_SEL;
-constexpr int kWsFillRegs = IGMK_WS_FILL_REGS; // 32 (kWsFill Rf + kWsSel Rs) <= threads x launch registers
-constexpr int kWsSelRegs = IGMK_WS_SEL_REGS;
-constexpr bool kWsPipe = IGMK_WS_PIPE != 0;
-struct WsMeta { long long pair; int cnt; uint32_t kmin, kmax; int pad; };
-
-__device__ __forceinline__ void ws_wait(uint32_t addr, uint32_t want, int lane) {
-    if (lane == 0) {
-        int spins = 0;
-        while (lds32_volatile(addr) != want) {
-            __nanosleep(IGMK_WS_SLEEP);
-            if (++spins > (1 << 24)) __trap();          // never hang the GPU on a protocol error
-        }
-    }
-    __syncwarp();
-    __threadfence_block();
-}
-
-__global__ void __launch_bounds__(32 * (kWsFill + kWsSel), 1)
-actdist_ws_kernel(const ActdistParams P, const int V, const int nbuf) {
-    extern __shared__ uint4 s_keys[];             // [nbuf][2 V][32] key quads, then the locus-i tile
-    __shared__ uint32_t s_list[kWsSel][kWarpListCap];
-    __shared__ uint32_t s_cnt[kWsSel];
-    __shared__ WsMeta s_meta[32];
-    __shared__ uint32_t s_state[32];
-    __shared__ uint32_t s_slot[2];
-    __shared__ unsigned int s_ticket[2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x < 32) s_state[threadIdx.x] = 0u;
-    if (threadIdx.x == 0) {
-        s_slot[0] = (0xfffffu << 12) | (TS_EMPTY << 10);
-        s_slot[1] = (0xfffffu << 12) | (TS_EMPTY << 10);
-        s_ticket[0] = 0u; s_ticket[1] = 0u;
-    }
-    __syncthreads();
-    const unsigned int B = (unsigned int)P.tile_block;
-    const uint32_t keys0 = smem_addr(s_keys);
-    const uint32_t buf_bytes = 2u * (uint32_t)V * 512u;
-    Group<false> g;
-    g.tid = lane; g.nthr = 32; g.kstride = 512u; g.red = 0u; g.list2 = 0u; g.bbuf = 0u; g.parity = 0;
-    g.cap = kWarpListCap;
-    if (warp < kWsFill) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kWsFillRegs));
-        TileCtl tile;
-        tile.base = keys0 + (uint32_t)nbuf * buf_bytes;
-        tile.slot_bytes = 24u * (uint32_t)P.npad;
-        tile.words = smem_addr(s_slot);
-        tile.nslots = 1;
-        g.list = 0u; g.ctl = 0u;
-        for (;;) {
-            unsigned int t = 0u;
-            if (lane == 0) t = atomicAdd(&s_ticket[0], 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            const unsigned int k = t / B, r = t - k * B;
-            const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
-            if (base >= P.n_pairs) break;
-            if (base + r >= P.n_pairs) continue;            // trailing tickets of the last block
-            const int b = (int)(t % (unsigned int)nbuf);
-            const uint32_t gen = t / (unsigned int)nbuf;
-            ws_wait(smem_addr(&s_state[b]), 2u * gen, lane);
-            g.kscr = keys0 + (uint32_t)b * buf_bytes + (uint32_t)lane * 16u;
-            // ---- first half of process_pair
-            const long long slot = base + r;
-            const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-            const int i = __ldg(P.pi + pair);
-            const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
-            int cnt = -1;
-            uint32_t kmin = 0u, kmax = 0u;
-            if (d.valid) {
-                const PairPtrs pp = pair_ptrs(P, d);
-                uint32_t mn2, mx2;
-                const int tslot = tile_acquire(P, tile, i, d, pp, lane);
-                if (tslot >= 0) {
-                    const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
-                    const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
-                    switch (pair_shape(d, P.mode)) {
-                        case SH_FULL4:  fill_keys<SH_FULL4, true, false, kWsPipe>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
-                        case SH_INTRA2: fill_keys<SH_INTRA2, true, false, kWsPipe>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
-                        case SH_GP4:    fill_keys<SH_GP4, true, false>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
-                        default:        fill_keys<SH_GENERIC, true, false>(P, d, pp, lane, 32, V, g.kscr, 512u, as0, as1, 0u, cnt, mn2, mx2); break;
-                    }
-                    tile_release(tile, tslot, lane);
-                } else {
-                    switch (pair_shape(d, P.mode)) {
-                        case SH_FULL4:  fill_keys<SH_FULL4, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
-                        case SH_INTRA2: fill_keys<SH_INTRA2, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
-                        case SH_GP4:    fill_keys<SH_GP4, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
-                        default:        fill_keys<SH_GENERIC, false, false>(P, d, pp, lane, 32, V, g.kscr, 512u, 0u, 0u, 0u, cnt, mn2, mx2); break;
-                    }
-                }
-                kmin = min(mn2 & 0xffffu, mn2 >> 16);
-                uint32_t mxl = mx2 & 0xffffu, mxh = mx2 >> 16;
-                mxl = (mxl > 0x7f80u) ? 0u : mxl;
-                mxh = (mxh > 0x7f80u) ? 0u : mxh;
-                kmax = max(mxl, mxh);
-                g.sum_min_max(cnt, kmin, kmax);
-            }
-            if (lane == 0) {
-                s_meta[b].pair = pair; s_meta[b].cnt = cnt; s_meta[b].kmin = kmin; s_meta[b].kmax = kmax;
-            }
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) sts32(smem_addr(&s_state[b]), 2u * gen + 1u);
-        }
-    } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kWsSelRegs));
-        const int sw = warp - kWsFill;
-        g.list = smem_addr(&s_list[sw][0]);
-        g.ctl = smem_addr(&s_cnt[sw]);
-        for (;;) {
-            unsigned int t = 0u;
-            if (lane == 0) t = atomicAdd(&s_ticket[1], 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            const unsigned int k = t / B, r = t - k * B;
-            const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
-            if (base >= P.n_pairs) break;
-            if (base + r >= P.n_pairs) continue;
-            const int b = (int)(t % (unsigned int)nbuf);
-            const uint32_t gen = t / (unsigned int)nbuf;
-            ws_wait(smem_addr(&s_state[b]), 2u * gen + 1u, lane);
-            const long long pair = s_meta[b].pair;
-            const int cnt = s_meta[b].cnt;
-            const uint32_t kmin = s_meta[b].kmin, kmax = s_meta[b].kmax;
-            if (cnt < 0) {
-                emit_empty(P, lane, pair);
-            } else {
-                const int i = __ldg(P.pi + pair);
-                const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
-                const PairPtrs pp = pair_ptrs(P, d);
-                g.kscr = keys0 + (uint32_t)b * buf_bytes + (uint32_t)lane * 16u;
-                if (lane == 0) sts32(g.ctl, 0u);
-                __syncwarp();
-                select_part<false, false>(P, g, V, pair, d, pp, 0.0, cnt, kmin, kmax);
-            }
-            __syncwarp();
-            if (lane == 0) sts32(smem_addr(&s_state[b]), 2u * (gen + 1u));
-        }
     }
 }
 
@@ -1095,8 +854,8 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     g.kstride = (uint32_t)blockDim.x * 16u;
     g.red = smem_addr(s_red);
     g.list2 = smem_addr(s_list2);
-    g.bbuf = 0u;
     g.parity = 0;
+    const long long n_pairs = P.n_pairs_dev ? (long long)__ldg(P.n_pairs_dev) : P.n_pairs;
     TileCtl tile;
     tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;
     if (P.block_counter) {
@@ -1107,13 +866,13 @@ actdist_block_kernel(const ActdistParams P, const int V) {
             if (threadIdx.x == 0) s_next = atomicAdd(P.block_counter, 1u);
             __syncthreads();
             const long long pair = (long long)s_next;
-            if (pair >= P.n_pairs) break;
+            if (pair >= n_pairs) break;
             process_pair<true, DAMID>(P, g, V, pair, tile);
             __syncthreads();
         }
         return;
     }
-    for (long long pair = blockIdx.x; pair < P.n_pairs; pair += gridDim.x) {
+    for (long long pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         process_pair<true, DAMID>(P, g, V, pair, tile);
         __syncthreads();
     }

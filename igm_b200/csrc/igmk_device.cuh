@@ -67,6 +67,13 @@ struct ActdistParams {
     unsigned int* block_counter;  // warp kernel: device-wide counter handing out pair blocks (NULL: static round-robin)
     int   block_stop;         // CTA groups: the key bisection stops at <= block_stop candidates (<= kBlockListCap)
     u64   negzero2;           // {-0.0f, -0.0f}: opaque addend of the packed squares (igmk_actdist.cuh)
+    // list form (igmk_actdist_list.cuh): pairs it cannot answer are appended to `redo`; the key-array
+    // kernels then take their pair count from the device (n_pairs_dev) and `redo` as processing order
+    int32_t* redo;
+    unsigned int* redo_count;
+    const unsigned int* n_pairs_dev;
+    float list_z;             // safety margin of the sample threshold, in standard deviations
+    float list_budget;        // expected list length beyond which a pair goes to the key-array kernel
 };
 
 // Combination shapes of one pair (which of the four copy combinations
@@ -429,33 +436,12 @@ __device__ __forceinline__ Row6 load_row6_shared(uint32_t addr) {   // same layo
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2+1024];" : "=l"(r.z01), "=l"(r.z23) : "r"(addr) : "memory");
     return r;
 }
-// Asynchronous 16-byte copies global -> shared (LDGSTS, L2 only): the rows of locus j of
-// the NEXT chunk travel while the current chunk is being computed.
-__device__ __forceinline__ void cp_async16(uint32_t dst, const float* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_row(uint32_t dst, const float* p) {     // x / y / z of one row chunk
-    cp_async16(dst, p);
-    cp_async16(dst + 512u, p + kSeg);
-    cp_async16(dst + 1024u, p + 2 * kSeg);
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 template <int HINT>
 __device__ __forceinline__ Row6 load_row6(const float* p) {
     Row6 r;
     ldg_v2b64<HINT>(p, r.x01, r.x23);
     ldg_v2b64<HINT>(p + kSeg, r.y01, r.y23);
     ldg_v2b64<HINT>(p + 2 * kSeg, r.z01, r.z23);
-    return r;
-}
-// Same loads pinned in program order (software-pipelined fill of the warp-specialised
-// kernel: issued half a chunk before their first use, which lies in the NEXT iteration).
-__device__ __forceinline__ Row6 load_row6_stream_pinned(const float* p) {
-    Row6 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.x01), "=l"(r.x23) : "l"(p));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.y01), "=l"(r.y23) : "l"(p + kSeg));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(r.z01), "=l"(r.z23) : "l"(p + 2 * kSeg));
     return r;
 }
 // d2 of structures (4c+2h, 4c+2h+1), h = 0 / 1

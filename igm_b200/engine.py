@@ -194,6 +194,11 @@ class ActdistEngine:
                                                   int(it_corr), _MODES[mode], ptr(d_peer_slices),
                                                   int(n_peers), stream or None))
 
+    def last_redo_count(self) -> int:
+        """Pairs of the most recent A-step launch that the list-form kernel handed back
+        to the key-array kernels (diagnostic; synchronises the device)."""
+        return int(self._lib.igmk_last_redo_count(self._ctx))
+
     def finish_results(self, d_results, n: int, stream: int = 0) -> None:
         check(self._lib.igmk_finish_results_device(self._ctx, ptr(d_results), int(n), stream or None))
 

@@ -103,6 +103,11 @@ int igmk_actdist_host(igmk_ctx* ctx, int64_t n_pairs,
                       float contact_range, int it_corr, int mode, int algo,
                       igmk_pair_result* out);
 
+/* Diagnostic: how many pairs of the most recent igmk_actdist_* launch on this context the
+ * list-form kernel handed back to the key-array kernels (large order index, many contacts,
+ * or a population sample that misjudged the pair).  Synchronises the device. */
+int64_t igmk_last_redo_count(igmk_ctx* ctx);
+
 /* Multi-GPU form (one process per GPU, pairs sharded, coordinates replicated;
  * the reference farms 1000-pair batches to CPU workers and meets again on the
  * shared filesystem, igm/steps/ActivationDistanceStep.py:181-194,

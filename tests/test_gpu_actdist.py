@@ -208,35 +208,123 @@ def test_block_groups_many_equal_distances(nconf, monkeypatch):
                 _check_against_details(res, dets)
 
 
-def test_warp_specialised_variant_matches(monkeypatch):
-    """IGMK_WS=1: the experimental kernel that runs the fill and select halves of a pair on
-    different warps (setmaxnreg, ring of key arrays) gives byte-identical results."""
-    from igm_b200 import synthetic
-    pop = synthetic.make_population(2_000_000, 700, seed=41, genome_scale=0.05)
-    rng = np.random.default_rng(8)
-    nh = pop.n_hap
-    ii = rng.integers(0, nh, 70000)
-    jj = rng.integers(0, nh, 70000)
+def _sorted_pairs(rng, nh, n):
+    ii = rng.integers(0, nh, n)
+    jj = rng.integers(0, nh, n)
     k = ii < jj
     ii, jj = ii[k].astype(np.int32), jj[k].astype(np.int32)
     order = np.lexsort((jj, ii))
-    ii, jj = ii[order], jj[order]
+    return ii[order], jj[order]
+
+
+def test_dynamic_blocks_variant_matches(monkeypatch):
+    """Key-array kernels alone (IGMK_LIST=0): pair blocks handed out by a device-wide counter
+    instead of round-robin give byte-identical results."""
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, 700, seed=41, genome_scale=0.05)
+    rng = np.random.default_rng(8)
+    ii, jj = _sorted_pairs(rng, pop.n_hap, 70000)
     pw = rng.uniform(0.001, 1.0, len(ii))
+    monkeypatch.setenv("IGMK_LIST", "0")
     with _engine(pop) as eng:
         base = eng.actdist(ii, jj, pw, None, 2.0, 1, "lb", 0)
-        base_gp = eng.actdist(ii, jj, pw, None, 2.0, 0, "gp", 0)
-    monkeypatch.setenv("IGMK_WS", "1")
-    with _engine(pop) as eng:
-        ws = eng.actdist(ii, jj, pw, None, 2.0, 1, "lb", 0)
-        ws_gp = eng.actdist(ii, jj, pw, None, 2.0, 0, "gp", 0)
-    assert ws.tobytes() == base.tobytes()
-    assert ws_gp.tobytes() == base_gp.tobytes()
-    # pair blocks handed out by a device-wide counter instead of round-robin
-    monkeypatch.delenv("IGMK_WS")
     monkeypatch.setenv("IGMK_DYNAMIC_BLOCKS", "1")
     with _engine(pop) as eng:
         dyn = eng.actdist(ii, jj, pw, None, 2.0, 1, "lb", 0)
     assert dyn.tobytes() == base.tobytes()
+
+
+@pytest.mark.parametrize("nstruct", [100, 130, 700, 1000, 1024])
+def test_list_form_matches_key_arrays_warp(nstruct, monkeypatch):
+    """Small target probabilities (the sigma = 0.01 regime): the list-form kernel answers
+    most pairs itself; results are byte-identical to the key-array kernels and the oracle."""
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, nstruct, seed=300 + nstruct, genome_scale=0.05)
+    rng = np.random.default_rng(nstruct)
+    ii, jj = _sorted_pairs(rng, pop.n_hap, 40000)
+    pw = np.exp(rng.uniform(np.log(0.004), np.log(0.08), len(ii))).astype(np.float32).astype(np.float64)
+    pw[::97] = rng.uniform(0.2, 1.0, len(pw[::97]))          # a few heavy pairs in between
+    pl = np.where(rng.random(len(ii)) < 0.5, 0.0,
+                  orc.text_roundtrip(rng.uniform(0, 0.05, len(ii))).astype(np.float64))
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("IGMK_LIST", flag)
+        with _engine(pop) as eng:
+            for mode in ("lb", "gp"):
+                for it_corr in (0, 1):
+                    out[flag, mode, it_corr] = eng.actdist(ii, jj, pw, pl, 2.0, it_corr, mode, 0)
+                    if flag == "1":
+                        redo = eng.last_redo_count()
+                        assert 0 <= redo < 0.5 * len(ii), (mode, it_corr, redo)   # the fast path is really used
+    for mode in ("lb", "gp"):
+        for it_corr in (0, 1):
+            assert out["1", mode, it_corr].tobytes() == out["0", mode, it_corr].tobytes(), (mode, it_corr)
+    sel = np.sort(rng.choice(len(ii), 400, replace=False))
+    for mode in ("lb", "gp"):
+        _, dets = orc.run_pairs(ii[sel], jj[sel], pw[sel], pl[sel], pop.coordinates, pop.radii, pop.chrom_hap(),
+                                pop.copy_index, 1, 2.0, MODES[mode])
+        _check_against_details(out["1", mode, 1][sel], dets)
+
+
+@pytest.mark.parametrize("nstruct", [1500, 4100, 10000])
+def test_list_form_matches_key_arrays_block(nstruct, monkeypatch):
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, nstruct, seed=17 + nstruct, genome_scale=0.01)
+    rng = np.random.default_rng(nstruct)
+    ii, jj = _sorted_pairs(rng, pop.n_hap, 3000)
+    pw = np.exp(rng.uniform(np.log(0.004), np.log(0.08), len(ii))).astype(np.float32).astype(np.float64)
+    pw[::53] = rng.uniform(0.2, 1.0, len(pw[::53]))
+    pl = np.zeros(len(ii))
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("IGMK_LIST", flag)
+        with _engine(pop) as eng:
+            for mode in ("lb", "gp"):
+                out[flag, mode] = eng.actdist(ii, jj, pw, pl, 2.0, 1, mode, 0)
+                if flag == "1":
+                    assert 0 <= eng.last_redo_count() < 0.5 * len(ii)
+    for mode in ("lb", "gp"):
+        assert out["1", mode].tobytes() == out["0", mode].tobytes(), mode
+    sel = np.sort(rng.choice(len(ii), 60, replace=False))
+    _, dets = orc.run_pairs(ii[sel], jj[sel], pw[sel], pl[sel], pop.coordinates, pop.radii, pop.chrom_hap(),
+                            pop.copy_index, 1, 2.0, MODES["lb"])
+    _check_against_details(out["1", "lb"][sel], dets)
+
+
+@pytest.mark.parametrize("kind", ["near_first", "far_first", "grid"])
+def test_list_form_unrepresentative_sample(kind, monkeypatch):
+    """The list form takes its threshold from the first 128 structures.  Populations whose
+    first structures are NOT representative (all compact / all extended) make it misjudge
+    the threshold - too few values kept, or thread lists overflowing - and coordinates on a
+    coarse grid give thousands of tied distances.  The answers must not change."""
+    from igm_b200 import synthetic
+    from igm_b200.population import Population
+    nstruct = 900
+    pop0 = synthetic.make_population(2_000_000, nstruct, seed=77, genome_scale=0.03)
+    crd = pop0.coordinates.copy()
+    if kind == "grid":
+        crd = (np.round(crd / 400.0) * 400.0).astype(np.float32)
+    else:
+        scale = np.ones(nstruct, np.float32)
+        scale[:128] = 0.05 if kind == "near_first" else 1.0
+        scale[128:] = 1.0 if kind == "near_first" else 0.05
+        crd = crd * scale[None, :, None]
+    pop = Population(crd, pop0.radii, pop0.chrom, pop0.copy_index, pop0.copy)
+    rng = np.random.default_rng(5)
+    ii, jj = _sorted_pairs(rng, pop.n_hap, 6000)
+    pw = np.exp(rng.uniform(np.log(0.004), np.log(0.3), len(ii))).astype(np.float32).astype(np.float64)
+    pl = np.zeros(len(ii))
+    with _engine(pop) as eng:
+        res = {m: eng.actdist(ii, jj, pw, pl, 2.0, 1, m, 0) for m in ("lb", "gp")}
+    monkeypatch.setenv("IGMK_LIST", "0")
+    with _engine(pop) as eng:
+        for m in ("lb", "gp"):
+            assert eng.actdist(ii, jj, pw, pl, 2.0, 1, m, 0).tobytes() == res[m].tobytes(), m
+    sel = np.sort(rng.choice(len(ii), 300, replace=False))
+    for m in ("lb", "gp"):
+        _, dets = orc.run_pairs(ii[sel], jj[sel], pw[sel], pl[sel], pop.coordinates, pop.radii, pop.chrom_hap(),
+                                pop.copy_index, 1, 2.0, MODES[m])
+        _check_against_details(res[m][sel], dets)
 
 
 def test_degenerate_inputs():
