@@ -82,6 +82,7 @@ struct igmk_ctx {
                                  // residency: config 5 +4 %; config 2 -1 %)
     int list_form = 1;           // IGMK_LIST: 1 = list form first, key-array kernels for what it hands back; 0 = key arrays only
     float list_z = 2.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
+    int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
     float list_budget = 12.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
     void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
     unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
@@ -162,6 +163,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov) c->list_form = atoi(ov);
     ov = getenv("IGMK_LIST_Z");
     if (ov) c->list_z = (float)atof(ov);
+    ov = getenv("IGMK_LIST_TILE_SLOTS");
+    if (ov) c->list_tile_slots = atoi(ov);
     ov = getenv("IGMK_LIST_BUDGET");
     if (ov) c->list_budget = (float)atof(ov);
     ov = getenv("IGMK_BLOCK_STOP");
@@ -369,27 +372,25 @@ static int launch_list_warp(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     const int V = (c->nchunks + 31) / 32;
     int rc = list_prepare(c, P, st, 32);
     if (rc) return rc;
-    const size_t budget = 224 * 1024;
-    const size_t per_warp = (size_t)kRing * kStageBytes + (size_t)kListSlots * 128;
-    size_t tile_bytes = (c->tile_block > 0 && c->n_hap < (1 << 20)) ? (size_t)24 * c->npad : 0;
-    if (tile_bytes + 8 * per_warp > budget) tile_bytes = 0;             // keep >= 8 warps
-    int warps = (int)((budget - tile_bytes) / per_warp);
-    if (warps > kListWarps) warps = kListWarps;
+    const size_t budget = 220 * 1024;
+    int warps = kListWarps;
     if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
-    P.tile_block = c->tile_block > 0 ? c->tile_block : 512;
-    P.tile_slots = tile_bytes ? 1 : 0;
-    {
-        // short lists: blocks are dealt to the CTAs round-robin, so keep about eight per CTA
-        const long long per_cta = (P.n_pairs + c->sm_count - 1) / c->sm_count;
-        if (per_cta < 8LL * P.tile_block) {
-            long long b = ((per_cta + 7) / 8 + 31) / 32 * 32;
-            if (b < 32) b = 32;
-            if (b < P.tile_block) P.tile_block = (int)b;
-        }
-    }
-    const size_t smem = (size_t)warps * per_warp + tile_bytes;
+    const size_t list_bytes = (size_t)warps * 32 * kListBytes;
+    const size_t one_tile = (size_t)24 * c->npad;
+    int slots = (c->tile_block > 0 && c->n_hap < (1 << 20)) ? c->list_tile_slots : 0;
+    if (slots > 2) slots = 2;
+    while (slots > 0 && list_bytes + slots * one_tile > budget) --slots;
+    P.tile_slots = slots;
+    // CTA-contiguous blocks of 2^shift pairs; short lists: blocks are dealt to the CTAs
+    // round-robin, so keep about eight per CTA
+    int shift = 9;
+    if (c->tile_block > 0) { shift = 0; while ((2 << shift) <= c->tile_block) ++shift; }
+    const long long per_cta = (P.n_pairs + c->sm_count - 1) / c->sm_count;
+    while (shift > 5 && per_cta < (8LL << shift)) --shift;
+    P.tile_block = shift;
+    const size_t smem = list_bytes + (size_t)slots * one_tile;
     CUDA_TRY(cudaFuncSetAttribute(actdist_list_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long want = (P.n_pairs + P.tile_block - 1) / P.tile_block;
+    const long long want = (P.n_pairs + (1LL << shift) - 1) >> shift;
     const int grid = (int)((want < c->sm_count) ? want : c->sm_count);
     actdist_list_warp_kernel<<<grid, 32 * warps, smem, st>>>(P, V);
     g_launches++;
@@ -402,7 +403,7 @@ static int launch_list_block(igmk_ctx* c, ActdistParams P, int threads, cudaStre
     const int V = (c->nchunks + threads - 1) / threads;
     int rc = list_prepare(c, P, st, threads);
     if (rc) return rc;
-    const size_t smem = (size_t)(threads / 32) * kRing * kStageBytes + (size_t)kListSlots * threads * 4;
+    const size_t smem = (size_t)threads * kListBytes;
     int per_sm = 0;
     CUDA_TRY(cudaFuncSetAttribute(actdist_list_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actdist_list_block_kernel, threads, smem));

@@ -231,7 +231,7 @@ __device__ __forceinline__ void fill_keys(const ActdistParams& P, const PairDesc
         float s[4][NS];   // [q][slot]
         {
             Row6 a0, a1;
-            const Row6 b0 = load_row6<LD_STREAM>(pb0), b1 = load_row6<LD_STREAM>(pb1);
+            const Row6 b0 = load_row6<IGMK_JLOAD>(pb0), b1 = load_row6<IGMK_JLOAD>(pb1);
             if (AS) {
                 a0 = load_row6_shared(sa0); a1 = load_row6_shared(sa1);
             } else {
@@ -431,7 +431,28 @@ struct TileCtl {
     uint32_t slot_bytes;  // 2 rows * 12 * npad
     uint32_t words;       // shared address of the slot words
     int nslots;           // 1 or 2
+    uint32_t bars;        // shared address of one mbarrier per slot (bulk copies of the rows complete on it)
+    uint32_t pars;        // shared address of one word per slot: phase parity of the next load
 };
+// Shared control block of the tiles: slot words, phase parities, mbarriers.
+struct __align__(8) TileShared {
+    unsigned long long bar[2];
+    uint32_t slot[2];
+    uint32_t par[2];
+};
+__device__ __forceinline__ void tile_init(TileShared* ts) {   // one thread, before a CTA barrier
+    ts->slot[0] = (0xfffffu << 12) | (0u << 10);
+    ts->slot[1] = (0xfffffu << 12) | (0u << 10);
+    ts->par[0] = 0u; ts->par[1] = 0u;
+    mbar_init((uint32_t)__cvta_generic_to_shared(&ts->bar[0]), 1u);
+    mbar_init((uint32_t)__cvta_generic_to_shared(&ts->bar[1]), 1u);
+    mbar_fence_init();
+}
+__device__ __forceinline__ void tile_bind(TileShared* ts, TileCtl& tile) {
+    tile.words = (uint32_t)__cvta_generic_to_shared(&ts->slot[0]);
+    tile.pars = (uint32_t)__cvta_generic_to_shared(&ts->par[0]);
+    tile.bars = (uint32_t)__cvta_generic_to_shared(&ts->bar[0]);
+}
 __device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint32_t val) {
     uint32_t old;
     asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
@@ -488,24 +509,44 @@ __device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCt
         return found;
     }
     if (claimed < 0) return -1;
-    // load both rows of locus i (global -> shared, 128-bit, whole warp)
+#ifndef IGMK_TILE_BULK
+#define IGMK_TILE_BULK 0
+#endif
     const uint32_t dst0 = tile.base + (uint32_t)claimed * tile.slot_bytes;
-    const int n16 = (int)(tile.slot_bytes >> 5);          // 16-byte words per row
-    const float4* r0 = reinterpret_cast<const float4*>(pp.A0);
-    const float4* r1 = reinterpret_cast<const float4*>(pp.A1);
-    for (int k = lane; k < n16; k += 32) {
-        const float4 x0 = __ldg(r0 + k);
-        sts128(dst0 + (uint32_t)k * 16u, __float_as_uint(x0.x), __float_as_uint(x0.y),
-               __float_as_uint(x0.z), __float_as_uint(x0.w));
+    const uint32_t rowb = tile.slot_bytes >> 1;
+#if IGMK_TILE_BULK
+    // load both rows of locus i: two bulk asynchronous copies (TMA engine, 12 * npad bytes
+    // each) issued by one lane, completing on the slot's mbarrier; the warp waits for the
+    // bytes, then publishes the slot.  Nobody else touches a LOADING slot.
+    const uint32_t bar = tile.bars + 8u * (uint32_t)claimed;
+    const uint32_t par = lds32_volatile(tile.pars + 4u * (uint32_t)claimed);
+    __syncwarp();
+    if (lane == 0) {
+        mbar_expect_tx(bar, (d.a1 >= 0) ? 2u * rowb : rowb);
+        bulk_g2s(dst0, pp.A0, rowb, bar);
+        if (d.a1 >= 0) bulk_g2s(dst0 + rowb, pp.A1, rowb, bar);
+        sts32(tile.pars + 4u * (uint32_t)claimed, par ^ 1u);
     }
-    if (d.a1 >= 0) {
-        const uint32_t dst1 = dst0 + (tile.slot_bytes >> 1);
+    mbar_wait(bar, par);
+#else
+    {   // global -> shared, 128-bit, whole warp
+        const int n16 = (int)(rowb >> 4);
+        const float4* r0 = reinterpret_cast<const float4*>(pp.A0);
+        const float4* r1 = reinterpret_cast<const float4*>(pp.A1);
         for (int k = lane; k < n16; k += 32) {
-            const float4 x1 = __ldg(r1 + k);
-            sts128(dst1 + (uint32_t)k * 16u, __float_as_uint(x1.x), __float_as_uint(x1.y),
-                   __float_as_uint(x1.z), __float_as_uint(x1.w));
+            const float4 x0 = __ldg(r0 + k);
+            sts128(dst0 + (uint32_t)k * 16u, __float_as_uint(x0.x), __float_as_uint(x0.y),
+                   __float_as_uint(x0.z), __float_as_uint(x0.w));
+        }
+        if (d.a1 >= 0) {
+            for (int k = lane; k < n16; k += 32) {
+                const float4 x1 = __ldg(r1 + k);
+                sts128(dst0 + rowb + (uint32_t)k * 16u, __float_as_uint(x1.x), __float_as_uint(x1.y),
+                       __float_as_uint(x1.z), __float_as_uint(x1.w));
+            }
         }
     }
+#endif
     __threadfence_block();
     __syncwarp();
     if (lane == 0) {
@@ -743,7 +784,7 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     extern __shared__ uint4 s_keys[];             // [warp][2 V][32] key quads, then 2 locus-i tiles
     __shared__ uint32_t s_list[kWarpsPerBlock][kWarpListCap];
     __shared__ uint32_t s_cnt[kWarpsPerBlock];
-    __shared__ uint32_t s_slot[2];
+    __shared__ TileShared s_tile;
     __shared__ unsigned int s_ticket;
     __shared__ unsigned long long s_gblock[8];
     const int warp = threadIdx.x >> 5;
@@ -761,13 +802,13 @@ actdist_warp_kernel(const ActdistParams P, const int V) {
     g.list2 = 0u;
     g.parity = 0;
     TileCtl tile;
-    tile.base = 0u; tile.slot_bytes = 0u; tile.words = smem_addr(s_slot); tile.nslots = P.tile_slots;
+    tile.base = 0u; tile.slot_bytes = 0u; tile.nslots = P.tile_slots;
+    tile_bind(&s_tile, tile);
     if (P.tile_block > 0) {
         tile.base = smem_addr(s_keys) + (uint32_t)nwarps * 2u * (uint32_t)V * 512u;
         tile.slot_bytes = 24u * (uint32_t)P.npad;
         if (threadIdx.x == 0) {
-            s_slot[0] = (0xfffffu << 12) | (TS_EMPTY << 10);
-            s_slot[1] = (0xfffffu << 12) | (TS_EMPTY << 10);
+            tile_init(&s_tile);
             s_ticket = 0u;
         }
         if (threadIdx.x < 8) s_gblock[threadIdx.x] = 0ull;
@@ -857,7 +898,7 @@ actdist_block_kernel(const ActdistParams P, const int V) {
     g.parity = 0;
     const long long n_pairs = P.n_pairs_dev ? (long long)__ldg(P.n_pairs_dev) : P.n_pairs;
     TileCtl tile;
-    tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;
+    tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0; tile.bars = 0u; tile.pars = 0u;
     if (P.block_counter) {
         // pairs handed out by a device-wide counter (list order): the CTAs stay together in
         // the list and share the J-block's L2 residency instead of drifting apart

@@ -7,18 +7,16 @@
 // a pair, i.e. ~95 % of the values can never be the answer.  So instead of parking every
 // value (as a 16-bit key) in shared memory and bisecting over all of them
 // (igmk_actdist.cuh), this kernel
-//   1. sample: computes the first chunk of every thread (the first 4 * G structures), and
-//      picks a threshold T from the sample's order statistics with a safety margin
-//      (bisection on the 16-bit keys held in registers);  T_eff = max(T, rcutsq);
+//   1. sample: takes the first chunk of every thread (the first 4 * G structures) and picks
+//      a threshold T from the sample's order statistics with a safety margin (bisection on
+//      the 16-bit keys held in registers);  T_eff = max(T, rcutsq);
 //   2. fill: streams all chunks and appends only the values <= T_eff, in FULL float32, to a
-//      short thread-private list in shared memory (one predicated store per hit).  The rows
-//      of locus j arrive through a per-warp ring of shared-memory stages filled by bulk
-//      asynchronous copies (cp.async.bulk + mbarrier: one elected lane issues two 1536-byte
-//      copies per stage; the stages of the NEXT pair are requested before the current pair's
-//      select phase, so their L2 latency is hidden behind it);
+//      short thread-private list in shared memory (one compare, one predicated store, one
+//      predicated pointer bump per value; no contact counting, no key packing);
 //   3. select: contact count = #{list <= rcutsq} (T_eff >= rcutsq), p and o in float64, then
-//      the o-th smallest of the list: bisection in value space over the thread-private
-//      lists until <= 32 candidates remain, exact rank by one warp.
+//      the o-th smallest of the list: bisection in value space, every thread reading its own
+//      list with 128-bit loads, until <= 32 candidates remain; exact rank by a bitonic
+//      sort across the lanes of one warp.
 // Exactness does not depend on the sample: the list is complete for values <= T_eff, so if
 // it holds at least o + 1 values the o-th smallest of the list IS the o-th smallest of the
 // population.  Pairs for which that fails (sample not representative, thread list full,
@@ -29,11 +27,8 @@
 
 namespace igmk {
 
-#ifndef IGMK_LCAP
-#define IGMK_LCAP 24              // guaranteed list entries per thread
-#endif
-#ifndef IGMK_RING
-#define IGMK_RING 2               // stages of the locus-j ring per warp (power of two)
+#ifndef IGMK_LSLOTS
+#define IGMK_LSLOTS 44            // list words per thread; = 4 (mod 8): conflict-free 128-bit reads
 #endif
 #ifndef IGMK_LWPB
 #define IGMK_LWPB 20              // warps per CTA of the warp-group kernel
@@ -41,118 +36,35 @@ namespace igmk {
 #ifndef IGMK_LBT
 #define IGMK_LBT 320              // threads per CTA of the CTA-group kernel
 #endif
-constexpr int kListCap = IGMK_LCAP;
-constexpr int kListSpare = 4;                       // the bound is checked every 4 values
-constexpr int kListSlots = kListCap + kListSpare;
-constexpr int kRing = IGMK_RING;
-constexpr uint32_t kRowSegBytes = kSegFloats * 4u;  // x | y | z of 128 structures of one bead
-constexpr uint32_t kStageBytes = 2u * kRowSegBytes; // both copies of locus j
+constexpr int kListSlots = IGMK_LSLOTS;
+constexpr int kListSpare = 16 + 3;                  // one chunk's appends + the sentinel padding
+constexpr int kListCap = kListSlots - kListSpare;   // entries a thread may hold before a chunk
+constexpr uint32_t kListBytes = (uint32_t)kListSlots * 4u;
+constexpr uint32_t kListSentinel = 0x7fffffffu;     // compares above every pivot
 constexpr int kListWarps = IGMK_LWPB;
 constexpr int kListBlockThreads = IGMK_LBT;
-static_assert((kRing & (kRing - 1)) == 0 && kRing >= 1, "ring depth must be a power of two");
+static_assert(kListSlots % 8 == 4, "list stride must be 4 mod 8 words");
 
-// ------------------------------------------------------------ mbarrier / bulk copies
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0u;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    int spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1 << 22)) __trap();          // protocol error: never hang the GPU
-    }
-}
-// global -> shared bulk copy (TMA engine, 1-D), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+struct SampleOut { uint32_t T_bits; int ok; };
 
-// Per-warp ring of locus-j stages.  Stage k of the warp's issue sequence lives in slot
-// k % kRing and completes phase (k / kRing) & 1 of that slot's mbarrier; stages are
-// consumed in issue order, so two counters describe the whole state.
-struct Ring {
-    uint32_t base;        // shared address of slot 0
-    uint32_t bar;         // shared address of mbarrier 0
-    uint32_t issued, consumed;
-    __device__ __forceinline__ void issue(const float* b0seg, const float* b1seg, int lane) {
-        const uint32_t s = issued & (uint32_t)(kRing - 1);
-        if (lane == 0) {
-            const uint32_t bar_s = bar + 8u * s, dst = base + s * kStageBytes;
-            mbar_expect_tx(bar_s, kStageBytes);
-            bulk_g2s(dst, b0seg, kRowSegBytes, bar_s);
-            bulk_g2s(dst + kRowSegBytes, b1seg, kRowSegBytes, bar_s);
-        }
-        ++issued;
-    }
-    __device__ __forceinline__ uint32_t acquire() {
-        const uint32_t s = consumed & (uint32_t)(kRing - 1);
-        mbar_wait(bar + 8u * s, (consumed / (uint32_t)kRing) & 1u);
-        ++consumed;
-        return base + s * kStageBytes;
-    }
-};
-
-// The pair a group will work on next: enough to request its first locus-j stages.
-struct NextPair {
-    long long slot;       // position in processing order, -1: none
-    int b0, b1;           // beads of locus j (-1, -1: the pair needs no fill)
-};
-
-__device__ __forceinline__ NextPair peek_pair(const ActdistParams& P, long long slot) {
-    NextPair n;
-    n.slot = slot; n.b0 = -1; n.b1 = -1;
-    if (slot < 0) return n;
-    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-    const int i = __ldg(P.pi + pair), j = __ldg(P.pj + pair);
-    if (i != j && i >= 0 && j >= 0 && i < P.n_hap && j < P.n_hap) {
-        const int4 hb = __ldg(reinterpret_cast<const int4*>(P.hap + j));
-        n.b0 = hb.x;
-        n.b1 = (hb.y >= 0) ? hb.y : hb.x;
-    }
-    return n;
-}
-
-template <int NW>
-__device__ __forceinline__ int count_le_regs(const uint32_t (&kw)[NW], uint32_t piv2) {
-    uint32_t a0 = 0u, a1 = 0u;
-#pragma unroll
-    for (int w = 0; w < NW; w += 2) {
-        a0 -= bf2_le_mask(kw[w], piv2);
-        a1 -= bf2_le_mask(kw[w + 1], piv2);
-    }
-    const uint32_t acc = a0 + a1;
-    return ((int)acc >> 16) + 2 * (int)(acc & 0xffffu);
-}
-
-// Threshold from the group's first chunks (the first `ns` structures).  Returns false when
-// the list such a threshold produces is expected to exceed the budget (large o or many
-// contacts): the pair then goes to the key-array kernel.
-template <bool BLOCK, int NS>
-__device__ __forceinline__ bool sample_threshold(const ActdistParams& P, Group<BLOCK>& g, const PairDesc& d,
-                                                 const float (&s)[4][NS], int omax, uint32_t& T_bits) {
-    uint32_t kw[2 * NS];
+// Threshold from the group's first chunks (the first `ns` structures): kw = the 16-bit keys
+// (high halves of the float32 values, two per word, NaN = not a value) of this thread's
+// first chunk.  ok = 0 when the list such a threshold produces is expected to exceed the
+// budget (large o or many contacts): the pair then goes to the key-array kernel.
+// Deliberately out of line: one copy for all pair shapes.
+template <bool BLOCK>
+__device__ __noinline__ SampleOut sample_threshold(uint4 kwa, uint4 kwb, int tid, int nthr, uint32_t red,
+                                                   int keep, int nstruct, int omax, uint32_t rcb,
+                                                   float z, float budget) {
+    Group<BLOCK> g;
+    g.tid = tid; g.nthr = nthr; g.red = red; g.parity = 0;
+    g.kscr = 0u; g.kstride = 0u; g.list = 0u; g.ctl = 0u; g.cap = 0; g.list2 = 0u;
+    const uint32_t kw[8] = {kwa.x, kwa.y, kwa.z, kwa.w, kwb.x, kwb.y, kwb.z, kwb.w};
     uint32_t lmn = 0x7fff7fffu, lmx = 0x7fff7fffu;
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-#pragma unroll
-        for (int qh = 0; qh < 2; ++qh)
-            kw[2 * k + qh] = __byte_perm(__float_as_uint(s[2 * qh][k]), __float_as_uint(s[2 * qh + 1][k]), 0x7632);
-        lmn = bf2_min(lmn, bf2_min(kw[2 * k], kw[2 * k + 1]));     // NaN halves are ignored
-        lmx = bf2_max(lmx, bf2_max(kw[2 * k], kw[2 * k + 1]));
+    for (int w = 0; w < 8; w += 2) {
+        lmn = bf2_min(lmn, bf2_min(kw[w], kw[w + 1]));         // NaN halves are ignored
+        lmx = bf2_max(lmx, bf2_max(kw[w], kw[w + 1]));
     }
     uint32_t kmin = min(lmn & 0xffffu, lmn >> 16);
     uint32_t mxl = lmx & 0xffffu, mxh = lmx >> 16;
@@ -163,23 +75,33 @@ __device__ __forceinline__ bool sample_threshold(const ActdistParams& P, Group<B
     g.sum_min_max(zero, kmin, kmax);
     if (kmax < kmin) kmax = kmin;
 
-    const int ns = min(P.nstruct, 4 * g.nthr);
-    const float Sv = (float)(d.keep * ns), M = (float)(d.keep * P.nstruct);
+    SampleOut out;
+    out.T_bits = 0u; out.ok = 0;
+    const int ns = min(nstruct, 4 * nthr);
+    const float Sv = (float)(keep * ns), M = (float)(keep * nstruct);
     int k_t;
-    if (ns == P.nstruct) {
+    if (ns == nstruct) {
         k_t = omax + 1;                                // the sample is the population
     } else {
         // smallest k with  k - z sqrt(k) >= r0  (r0: expected sample rank of element o_max)
-        const float r0 = (float)(omax + 1) * Sv / M, z = P.list_z;
+        const float r0 = (float)(omax + 1) * Sv / M;
         k_t = (int)(r0 + 0.5f * z * z + 0.5f * z * sqrtf(z * z + 4.f * r0)) + 1;
     }
-    if ((float)k_t * M > P.list_budget * Sv) return false;
-    const int k_hi = k_t + max(1, k_t >> 3);
+    if ((float)k_t * M > budget * Sv) return out;
+    const int k_hi = k_t + max(2, k_t >> 2);
     uint32_t lo = kmin, hi = kmax;
-    int ch = d.keep * ns;
+    int ch = keep * ns;
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        const int c = g.sum(count_le_regs(kw, mid | (mid << 16)));
+        const uint32_t m2 = mid | (mid << 16);
+        uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; w += 2) {
+            a0 -= bf2_le_mask(kw[w], m2);
+            a1 -= bf2_le_mask(kw[w + 1], m2);
+        }
+        const uint32_t acc = a0 + a1;
+        const int c = g.sum(((int)acc >> 16) + 2 * (int)(acc & 0xffffu));
         if (c >= k_t) {
             hi = mid; ch = c;
             if (c <= k_hi) break;
@@ -188,138 +110,152 @@ __device__ __forceinline__ bool sample_threshold(const ActdistParams& P, Group<B
         }
     }
     uint32_t T = (hi << 16) | 0xffffu;
-    const uint32_t rcb = __float_as_uint(d.rcutsq);
     if (rcb > T) {                                     // the list must hold every contact
         T = rcb;
-        const uint32_t rk = rcb >> 16;
-        ch = g.sum(count_le_regs(kw, rk | (rk << 16)));
+        const uint32_t rk = rcb >> 16, r2 = rk | (rk << 16);
+        uint32_t a0 = 0u, a1 = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; w += 2) {
+            a0 -= bf2_le_mask(kw[w], r2);
+            a1 -= bf2_le_mask(kw[w + 1], r2);
+        }
+        const uint32_t acc = a0 + a1;
+        ch = g.sum(((int)acc >> 16) + 2 * (int)(acc & 0xffffu));
     }
-    if ((float)ch * M > P.list_budget * Sv) return false;
-    T_bits = T;
-    return true;
+    if ((float)ch * M > budget * Sv) return out;
+    out.T_bits = T; out.ok = 1;
+    return out;
 }
 
 // Fill of one pair.  Returns 0 when the thread lists are complete for values <= T_bits,
-// 1 when the pair has to be redone by the key-array kernel.  `pre`: stages of this pair
-// already requested; on return `pre` = stages of `nxt` requested.
+// 1 when the pair has to be redone by the key-array kernel.
 template <int SH, bool AS, bool BLOCK>
-__device__ __forceinline__ int fill_list(const ActdistParams& P, Group<BLOCK>& g, const PairDesc& d,
+__device__ __forceinline__ int fill_list(const ActdistParams& P, const Group<BLOCK>& g, const PairDesc& d,
                                          const PairPtrs& pp, int V, uint32_t as0, uint32_t as1,
-                                         Ring& ring, int& pre, const NextPair& nxt,
-                                         uint32_t lbase, uint32_t lstride, int omax,
+                                         uint32_t lbase, uint32_t sred, int omax,
                                          uint32_t& T_bits, int& mycnt, bool& ovf) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
     const u64 nz = P.negzero2;
-    const int tid = g.tid, lane = tid & 31, warp = tid >> 5, nw = g.nthr >> 5;
-    const int nseg = P.npad / kSeg;
-    const int Vw = (nseg > warp) ? (nseg - warp + nw - 1) / nw : 0;   // this warp's segments
-    const size_t seg0 = (size_t)warp * kSegFloats, vstride = (size_t)nw * kSegFloats;
-    const float* pa0 = pp.A0 + seg0 + (size_t)lane * 4;
-    const float* pa1 = pp.A1 + seg0 + (size_t)lane * 4;
-    uint32_t sa0 = as0 + (uint32_t)(seg0 + (size_t)lane * 4) * 4u;
-    uint32_t sa1 = as1 + (uint32_t)(seg0 + (size_t)lane * 4) * 4u;
-    const float* jb0 = pp.B0 + seg0;                   // segment bases of locus j (warp-uniform)
-    const float* jb1 = pp.B1 + seg0;
-    const size_t row = (size_t)3 * P.npad;
-    const float* nb0 = (nxt.b0 >= 0) ? P.coords + (size_t)nxt.b0 * row + seg0 : nullptr;
-    const float* nb1 = (nxt.b0 >= 0) ? P.coords + (size_t)nxt.b1 * row + seg0 : nullptr;
-
-    for (int k = pre; k < kRing && k < Vw; ++k) ring.issue(jb0 + (size_t)k * vstride, jb1 + (size_t)k * vstride, lane);
-    pre = 0;
-
+    const int tid = g.tid, nthr = g.nthr;
+    const size_t off0 = (size_t)(tid >> 5) * kSegFloats + (size_t)(tid & 31) * 4;
+    const size_t vstride = (size_t)(nthr >> 5) * kSegFloats;
+    const float* pa0 = pp.A0 + off0;
+    const float* pb0 = pp.B0 + off0;
+    const float* pa1 = pp.A1 + off0;
+    const float* pb1 = pp.B1 + off0;
+    uint32_t sa0 = as0 + (uint32_t)off0 * 4u, sa1 = as1 + (uint32_t)off0 * 4u;
     uint32_t lptr = lbase;
-    const uint32_t llimit = lbase + (uint32_t)kListCap * lstride;
+    const uint32_t llimit = lbase + (uint32_t)kListCap * 4u;
     float T = 0.f;
     ovf = false;
     int status = 0;
+    const u64 pol = (IGMK_JLOAD == LD_STREAM_L2KEEP || IGMK_JLOAD == LD_PLAIN_L2KEEP) ? l2_policy_evict_last() : 0ull;
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
-        const bool live = v < Vw;                      // warp-uniform
-        const int c = tid + v * g.nthr;
+        const int c = tid + v * nthr;
+        if (v > 0 && c >= P.nchunks) break;            // padding chunks (c only grows)
         float s[4][NS];
-        if (live) {
-            const uint32_t st = ring.acquire() + (uint32_t)lane * 16u;
+        {
+            // a padding chunk at v = 0 (tiny populations) still takes part in the sample;
+            // its loads fall inside the zero-padded rows (npad >= 128)
             Row6 a0, a1;
-            const Row6 b0 = load_row6_shared(st), b1 = load_row6_shared(st + kRowSegBytes);
+            const Row6 b0 = load_row6<IGMK_JLOAD>(pb0, pol), b1 = load_row6<IGMK_JLOAD>(pb1, pol);
             if (AS) {
                 a0 = load_row6_shared(sa0); a1 = load_row6_shared(sa1);
             } else {
                 a0 = load_row6<LD_KEEP>(pa0); a1 = load_row6<LD_KEEP>(pa1);
             }
             chunk_values<SH, NS>(d, P.mode, a0, a1, b0, b1, nz, s);
-            if (4 * c + 4 > P.nstruct) {               // tail / padding chunk of the population
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (4 * c + q >= P.nstruct) {
-#pragma unroll
-                        for (int k = 0; k < NS; ++k) s[q][k] = qnan;
-                    }
-            }
-        } else {
+        }
+        if (4 * c + 4 > P.nstruct) {                   // tail / padding chunk of the population
 #pragma unroll
             for (int q = 0; q < 4; ++q)
+                if (4 * c + q >= P.nstruct) {
 #pragma unroll
-                for (int k = 0; k < NS; ++k) s[q][k] = qnan;
+                    for (int k = 0; k < NS; ++k) s[q][k] = qnan;
+                }
         }
         if (v == 0) {                                  // uniform over the group
-            if (!sample_threshold<BLOCK, NS>(P, g, d, s, omax, T_bits)) {
-                // hand the pair over; the stages already requested must still land
-                const int out = min(kRing, Vw) - (live ? 1 : 0);
-                for (int k = 0; k < out; ++k) ring.acquire();
-                status = 1;
-                break;
-            }
-            T = __uint_as_float(T_bits);
-        }
-        if (live) {
+            uint32_t kw[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    if (s[q][k] <= T) {
-                        sts32(lptr, __float_as_uint(s[q][k]));
-                        lptr += lstride;
-                    }
-                }
-                if (NS == 4 || (q & 1)) {              // every 4 values: keep inside the spare slots
-                    if (lptr > llimit) { ovf = true; lptr = llimit; }
-                }
-            }
-            __syncwarp();                              // every lane has consumed the stage
-            const int kk = v + kRing;
-            if (kk < Vw) {
-                ring.issue(jb0 + (size_t)kk * vstride, jb1 + (size_t)kk * vstride, lane);
-            } else if (nb0 != nullptr && pre < Vw) {   // the freed slot takes the next pair's next stage
-                ring.issue(nb0 + (size_t)pre * vstride, nb1 + (size_t)pre * vstride, lane);
-                ++pre;
-            }
+                for (int qh = 0; qh < 2; ++qh)
+                    kw[2 * k + qh] = (k < NS) ? __byte_perm(__float_as_uint(s[2 * qh][k < NS ? k : 0]),
+                                                             __float_as_uint(s[2 * qh + 1][k < NS ? k : 0]), 0x7632)
+                                              : 0x7fff7fffu;
+            const SampleOut so = sample_threshold<BLOCK>(make_uint4(kw[0], kw[1], kw[2], kw[3]),
+                                                         make_uint4(kw[4], kw[5], kw[6], kw[7]), tid, nthr, sred,
+                                                         d.keep, P.nstruct, omax, __float_as_uint(d.rcutsq),
+                                                         P.list_z, P.list_budget);
+            if (!so.ok) { status = 1; break; }
+            T_bits = so.T_bits;
+            T = __uint_as_float(so.T_bits);
         }
-        pa0 += vstride; pa1 += vstride;
+        if (lptr > llimit) {                           // thread list full: stop appending, redo the pair
+            ovf = true;
+            T = -1.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (s[q][k] <= T) {
+                    sts32(lptr, __float_as_uint(s[q][k]));
+                    lptr += 4u;
+                }
+        pa0 += vstride; pb0 += vstride; pa1 += vstride; pb1 += vstride;
         sa0 += (uint32_t)vstride * 4u; sa1 += (uint32_t)vstride * 4u;
     }
-    mycnt = (int)((lptr - lbase) / lstride);
+    // pad to a whole quad: the select reads the list with 128-bit loads
+    sts32(lptr, kListSentinel); sts32(lptr + 4u, kListSentinel); sts32(lptr + 8u, kListSentinel);
+    mycnt = (int)((lptr - lbase) >> 2);
     return status;
 }
 
-__device__ __forceinline__ int list_count_le(uint32_t lbase, uint32_t lstride, int n, int piv) {
+// #{own list values <= piv} (bit patterns of non-negative floats compare like the values)
+__device__ __forceinline__ int list_count_le(uint32_t lbase, int nq, int piv) {
     int c = 0;
-#pragma unroll 4
-    for (int k = 0; k < n; ++k) c += ((int)lds32(lbase + (uint32_t)k * lstride) <= piv) ? 1 : 0;
+#pragma unroll 2
+    for (int q = 0; q < nq; ++q) {
+        uint32_t x0, x1, x2, x3;
+        lds128(lbase + (uint32_t)q * 16u, x0, x1, x2, x3);
+        c += ((int)x0 <= piv) ? 1 : 0;
+        c += ((int)x1 <= piv) ? 1 : 0;
+        c += ((int)x2 <= piv) ? 1 : 0;
+        c += ((int)x3 <= piv) ? 1 : 0;
+    }
     return c;
+}
+
+// r-th smallest (0-based) of the n <= 32 words at `list`: bitonic sort across the lanes.
+__device__ __forceinline__ uint32_t warp_rank(uint32_t list, int n, int r, int lane) {
+    uint32_t x = (lane < n) ? lds32(list + (uint32_t)lane * 4u) : 0xffffffffu;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+            const bool keep_min = (((lane & k) == 0) == ((lane & j) == 0));
+            x = keep_min ? min(x, y) : max(x, y);
+        }
+    }
+    return __shfl_sync(0xffffffffu, x, r);
 }
 
 // p, o and the o-th smallest value from the thread lists.  Returns false when the lists
 // cannot answer (overflow, or fewer than o + 1 values: the sample misjudged the pair).
 template <bool BLOCK>
 __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>& g, long long pair,
-                                            const PairDesc& d, uint32_t lbase, uint32_t lstride,
+                                            const PairDesc& d, uint32_t lbase,
                                             int mycnt, bool ovf, uint32_t T_bits) {
     const int n = g.sum(mycnt + (ovf ? (1 << 20) : 0));       // lists hold < 2^20 values
     if (n >> 20) return false;
+    const int nq = (mycnt + 3) >> 2;
     const int rcb = (int)__float_as_uint(d.rcutsq), tb = (int)T_bits;
     // every value <= rcutsq is in the list (T >= rcutsq)
-    const int cnt = (rcb >= tb) ? n : g.sum(list_count_le(lbase, lstride, mycnt, rcb));
+    const int cnt = (rcb >= tb) ? n : g.sum(list_count_le(lbase, nq, rcb));
     double p;
     int o;
     compute_p_o(cnt, d.keep, P.nstruct, __ldg(P.pwish + pair), __ldg(P.plast + pair), P.it_corr, p, o);
@@ -328,7 +264,7 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
         return true;
     }
     if (n < o + 1) return false;
-    // bracket (lo, hi] in bit-pattern order (non-negative floats: same as value order)
+    // bracket (lo, hi] in bit-pattern order
     int lo = -1, hi = tb, cb = 0, ch = n;
     if (rcb < tb) {
         if (cnt > o) { hi = rcb; ch = cnt; } else { lo = rcb; cb = cnt; }
@@ -343,7 +279,7 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
             mid = lo + ((hi - lo) >> 1);
         }
         mid = max(lo + 1, min(mid, hi - 1));
-        const int c = g.sum(list_count_le(lbase, lstride, mycnt, mid));
+        const int c = g.sum(list_count_le(lbase, nq, mid));
         if (c > o) { hi = mid; ch = c; } else { lo = mid; cb = c; }
         ++pass;
     }
@@ -353,7 +289,7 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
     }
     g.sync();                                          // candidate counter = 0 is visible
     for (int k = 0; k < mycnt; ++k) {
-        const int x = (int)lds32(lbase + (uint32_t)k * lstride);
+        const int x = (int)lds32(lbase + (uint32_t)k * 4u);
         if (x > lo && x <= hi) {
             const uint32_t slot = atoms_inc(g.ctl);
             if (slot < (uint32_t)kRankCap) sts32(g.list + slot * 4, (uint32_t)x);
@@ -361,7 +297,7 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
     }
     g.sync();
     if (g.leader_warp()) {
-        const uint32_t ans = warp_select(g.list, ch - cb, o - cb, g.tid & 31);
+        const uint32_t ans = warp_rank(g.list, ch - cb, o - cb, g.tid & 31);
         emit_result(P, g.tid, pair, d, ans, cnt, o, p, 0.0);
     }
     return true;
@@ -374,19 +310,15 @@ __device__ __forceinline__ void push_redo(const ActdistParams& P, int tid, long 
     }
 }
 
-// One pair in list form.  `cur` was peeked before (its first stages may be in flight:
-// `pre`); `nxt` is the group's next pair.
 template <bool BLOCK>
 __device__ __forceinline__ void process_pair_list(const ActdistParams& P, Group<BLOCK>& g, int V,
-                                                  const NextPair& cur, const NextPair& nxt, Ring& ring,
-                                                  int& pre, const TileCtl& tile,
-                                                  uint32_t lbase, uint32_t lstride) {
-    const long long pair = P.perm ? (long long)__ldg(P.perm + cur.slot) : cur.slot;
+                                                  long long slot, const TileCtl& tile,
+                                                  uint32_t lbase, uint32_t sred) {
+    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
     const int i = __ldg(P.pi + pair);
     const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
-    if (!d.valid) {                        // uniform over the group; nothing was requested
+    if (!d.valid) {                        // uniform over the group
         emit_empty(P, g.tid, pair);
-        pre = 0;
         return;
     }
     const PairPtrs pp = pair_ptrs(P, d);
@@ -407,103 +339,78 @@ __device__ __forceinline__ void process_pair_list(const ActdistParams& P, Group<
         const uint32_t as0 = tile.base + (uint32_t)tslot * tile.slot_bytes;
         const uint32_t as1 = (d.a1 >= 0) ? as0 + (tile.slot_bytes >> 1) : as0;
         switch (pair_shape(d, P.mode)) {       // uniform over the group
-            case SH_FULL4:  status = fill_list<SH_FULL4, true, BLOCK>(P, g, d, pp, V, as0, as1, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
-            case SH_INTRA2: status = fill_list<SH_INTRA2, true, BLOCK>(P, g, d, pp, V, as0, as1, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
-            case SH_GP4:    status = fill_list<SH_GP4, true, BLOCK>(P, g, d, pp, V, as0, as1, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
-            default:        status = fill_list<SH_GENERIC, true, BLOCK>(P, g, d, pp, V, as0, as1, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
+            case SH_FULL4:  status = fill_list<SH_FULL4, true, BLOCK>(P, g, d, pp, V, as0, as1, lbase, sred, omax, T_bits, mycnt, ovf); break;
+            case SH_INTRA2: status = fill_list<SH_INTRA2, true, BLOCK>(P, g, d, pp, V, as0, as1, lbase, sred, omax, T_bits, mycnt, ovf); break;
+            case SH_GP4:    status = fill_list<SH_GP4, true, BLOCK>(P, g, d, pp, V, as0, as1, lbase, sred, omax, T_bits, mycnt, ovf); break;
+            default:        status = fill_list<SH_GENERIC, true, BLOCK>(P, g, d, pp, V, as0, as1, lbase, sred, omax, T_bits, mycnt, ovf); break;
         }
         tile_release(tile, tslot, g.tid);
     } else {
         switch (pair_shape(d, P.mode)) {
-            case SH_FULL4:  status = fill_list<SH_FULL4, false, BLOCK>(P, g, d, pp, V, 0u, 0u, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
-            case SH_INTRA2: status = fill_list<SH_INTRA2, false, BLOCK>(P, g, d, pp, V, 0u, 0u, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
-            case SH_GP4:    status = fill_list<SH_GP4, false, BLOCK>(P, g, d, pp, V, 0u, 0u, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
-            default:        status = fill_list<SH_GENERIC, false, BLOCK>(P, g, d, pp, V, 0u, 0u, ring, pre, nxt, lbase, lstride, omax, T_bits, mycnt, ovf); break;
+            case SH_FULL4:  status = fill_list<SH_FULL4, false, BLOCK>(P, g, d, pp, V, 0u, 0u, lbase, sred, omax, T_bits, mycnt, ovf); break;
+            case SH_INTRA2: status = fill_list<SH_INTRA2, false, BLOCK>(P, g, d, pp, V, 0u, 0u, lbase, sred, omax, T_bits, mycnt, ovf); break;
+            case SH_GP4:    status = fill_list<SH_GP4, false, BLOCK>(P, g, d, pp, V, 0u, 0u, lbase, sred, omax, T_bits, mycnt, ovf); break;
+            default:        status = fill_list<SH_GENERIC, false, BLOCK>(P, g, d, pp, V, 0u, 0u, lbase, sred, omax, T_bits, mycnt, ovf); break;
         }
     }
-    if (status != 0 || !select_list<BLOCK>(P, g, pair, d, lbase, lstride, mycnt, ovf, T_bits))
+    if (status != 0 || !select_list<BLOCK>(P, g, pair, d, lbase, mycnt, ovf, T_bits))
         push_redo(P, g.tid, pair);
 }
 
 // ---------------------------------------------------------------- kernels
-// G = 32: one pair per warp, no CTA barrier after the set-up.  Shared memory per warp:
-// kListSlots x 128 bytes of thread lists and kRing x 3072 bytes of locus-j stages; one
-// locus-i tile per CTA (igmk_actdist.cuh).
+// G = 32: one pair per warp, no CTA barrier after the set-up.  Shared memory: kListSlots
+// words of list per thread, then the locus-i tiles (igmk_actdist.cuh; their rows arrive by
+// bulk asynchronous copies).
 __global__ void __launch_bounds__(32 * kListWarps, 1)
 actdist_list_warp_kernel(const ActdistParams P, const int V) {
-    extern __shared__ uint4 s_dyn[];              // [warp] rings | [warp] lists | locus-i tile
-    __shared__ __align__(8) unsigned long long s_bar[kListWarps][kRing];
-    __shared__ uint32_t s_list[kListWarps][kWarpListCap];
+    extern __shared__ uint4 s_dyn[];              // [thread] lists | locus-i tiles
+    __shared__ uint32_t s_list[kListWarps][kRankCap];
     __shared__ uint32_t s_cnt[kListWarps];
-    __shared__ uint32_t s_slot[2];
+    __shared__ TileShared s_tile;
     __shared__ unsigned int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = blockDim.x >> 5;
     Group<false> g;
     g.tid = lane;
     g.nthr = 32;
     g.list = smem_addr(&s_list[warp][0]);
     g.ctl = smem_addr(&s_cnt[warp]);
-    g.cap = kWarpListCap;
+    g.cap = kRankCap;
     g.kscr = 0u; g.kstride = 0u; g.red = 0u; g.list2 = 0u; g.parity = 0;
     const uint32_t dyn0 = smem_addr(s_dyn);
-    Ring ring;
-    ring.base = dyn0 + (uint32_t)warp * (uint32_t)kRing * kStageBytes;
-    ring.bar = smem_addr(&s_bar[warp][0]);
-    ring.issued = 0u; ring.consumed = 0u;
-    const uint32_t lists0 = dyn0 + (uint32_t)nwarps * (uint32_t)kRing * kStageBytes;
-    const uint32_t lbase = lists0 + (uint32_t)warp * (uint32_t)kListSlots * 128u + (uint32_t)lane * 4u;
+    const uint32_t lbase = dyn0 + (uint32_t)threadIdx.x * kListBytes;
     TileCtl tile;
-    tile.base = 0u; tile.slot_bytes = 24u * (uint32_t)P.npad; tile.words = smem_addr(s_slot); tile.nslots = 1;
-    if (P.tile_block > 0 && P.tile_slots > 0)
-        tile.base = lists0 + (uint32_t)nwarps * (uint32_t)kListSlots * 128u;
+    tile.base = 0u; tile.slot_bytes = 24u * (uint32_t)P.npad; tile.nslots = P.tile_slots;
+    tile_bind(&s_tile, tile);
+    if (P.tile_slots > 0) tile.base = dyn0 + (uint32_t)blockDim.x * kListBytes;
     if (threadIdx.x == 0) {
-        s_slot[0] = (0xfffffu << 12) | (TS_EMPTY << 10);
-        s_slot[1] = (0xfffffu << 12) | (TS_EMPTY << 10);
+        tile_init(&s_tile);
         s_ticket = 0u;
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kRing; ++s) mbar_init(ring.bar + 8u * s, 1u);
-        mbar_fence_init();
-    }
     __syncthreads();
-    // CTA-contiguous blocks of B pairs (block k of this CTA = list block blockIdx + k *
-    // gridDim), handed to the warps one pair at a time by a shared ticket counter:
+    // CTA-contiguous blocks of 2^bshift pairs (block k of this CTA = list block blockIdx +
+    // k * gridDim), handed to the warps one pair at a time by a shared ticket counter:
     // consecutive pairs share locus i, fast and slow pairs balance out across the warps.
-    const unsigned int B = (unsigned int)max(P.tile_block, 1);
-    auto draw = [&]() -> long long {
-        for (;;) {
-            unsigned int t = 0u;
-            if (lane == 0) t = atomicAdd(&s_ticket, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            const unsigned int k = t / B, r = t - k * B;
-            const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) * B;
-            if (base >= P.n_pairs) return -1;
-            if (base + r < P.n_pairs) return base + r;
-        }
-    };
-    int pre = 0;
-    NextPair nxt = peek_pair(P, draw());
-    while (nxt.slot >= 0) {
-        const NextPair cur = nxt;
-        nxt = peek_pair(P, draw());
-        process_pair_list<false>(P, g, V, cur, nxt, ring, pre, tile, lbase, 128u);
+    const unsigned int bshift = (unsigned int)P.tile_block;      // log2 of the block size
+    for (;;) {
+        unsigned int t = 0u;
+        if (lane == 0) t = atomicAdd(&s_ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const unsigned int k = t >> bshift, r = t & ((1u << bshift) - 1u);
+        const long long base = ((long long)blockIdx.x + (long long)k * gridDim.x) << bshift;
+        if (base >= P.n_pairs) break;
+        if (base + r < P.n_pairs) process_pair_list<false>(P, g, V, base + r, tile, lbase, 0u);
         __syncwarp();
     }
 }
 
-// G = blockDim.x: one pair per CTA, two CTAs per SM (N > 1024).  Every warp runs its own
-// ring over its own segments of the locus-j rows; the rows of locus i come through L1.
+// G = blockDim.x: one pair per CTA, two CTAs per SM (N > 1024).
 __global__ void __launch_bounds__(kListBlockThreads, 2)
 actdist_list_block_kernel(const ActdistParams P, const int V) {
-    extern __shared__ uint4 s_dyn[];              // [warp] rings | [slot][thread] lists
-    __shared__ __align__(8) unsigned long long s_bar[kListBlockThreads / 32][kRing];
+    extern __shared__ uint4 s_dyn[];              // [thread] lists
     __shared__ uint32_t s_list[kRankCap];
     __shared__ uint32_t s_cnt;
     __shared__ uint32_t s_red[2 * 96];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = blockDim.x >> 5;
+    __shared__ uint32_t s_red2[2 * 96];           // reductions of the sample phase
     Group<true> g;
     g.tid = threadIdx.x;
     g.nthr = blockDim.x;
@@ -514,29 +421,11 @@ actdist_list_block_kernel(const ActdistParams P, const int V) {
     g.red = smem_addr(s_red);
     g.list2 = 0u;
     g.parity = 0;
-    const uint32_t dyn0 = smem_addr(s_dyn);
-    Ring ring;
-    ring.base = dyn0 + (uint32_t)warp * (uint32_t)kRing * kStageBytes;
-    ring.bar = smem_addr(&s_bar[warp][0]);
-    ring.issued = 0u; ring.consumed = 0u;
-    const uint32_t lbase = dyn0 + (uint32_t)nwarps * (uint32_t)kRing * kStageBytes + (uint32_t)threadIdx.x * 4u;
-    const uint32_t lstride = (uint32_t)blockDim.x * 4u;
+    const uint32_t lbase = smem_addr(s_dyn) + (uint32_t)threadIdx.x * kListBytes;
     TileCtl tile;
-    tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kRing; ++s) mbar_init(ring.bar + 8u * s, 1u);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    int pre = 0;
-    long long slot = blockIdx.x;
-    NextPair nxt = peek_pair(P, (slot < P.n_pairs) ? slot : -1);
-    while (nxt.slot >= 0) {
-        const NextPair cur = nxt;
-        slot += gridDim.x;
-        nxt = peek_pair(P, (slot < P.n_pairs) ? slot : -1);
-        process_pair_list<true>(P, g, V, cur, nxt, ring, pre, tile, lbase, lstride);
+    tile.base = 0u; tile.slot_bytes = 0u; tile.words = 0u; tile.nslots = 0; tile.bars = 0u; tile.pars = 0u;
+    for (long long slot = blockIdx.x; slot < P.n_pairs; slot += gridDim.x) {
+        process_pair_list<true>(P, g, V, slot, tile, lbase, smem_addr(s_red2));
         __syncthreads();
     }
 }

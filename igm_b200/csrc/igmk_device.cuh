@@ -411,9 +411,22 @@ struct Row6 { u64 x01, x23, y01, y23, z01, z23; };
 // Row loads with an L1 policy: the rows of locus i are shared by every warp of the
 // CTA (consecutive pairs of the CSR-ordered list) and should stay in L1; the rows
 // of locus j are streamed once and must not evict them.
-enum : int { LD_KEEP = 0, LD_STREAM = 1, LD_PLAIN = 2 };
+enum : int { LD_KEEP = 0, LD_STREAM = 1, LD_PLAIN = 2, LD_STREAM_L2KEEP = 3, LD_PLAIN_L2KEEP = 4 };
+// How K1 loads the rows of locus j.  Plain loads: the L1::no_allocate hint (LDG.NA) also
+// demotes the lines in L2 - with it the rows of the current J-block are evicted before
+// their next use (L2 hit rate 39 % against 86 %, DRAM traffic 43 GB against 6.6 GB per
+// launch on config 2; ncu, profiles/r02_*).
+#ifndef IGMK_JLOAD
+#define IGMK_JLOAD LD_PLAIN
+#endif
+// L2 eviction policy "keep" (evict_last) for the rows of the current J-block
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 template <int HINT>
-__device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b) {
+__device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b, u64 pol = 0ull) {
 #ifdef IGMK_NO_L1_HINTS
     asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 #else
@@ -421,6 +434,10 @@ __device__ __forceinline__ void ldg_v2b64(const float* p, u64& a, u64& b) {
         asm("ld.global.nc.L1::evict_last.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
     else if (HINT == LD_STREAM)
         asm("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+    else if (HINT == LD_STREAM_L2KEEP)
+        asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol));
+    else if (HINT == LD_PLAIN_L2KEEP)
+        asm("ld.global.nc.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(a), "=l"(b) : "l"(p), "l"(pol));
     else
         asm("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
 #endif
@@ -437,11 +454,11 @@ __device__ __forceinline__ Row6 load_row6_shared(uint32_t addr) {   // same layo
     return r;
 }
 template <int HINT>
-__device__ __forceinline__ Row6 load_row6(const float* p) {
+__device__ __forceinline__ Row6 load_row6(const float* p, u64 pol = 0ull) {
     Row6 r;
-    ldg_v2b64<HINT>(p, r.x01, r.x23);
-    ldg_v2b64<HINT>(p + kSeg, r.y01, r.y23);
-    ldg_v2b64<HINT>(p + 2 * kSeg, r.z01, r.z23);
+    ldg_v2b64<HINT>(p, r.x01, r.x23, pol);
+    ldg_v2b64<HINT>(p + kSeg, r.y01, r.y23, pol);
+    ldg_v2b64<HINT>(p + 2 * kSeg, r.z01, r.z23, pol);
     return r;
 }
 // d2 of structures (4c+2h, 4c+2h+1), h = 0 / 1
@@ -536,6 +553,36 @@ __device__ __forceinline__ uint32_t atoms_inc(uint32_t addr) {
     uint32_t v;
     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(addr) : "memory");
     return v;
+}
+
+// ---- mbarrier + bulk asynchronous copies (TMA engine, 1-D): global -> shared, completion
+// counted in bytes on an mbarrier.  Used for the locus-i tiles of K1 (igmk_actdist.cuh).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1 << 22)) __trap();          // protocol error: never hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 }  // namespace igmk

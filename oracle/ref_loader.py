@@ -24,7 +24,12 @@ import os
 import sys
 import types
 
+HERE = os.path.dirname(os.path.abspath(__file__))
+# the read-only reference tree in the build container; on the GPU box the copy of its
+# Python package that `make -C oracle ref_py` left in git-ignored oracle/_ref/
 REFERENCE_ROOT = os.environ.get("IGM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "igm", "steps")):
+    REFERENCE_ROOT = os.path.join(HERE, "_ref")
 
 _STUB_ROOTS = (
     "alabtools", "h5py", "ipyparallel", "zmq", "cloudpickle", "tornado",

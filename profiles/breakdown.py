@@ -6,8 +6,8 @@ report (run in the build container; needs no GPU):
 
 The SASS page of the report (`ncu -i REPORT --page source --csv`) is joined by instruction
 offset with `nvdisasm --print-line-info` of the kernel in igm_b200/libigmk.so (same build),
-and every instruction is attributed to the function of igmk_actdist.cuh whose line range
-holds the most recent igmk_actdist.cuh line seen in address order (inlined helpers of
+and every instruction is attributed to the function of igmk_actdist.cuh / igmk_actdist_list.cuh whose line range
+holds the most recent line of those files seen in address order (inlined helpers of
 igmk_device.cuh therefore count for their caller).
 """
 import collections
@@ -69,10 +69,11 @@ def main():
     if len(prof) != len(ins):
         sys.stderr.write("warning: %d profiled vs %d disassembled instructions (different build?)\n"
                          % (len(prof), len(ins)))
-    ranges = function_ranges(os.path.join(ROOT, "igm_b200", "csrc", "igmk_actdist.cuh"))
+    ranges = {f: function_ranges(os.path.join(ROOT, "igm_b200", "csrc", f))
+              for f in ("igmk_actdist.cuh", "igmk_actdist_list.cuh")}
 
-    def func(ln):
-        for a, b, nm in ranges:
+    def func(f, ln):
+        for a, b, nm in ranges[f]:
             if a <= ln <= b:
                 return nm
         return "other"
@@ -87,8 +88,8 @@ def main():
             continue
         n = int(r[ix["Instructions Executed"]] or 0)
         s = int(r[ix["# Samples"]] or 0)
-        if f == "igmk_actdist.cuh":
-            cur = func(ln)
+        if f in ranges:
+            cur = func(f, ln)
         byf[cur] += n
         bys[cur] += s
         tot += n
