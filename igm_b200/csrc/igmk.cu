@@ -81,9 +81,9 @@ struct igmk_ctx {
                                  // more than 8 M pairs (CTAs drift apart over a long list and lose the J-block's L2
                                  // residency: config 5 +4 %; config 2 -1 %)
     int list_form = 1;           // IGMK_LIST: 1 = list form first, key-array kernels for what it hands back; 0 = key arrays only
-    float list_z = 2.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
+    float list_z = 1.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
     int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
-    float list_budget = 12.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
+    float list_budget = 16.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
     void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
     unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
     bool redo_pending = false;

@@ -214,19 +214,20 @@ __device__ __forceinline__ int fill_list(const ActdistParams& P, const Group<BLO
     return status;
 }
 
-// #{own list values <= piv} (bit patterns of non-negative floats compare like the values)
-__device__ __forceinline__ int list_count_le(uint32_t lbase, int nq, int piv) {
-    int c = 0;
+// #{own list values <= piv}: 1.0 / 0.0 flags (FSET.BF) accumulated two per FADD2, exact below
+// 2^24; the sentinel padding is a NaN pattern and never counts.
+__device__ __forceinline__ int list_count_le(uint32_t lbase, int nq, float piv) {
+    u64 acc = 0ull;
 #pragma unroll 2
     for (int q = 0; q < nq; ++q) {
         uint32_t x0, x1, x2, x3;
         lds128(lbase + (uint32_t)q * 16u, x0, x1, x2, x3);
-        c += ((int)x0 <= piv) ? 1 : 0;
-        c += ((int)x1 <= piv) ? 1 : 0;
-        c += ((int)x2 <= piv) ? 1 : 0;
-        c += ((int)x3 <= piv) ? 1 : 0;
+        acc = f2add(acc, f2pack(f_le_one(__uint_as_float(x0), piv), f_le_one(__uint_as_float(x1), piv)));
+        acc = f2add(acc, f2pack(f_le_one(__uint_as_float(x2), piv), f_le_one(__uint_as_float(x3), piv)));
     }
-    return c;
+    float lo, hi;
+    f2split(acc, lo, hi);
+    return (int)(lo + hi);
 }
 
 // r-th smallest (0-based) of the n <= 32 words at `list`: bitonic sort across the lanes.
@@ -251,11 +252,11 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
                                             const PairDesc& d, uint32_t lbase,
                                             int mycnt, bool ovf, uint32_t T_bits) {
     const int n = g.sum(mycnt + (ovf ? (1 << 20) : 0));       // lists hold < 2^20 values
-    if (n >> 20) return false;
+    if ((n >> 20) || T_bits >= 0x7f800000u) return false;     // (overflowed distances: not for this path)
     const int nq = (mycnt + 3) >> 2;
     const int rcb = (int)__float_as_uint(d.rcutsq), tb = (int)T_bits;
     // every value <= rcutsq is in the list (T >= rcutsq)
-    const int cnt = (rcb >= tb) ? n : g.sum(list_count_le(lbase, nq, rcb));
+    const int cnt = (rcb >= tb) ? n : g.sum(list_count_le(lbase, nq, d.rcutsq));
     double p;
     int o;
     compute_p_o(cnt, d.keep, P.nstruct, __ldg(P.pwish + pair), __ldg(P.plast + pair), P.it_corr, p, o);
@@ -279,7 +280,7 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
             mid = lo + ((hi - lo) >> 1);
         }
         mid = max(lo + 1, min(mid, hi - 1));
-        const int c = g.sum(list_count_le(lbase, nq, mid));
+        const int c = g.sum(list_count_le(lbase, nq, __int_as_float(mid)));
         if (c > o) { hi = mid; ch = c; } else { lo = mid; cb = c; }
         ++pass;
     }
@@ -288,11 +289,15 @@ __device__ __forceinline__ bool select_list(const ActdistParams& P, Group<BLOCK>
         return true;
     }
     g.sync();                                          // candidate counter = 0 is visible
-    for (int k = 0; k < mycnt; ++k) {
-        const int x = (int)lds32(lbase + (uint32_t)k * 4u);
-        if (x > lo && x <= hi) {
-            const uint32_t slot = atoms_inc(g.ctl);
-            if (slot < (uint32_t)kRankCap) sts32(g.list + slot * 4, (uint32_t)x);
+    for (int q = 0; q < nq; ++q) {
+        uint32_t x[4];
+        lds128(lbase + (uint32_t)q * 16u, x[0], x[1], x[2], x[3]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if ((int)x[t] > lo && (int)x[t] <= hi) {   // (the sentinel is above every hi)
+                const uint32_t slot = atoms_inc(g.ctl);
+                if (slot < (uint32_t)kRankCap) sts32(g.list + slot * 4, x[t]);
+            }
         }
     }
     g.sync();
