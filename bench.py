@@ -8,16 +8,22 @@ One "step" = one pass of the Hi-C A-step hot path (get_actdist for every
 candidate pair, igm/steps/ActivationDistanceStep.py:215-219,336-485) over the
 candidate list of the final sigma (0.01) of the sweep on a synthetic population:
 config 2 of BASELINE.json - 1 000 structures x 200 kb male diploid (29 838
-beads).  For N > 1 every rank holds the full population (replicated), works on
-its own equal-count shard of candidate pairs and the per-pair results are
-collected with one NCCL all-gather (weak scaling: pairs per GPU fixed).
+beads).  The population comes from the seeded NumPy generator, so both arms of the
+bench (ours / --impl reference) work on the SAME coordinates and the SAME list.
+For N > 1 every rank holds the full population (replicated), works on its own
+equal-count list (weak scaling) and the per-pair results are gathered on every
+GPU (peer stores from inside the kernel, or one NCCL all-gather).
 
-Prints ONE JSON line (rank 0).  `value` = whole-job pairs/s with inputs
-resident in HBM; `e2e` = the same through the C-ABI host entry point
-(igmk_actdist_host) with pinned host buffers, H2D/D2H inside the timed region;
-`roofline` = algorithmic bytes / kernel time against the measured HBM copy
-bandwidth; `cpu_baseline` = the oracle port of the reference's get_actdist on
-the host cores (bounded sample).
+Prints ONE JSON line (rank 0).  `value` = whole-job pairs/s with inputs resident
+in HBM; `e2e` = the same through the C ABI with HOST buffers: the population is
+staged again every step (pinned host coordinates -> igmk_upload_coords: every
+A-step follows an M-step that rewrote the .hss), then igmk_actdist_host copies
+the pair list in and the results out; `e2e_pairs_only` leaves the population
+resident; `roofline` = algorithmic bytes / kernel time against the measured HBM
+copy bandwidth; `cpu_baseline` = the reference's own get_actdist on the host
+cores (bounded sample).  `config.extra` carries the other BASELINE.json configs,
+measured in the same run: config 3 (10 000 structures, one fixed list strong-scaled
+over the GPUs), config 4 (contact-frequency map) and config 5 (50 kb stress test).
 """
 import argparse
 import json
@@ -35,6 +41,7 @@ sys.path.insert(0, ROOT)
 METRIC = "A-step candidate pairs/sec"
 UNIT = "pairs/s"
 SEED = 20261018
+N_ALL_HAPLOID_PAIRS_200KB = 15453 * 15452 // 2       # "all candidate pairs" upper bound of config 3
 
 
 def parse_args():
@@ -52,23 +59,25 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs 3 / 4 / 5")
+    ap.add_argument("--extras", default="3,4,5", help="which extra configs to run")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------ workload
-def build_index_and_pairs(args, rank):
+def build_index_and_pairs(resolution, sigma, rank=0, max_pairs=0, native=True):
     """Candidate pairs of this rank: the sigma-filtered non-zeros of the synthetic
     probability matrix in CSR order (what setup() produces,
     ActivationDistanceStep.py:171-178); ranks > 0 take the same list rotated
     along the genome so every GPU does different, equally sized work."""
     from igm_b200 import synthetic
     from igm_b200.steps.ActivationDistanceStep import filter_candidates
-    bins = synthetic.genome_bins(args.resolution)
+    bins = synthetic.genome_bins(resolution)
     chrom_hap, chrom_bead, copy_bead, ci = synthetic.build_index(bins)
     pm = synthetic.make_prob_matrix(chrom_hap, seed=SEED)
-    ii, jj, pw = filter_candidates(pm, args.sigma, args.sigma)
-    if args.max_pairs:
-        ii, jj, pw = ii[:args.max_pairs], jj[:args.max_pairs], pw[:args.max_pairs]
+    ii, jj, pw = filter_candidates(pm, sigma, sigma, native=native)
+    if max_pairs:
+        ii, jj, pw = ii[:max_pairs], jj[:max_pairs], pw[:max_pairs]
     if rank:
         n = len(chrom_hap)
         sh = (rank * 977) % n
@@ -78,16 +87,22 @@ def build_index_and_pairs(args, rank):
         ok = ~((chrom_hap[a] == chrom_hap[b]) & (nc[a] != nc[b])) & (a != b)
         a[~ok], b[~ok] = ii[~ok], jj[~ok]
         ii, jj = a.astype(np.int32), b.astype(np.int32)
-    return chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw
+    return chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw, pm
 
 
-def config_name(args):
-    """Which BASELINE.json config the arguments correspond to."""
-    if args.resolution == 200_000 and args.nstruct == 1000:
+def host_population(chrom_bead, copy_bead, nstruct, radius):
+    """(nbead, nstruct, 3) float32 from the seeded NumPy generator - identical in both
+    arms of the bench."""
+    from igm_b200 import synthetic
+    return synthetic.random_walk_coordinates(chrom_bead, copy_bead, nstruct, radius, np.random.default_rng(SEED))
+
+
+def config_name(resolution, nstruct):
+    if resolution == 200_000 and nstruct == 1000:
         return "config 2"
-    if args.resolution == 200_000 and args.nstruct == 10000:
-        return "config 3 (per-GPU shard)"
-    if args.resolution == 50_000 and args.nstruct == 1000:
+    if resolution == 200_000 and nstruct == 10000:
+        return "config 3"
+    if resolution == 50_000 and nstruct == 1000:
         return "config 5"
     return "custom"
 
@@ -152,14 +167,13 @@ class ClockSampler(threading.Thread):
 
 
 def measured_traffic(nstruct, n_pairs, mode, key="dram_bytes_per_launch"):
-    """DRAM bytes (read + write) of ONE launch of the dominant kernel on this
-    workload, from the committed `ncu --set full` capture (profiles/traffic.json,
-    written by profiles/update_traffic.py); None when no capture matches.  ``key`` selects
-    another per-launch counter of the same capture (warp instructions)."""
+    """Counter of ONE launch of the dominant kernel on this workload from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by profiles/update_traffic.py);
+    None when no capture matches."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         for e in json.load(open(p))["captures"]:
-            if e["nstruct"] == nstruct and e["n_pairs"] == n_pairs and e["mode"] == mode:
+            if e["nstruct"] == nstruct and e["n_pairs"] == n_pairs and e["mode"] == mode and key in e:
                 return float(e[key])
     except Exception:
         pass
@@ -176,47 +190,285 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# ------------------------------------------------------------- CPU baseline
+# ------------------------------------------------------------- CPU arms
 _G = {}
 
 
-def _cpu_worker(sl):
-    from oracle import actdist_oracle as orc
-    ii, jj, pw, pl, coords, radii, chrom_hap, ci, it_corr, mode = _G["a"]
+def _ref_worker(sl):
+    """One batch of the reference's task() loop (ActivationDistanceStep.py:215-222) with
+    the reference's own, unmodified get_actdist."""
+    fn, hss, ii, jj, pw, it_corr = _G["a"]
     a, b = sl
-    recs, _ = orc.run_pairs(ii[a:b], jj[a:b], pw[a:b], pl[a:b], coords, radii, chrom_hap, ci,
-                            it_corr, 2.0, mode)
-    return len(recs)
+    n = 0
+    for k in range(a, b):
+        n += len(fn(int(ii[k]), int(jj[k]), pw[k], 0.0, hss, it_corr, contactRange=2.0))
+    return n
 
 
-def cpu_baseline(sample_coords, radii, chrom_hap, ci, ii, jj, pw, it_corr, mode, budget_s):
-    """The oracle's NumPy port of the reference get_actdist (same NumPy calls as
-    ActivationDistanceStep.py:405-473), batches of 1000 pairs as in setup (:129),
-    multiprocessing over all host cores, coordinates shared by fork."""
+def cpu_reference_rate(coords, radii, chrom_hap, ci, ii, jj, pw, it_corr, mode, budget_s, steps=1, warmup=0):
+    """The reference's own get_actdist (imported unmodified through oracle/ref_loader.py)
+    on all host cores: batches of 1000 pairs as in setup (:129) over a fork pool that is
+    created BEFORE the timed span; coordinates inherited by fork.  The sample is the
+    leading slice of the step's list, sized to about `budget_s` seconds per step."""
     import multiprocessing as mp
-    from oracle import actdist_oracle as orc
+    from oracle import ref_loader
+    ref = ref_loader.load_reference()
+    fn = ref["lb_get_actdist"] if mode == "LB" else ref["gp_get_actdist"]
+    hss = ref_loader.FakeHss(coords, radii, chrom_hap, ci)
     cores = os.cpu_count() or 1
-    pl = np.zeros(len(ii))
-    omode = orc.MODE_LB if mode == "LB" else orc.MODE_GP
-    _G["a"] = (ii, jj, pw, pl, sample_coords, radii, chrom_hap, ci, it_corr, omode)
+    root = ref_loader.REFERENCE_ROOT
+    nmax = min(len(ii), 4_000_000)
+    pw64 = np.ascontiguousarray(pw[:nmax], np.float64)      # pw64[k] is the np.float64 setup() hands over
+    _G["a"] = (fn, hss, ii, jj, pw64, it_corr)
     t0 = time.perf_counter()
-    _cpu_worker((0, min(200, len(ii))))
-    rate1 = min(200, len(ii)) / (time.perf_counter() - t0)
-    n = int(min(len(ii), max(1000, rate1 * cores * budget_s * 0.8)))
+    _ref_worker((0, min(100, nmax)))
+    rate1 = min(100, nmax) / (time.perf_counter() - t0)
+    n = int(min(nmax, len(pw64), max(1000, rate1 * cores * budget_s * 0.6)))
     batches = [(a, min(n, a + 1000)) for a in range(0, n, 1000)]
-    ctx = mp.get_context("fork")
+    rates, ms = [], []
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_ref_worker, [(0, 1)] * cores, chunksize=1)          # the workers are up
+        for k in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_ref_worker, batches, chunksize=1)
+            dt = time.perf_counter() - t0
+            if k >= warmup:
+                rates.append(n / dt)
+                ms.append(dt * 1e3)
+    where = os.path.relpath(root, ROOT) if root.startswith(ROOT) else root
+    return {"value": float(np.mean(rates)), "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": "first %d candidate pairs of the step's list through the reference's unmodified "
+                      "get_actdist (%s/igm/steps/ActivationDistanceStep.py), fork pool of %d processes created "
+                      "before the timed span, batches of 1000; %.1f s per step" % (
+                          n, where, cores, float(np.mean(ms)) / 1e3),
+            "single_core_pairs_per_s": rate1, "sample_pairs": n, "ms_per_step": float(np.mean(ms))}
+
+
+def c_oracle_check(ii, jj, pw, coords_sub, radii_sub, chrom_hap, ci, remap, it_corr, mode, got):
+    """Plain-C oracle (OpenMP) over the given pairs, compared field by field with `got`."""
+    from oracle import c_oracle
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, batches, chunksize=1)
+    exp = c_oracle.run_pairs(ii, jj, pw, np.zeros(len(ii)), coords_sub, radii_sub, chrom_hap, ci.ptr,
+                             remap[ci.beads].astype(np.int32), it_corr, 2.0, 0 if mode == "LB" else 1)
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "first %d candidate pairs of the step's list, NumPy oracle port of get_actdist, "
-                      "fork pool of %d processes, batches of 1000; %.1f s" % (n, cores, dt),
-            "single_core_pairs_per_s": rate1}
+    ok = exp["o"] >= 0
+    equal = bool(np.array_equal(got["d2_sel_bits"][ok], exp["d2_sel_bits"][ok])
+                 and np.array_equal(got["contact_count"], exp["contact_count"])
+                 and np.array_equal(got["o"], exp["o"])
+                 and np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64))
+                 and np.array_equal(got["nrec"], exp["nrec"]))
+    return equal, dt
 
 
-def sample_population_host(eng_coords_t, beads):
-    return eng_coords_t[beads].cpu().numpy()
+def sub_population(coords_get, ci, nbead, haps):
+    """Host copies of the beads the loci `haps` touch + the bead remap."""
+    haps = np.unique(haps)
+    nc = ci.ptr[haps + 1] - ci.ptr[haps]
+    beads = np.unique(np.concatenate([ci.beads[ci.ptr[haps]], ci.beads[ci.ptr[haps[nc > 1]] + 1]]))
+    remap = -np.ones(nbead, np.int64)
+    remap[beads] = np.arange(len(beads))
+    return beads, remap, coords_get(beads)
+
+
+# ------------------------------------------------------------------- extras
+def extra_config3(args, rank, world, dev, local_rank, dist, torch):
+    """Config 3: 10 000 structures x 200 kb; ONE fixed list (every stored non-zero of the
+    synthetic matrix = all candidate pairs) split into contiguous 1/N shares (strong
+    scaling); results of all ranks gathered on every GPU."""
+    from igm_b200 import synthetic, _lib
+    from igm_b200.engine import ActdistEngine, launch_count
+    from igm_b200.dist import shard_bounds
+    nstruct = 10000
+    chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw, _ = build_index_and_pairs(200_000, 0.0, 0, args.max_pairs)
+    nbead, n_all = len(chrom_bead), len(ii)
+    radius = float(synthetic.bead_radius(nbead))
+    radii = np.full(nbead, radius, np.float32)
+    coords_t = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, nstruct, radius, SEED + 3, dev)
+    eng = ActdistEngine(nbead=nbead, nstruct=nstruct, device=local_rank)
+    eng.upload_coordinates(coords_t)
+    eng.set_index(ci.ptr, ci.beads, chrom_hap, radii)
+    per, bounds = shard_bounds(n_all, world)
+    lo, hi = bounds[rank]
+    n_mine = hi - lo
+    d_i = torch.from_numpy(ii[lo:hi]).to(dev)
+    d_j = torch.from_numpy(jj[lo:hi]).to(dev)
+    d_pw = torch.from_numpy(pw[lo:hi]).to(dev)
+    d_pl = torch.zeros(n_mine, dtype=torch.float64, device=dev)
+    gather = torch.zeros((world, per, 32), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.actdist_device(d_i, d_j, d_pw, d_pl, gather[rank], n_mine, 2.0, args.it_corr, args.mode, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gather.view(world * per, 32), gather[rank])
+    step()
+    torch.cuda.synchronize()
+    steps = 3
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 2)]
+    ev[0].record()
+    for k in range(steps):
+        ev[2 * k + 1].record()
+        eng.actdist_device(d_i, d_j, d_pw, d_pl, gather[rank], n_mine, 2.0, args.it_corr, args.mode, stream=stream)
+        ev[2 * k + 2].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gather.view(world * per, 32), gather[rank])
+    ev[-1].record()
+    torch.cuda.synchronize()
+    launches = launch_count() - l0
+    redo = eng.last_redo_count()
+    t = torch.tensor([ev[0].elapsed_time(ev[-1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    k_ms = float(np.mean([ev[2 * k + 1].elapsed_time(ev[2 * k + 2]) for k in range(steps)]))
+    out = None
+    if rank == 0:
+        value = n_all / (ms_per_step * 1e-3)
+        peak, _ = measured_peak_gbs()
+        alg = algorithmic_bytes(ci, ii[lo:hi], jj[lo:hi], nstruct)
+        # parity: a sample of EVERY rank's slice of rank 0's gathered buffer against the C oracle
+        rng = np.random.default_rng(3)
+        n_chk = 24000
+        sel = np.sort(np.concatenate([blo + rng.choice(bhi - blo, size=min(n_chk // world, bhi - blo), replace=False)
+                                      for blo, bhi in bounds if bhi > blo]))
+        rows = np.concatenate([r * per + (sel[(sel >= blo) & (sel < bhi)] - blo) for r, (blo, bhi) in enumerate(bounds)])
+        got = gather.view(world * per, 32)[torch.from_numpy(rows).to(dev)].cpu().numpy().reshape(-1).view(
+            _lib.PAIR_RESULT_DTYPE)
+        beads, remap, sub = sub_population(lambda b: coords_t[torch.from_numpy(b).to(dev)].cpu().numpy(), ci, nbead,
+                                           np.concatenate([ii[sel], jj[sel]]))
+        equal, dt_c = c_oracle_check(ii[sel], jj[sel], pw[sel], sub, radii[beads], chrom_hap, ci, remap,
+                                     args.it_corr, args.mode, got)
+        out = {"workload": "config 3: synthetic 10000-structure population at 200 kb male diploid (%d beads), Hi-C "
+                           "A-step (%s) over ONE fixed list of %d pairs (every stored non-zero of the synthetic "
+                           "matrix), contiguous 1/%d shares" % (nbead, args.mode, n_all, world),
+               "value": value, "unit": UNIT, "scaling": "strong", "n_gpus": world, "steps": steps,
+               "ms_per_step": ms_per_step, "pairs_total": n_all, "pairs_per_gpu": per,
+               "kernel_ms_rank0": k_ms, "gpu_launches": int(launches), "list_form_redo_pairs_rank0": redo,
+               "seconds_for_all_119M_haploid_pairs_at_this_rate": N_ALL_HAPLOID_PAIRS_200KB / value,
+               "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                            "traffic": measured_traffic(nstruct, n_mine, args.mode),
+                            "algorithmic_bytes_per_launch": alg},
+               "gather_parity_ok": equal, "parity_pairs_checked": int(len(sel)),
+               "parity_note": "sample of every rank's slice of rank 0's gathered buffer vs the C oracle (%.1f s)" % dt_c}
+    del coords_t, gather, d_i, d_j, d_pw, d_pl
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_config5(args, dev, local_rank, torch):
+    """Config 5: 1 000 structures x 50 kb (119 k beads), sigma = 0.01 list; rank 0, one GPU."""
+    from igm_b200 import synthetic, _lib
+    from igm_b200.engine import ActdistEngine
+    nstruct = 1000
+    chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw, _ = build_index_and_pairs(50_000, 0.01, 0, args.max_pairs)
+    nbead, n_pairs = len(chrom_bead), len(ii)
+    radius = float(synthetic.bead_radius(nbead))
+    radii = np.full(nbead, radius, np.float32)
+    coords_t = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, nstruct, radius, SEED + 5, dev)
+    eng = ActdistEngine(nbead=nbead, nstruct=nstruct, device=local_rank)
+    eng.upload_coordinates(coords_t)
+    eng.set_index(ci.ptr, ci.beads, chrom_hap, radii)
+    d_i, d_j, d_pw = (torch.from_numpy(x).to(dev) for x in (ii, jj, pw))
+    d_pl = torch.zeros(n_pairs, dtype=torch.float64, device=dev)
+    d_out = torch.zeros((n_pairs, 32), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.actdist_device(d_i, d_j, d_pw, d_pl, d_out, n_pairs, 2.0, args.it_corr, args.mode, stream=stream)
+    torch.cuda.synchronize()
+    steps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.actdist_device(d_i, d_j, d_pw, d_pl, d_out, n_pairs, 2.0, args.it_corr, args.mode, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    redo = eng.last_redo_count()
+    rng = np.random.default_rng(5)
+    sel = np.sort(rng.choice(n_pairs, size=min(20000, n_pairs), replace=False))
+    got = d_out[torch.from_numpy(sel).to(dev)].cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)
+    beads, remap, sub = sub_population(lambda b: coords_t[torch.from_numpy(b).to(dev)].cpu().numpy(), ci, nbead,
+                                       np.concatenate([ii[sel], jj[sel]]))
+    equal, _ = c_oracle_check(ii[sel], jj[sel], pw[sel], sub, radii[beads], chrom_hap, ci, remap, args.it_corr,
+                              args.mode, got)
+    peak, _ = measured_peak_gbs()
+    alg = algorithmic_bytes(ci, ii, jj, nstruct)
+    out = {"workload": "config 5: synthetic 1000-structure population at 50 kb male diploid (%d beads), Hi-C A-step "
+                       "(%s) over the sigma=0.01 list, %d pairs, 1 GPU" % (nbead, args.mode, n_pairs),
+           "value": n_pairs / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "ms_per_step": ms,
+           "pairs": n_pairs, "list_form_redo_pairs": redo,
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": measured_traffic(nstruct, n_pairs, args.mode)},
+           "parity_c_oracle_ok": equal, "parity_pairs_checked": int(len(sel))}
+    del coords_t, d_out
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_config4(eng, nbead, nstruct, rank, world, dev, dist, torch, coords_host, radius):
+    """Config 4: population contact-frequency counts (K2, igm-report path) for all bead
+    pairs of the config-2 population: block rows of the upper triangle dealt to the ranks
+    (no collective: tiles are independent)."""
+    from igm_b200.contact import row_blocks
+    from igm_b200.engine import launch_count
+    B = 4096
+    out = torch.zeros((B, nbead), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    mine = row_blocks(nbead, B, rank, world)
+    eng.contact_counts_device(0, min(B, nbead), 0, min(B, nbead), out, 2.0, False, stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = launch_count()
+    e0.record()
+    pairs = 0
+    for _ in range(reps):
+        pairs = 0
+        for r0, r1 in mine:
+            eng.contact_counts_device(r0, r1 - r0, r0, nbead - r0, out, 2.0, False, stream)
+            pairs += (r1 - r0) * (nbead - r0)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1) / reps, float(pairs)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms, pairs = float(tmax[0].item()), int(t[1].item())
+    if rank != 0:
+        return None
+    ops = pairs * nstruct
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count * world
+    peak = sms * 128 * 1.965e9
+    res = {"workload": "config 4: contact-frequency counts (K2) of the config-2 population, all %d x %d bead pairs "
+                       "(upper triangle at block granularity, %d block rows of %d) x %d structures" % (
+                           nbead, nbead, (nbead + B - 1) // B, B, nstruct),
+           "metric": "contact-frequency bead-pair-structs/s", "value": ops / (ms * 1e-3), "ms": ms, "n_gpus": world,
+           "bead_pairs": pairs, "gpu_launches_rank0": int(launches), "reps": reps,
+           "roofline": {"bound": "fp32-lanes", "achieved_laneops_per_s": 9 * ops / (ms * 1e-3),
+                        "peak_laneops_per_s": peak, "frac": 9 * ops / (ms * 1e-3) / peak,
+                        "note": "9 lane-operations per bead pair and structure (8 non-FMA float32 + 1 compare); "
+                                "peak = SMs x 128 lanes x 1965 MHz"},
+           "parity": "unpinned against alabtools (not in the reference tree); sample checked against "
+                     "oracle/contact_oracle.py"}
+    if coords_host is not None:
+        from oracle import contact_oracle as co
+        got = torch.zeros((64, 64), dtype=torch.int32, device=dev)
+        eng.contact_counts_device(0, 64, 0, 64, got, 2.0, False, stream)
+        torch.cuda.synchronize()
+        exp = co.contact_counts_fast(np.ascontiguousarray(coords_host[:64]), np.full(64, radius, np.float32),
+                                     np.arange(64), np.arange(64))
+        res["parity_sample_ok"] = bool(np.array_equal(got.cpu().numpy().astype(np.uint32), exp))
+    return res
 
 
 # ------------------------------------------------------------------- main
@@ -241,21 +493,34 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw = build_index_and_pairs(args, rank)
+    chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw, _ = build_index_and_pairs(
+        args.resolution, args.sigma, rank, args.max_pairs)
     nbead = len(chrom_bead)
     n_pairs = len(ii)
     radius = float(synthetic.bead_radius(nbead))
     radii = np.full(nbead, radius, np.float32)
 
-    # population: generated on the device, then staged into the engine's layout
-    coords_t = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, args.nstruct, radius,
-                                                       SEED, dev)
+    # population: seeded NumPy generator (same coordinates as the reference arm) in pinned
+    # host memory; larger populations (debug runs with --nstruct) are generated on the device
+    host_pop = args.nstruct <= 2000
+    coords_np = None
+    if host_pop:
+        coords_h = torch.from_numpy(host_population(chrom_bead, copy_bead, args.nstruct, radius)).pin_memory()
+        coords_np = coords_h.numpy()
+
+        def coords_get(beads):
+            return coords_np[beads]
+    else:
+        coords_t = synthetic.random_walk_coordinates_torch(chrom_bead, copy_bead, args.nstruct, radius, SEED, dev)
+        coords_h = None
+
+        def coords_get(beads):
+            return coords_t[torch.from_numpy(beads).to(dev)].cpu().numpy()
     eng = ActdistEngine(nbead=nbead, nstruct=args.nstruct, device=local_rank)
-    eng.upload_coordinates(coords_t)
+    eng.upload_coordinates(coords_h if host_pop else coords_t)
     eng.set_index(ci.ptr, ci.beads, chrom_hap, radii)
 
-    # device-resident inputs; results land directly in this rank's slice of the
-    # all-gather buffer (in-place NCCL all-gather)
+    # device-resident inputs; results land directly in this rank's slice of the gather buffer
     d_i = torch.from_numpy(ii).to(dev)
     d_j = torch.from_numpy(jj).to(dev)
     d_pw = torch.from_numpy(pw).to(dev)
@@ -264,8 +529,8 @@ def main():
     mine = gather[rank]
     stream = torch.cuda.current_stream().cuda_stream
 
-    # N > 1: the kernel stores its results straight into every GPU's gather buffer
-    # over NVLink (peer-mapped memory); NCCL all-gather is the fallback
+    # N > 1: the kernel stores its (finished) records straight into every GPU's gather
+    # buffer over NVLink (peer-mapped memory); NCCL all-gather is the fallback
     from igm_b200.dist import PeerGather, peer_gather_available
     pg = None
     if world > 1 and peer_gather_available(world):
@@ -283,13 +548,13 @@ def main():
     def step():
         if pg is not None:
             return pg.step(eng, d_i, d_j, d_pw, d_pl, n_pairs, 2.0, args.it_corr, args.mode, stream)
-        eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode,
-                           stream=stream)
+        eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode, stream=stream)
         if world > 1:
             dist.all_gather_into_tensor(gather.view(world * n_pairs, 32), mine)
         return gather
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
 
@@ -315,11 +580,9 @@ def main():
                                      args.it_corr, args.mode, stream)
             ev[2 * k + 2].record()
             pg.hdls[b].barrier()
-            eng.finish_results(pg.bufs[b], world * n_pairs, stream)
             last = pg.bufs[b]
         else:
-            eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode,
-                               stream=stream)
+            eng.actdist_device(d_i, d_j, d_pw, d_pl, mine, n_pairs, 2.0, args.it_corr, args.mode, stream=stream)
             ev[2 * k + 2].record()
             if world > 1:
                 dist.all_gather_into_tensor(gather.view(world * n_pairs, 32), mine)
@@ -371,18 +634,15 @@ def main():
         sweep["sweep_pairs_per_s"] = tot_pairs / (tot_ms * 1e-3)
         del pm_s
 
-    # ---- parity gate inside the bench: a sample of pairs against the oracle
-    parity = None
+    # ---- parity gates inside the bench (rank 0): the NumPy oracle on a sample of the own slice,
+    # and - N > 1 - the C oracle on a sample of EVERY rank's slice of rank 0's gathered buffer
+    parity, gather_parity = None, None
     if rank == 0:
         from oracle import actdist_oracle as orc
         rng = np.random.default_rng(1)
         sel = np.sort(rng.choice(n_pairs, size=min(300, n_pairs), replace=False))
         got = last[rank].cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)[sel]
-        hap_needed = np.unique(np.concatenate([ii[sel], jj[sel]]))
-        beads = np.unique(np.concatenate([ci[h] for h in hap_needed]))
-        remap = -np.ones(nbead, np.int64)
-        remap[beads] = np.arange(len(beads))
-        sub_coords = coords_t[torch.from_numpy(beads).to(dev)].cpu().numpy()
+        beads, remap, sub_coords = sub_population(coords_get, ci, nbead, np.concatenate([ii[sel], jj[sel]]))
 
         class _CI:
             def __getitem__(self, i):
@@ -395,9 +655,24 @@ def main():
                       and np.array_equal(got["contact_count"], exp["contact_count"])
                       and np.array_equal(got["o"], exp["o"])
                       and np.array_equal(got["p"].view(np.uint64), exp["p"].view(np.uint64)))
+        if world > 1:
+            from oracle import c_oracle
+            if c_oracle.available():
+                oks, checked = [], 0
+                for r in range(world):
+                    _, _, _, _, ri, rj, rp, _ = build_index_and_pairs(args.resolution, args.sigma, r, args.max_pairs)
+                    s2 = np.sort(rng.choice(n_pairs, size=min(4000, n_pairs), replace=False))
+                    g2 = last[r][torch.from_numpy(s2).to(dev)].cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)
+                    b2, rm2, sc2 = sub_population(coords_get, ci, nbead, np.concatenate([ri[s2], rj[s2]]))
+                    eq, _ = c_oracle_check(ri[s2], rj[s2], rp[s2], sc2, radii[b2], chrom_hap, ci, rm2, args.it_corr,
+                                           args.mode, g2)
+                    oks.append(eq)
+                    checked += len(s2)
+                gather_parity = {"ok": bool(all(oks)), "per_rank": oks, "pairs_checked": checked,
+                                 "note": "sample of every rank's slice of rank 0's gathered buffer vs the C oracle"}
 
-    # ---- e2e: C-ABI host entry point, pinned host buffers, copies inside
-    e2e = None
+    # ---- e2e: C-ABI host entry points, pinned host buffers, copies inside the timed region
+    e2e = e2e_pairs = None
     if not args.no_e2e:
         h_i = torch.from_numpy(ii).pin_memory()
         h_j = torch.from_numpy(jj).pin_memory()
@@ -406,26 +681,64 @@ def main():
         h_out = torch.zeros(n_pairs * 32, dtype=torch.uint8).pin_memory()
         lib = _lib.load()
 
-        def e2e_step():
+        def e2e_step(with_population):
+            if with_population:
+                _lib.check(lib.igmk_upload_coords(eng._ctx, coords_h.data_ptr(), 0))
             _lib.check(lib.igmk_actdist_host(eng._ctx, n_pairs, h_i.data_ptr(), h_j.data_ptr(),
                                              h_pw.data_ptr(), h_pl.data_ptr(), 2.0, args.it_corr,
                                              0 if args.mode == "LB" else 1, 0, h_out.data_ptr()))
-        for _ in range(2):
-            e2e_step()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        dt = time.perf_counter() - t0
-        sampler.mark_stop()      # the clock samples cover both timed regions
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {"value": world * n_pairs * args.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(n_pairs * 24), "d2h_bytes_per_step": int(n_pairs * 32),
-               "api": "igmk_actdist_host (C ABI) with pinned host buffers"}
+
+        def timed(with_population):
+            for _ in range(2):
+                e2e_step(with_population)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step(with_population)
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        dt = timed(False)
+        e2e_pairs = {"value": world * n_pairs * args.steps / dt, "unit": UNIT,
+                     "h2d_bytes_per_step": int(n_pairs * 24), "d2h_bytes_per_step": int(n_pairs * 32),
+                     "api": "igmk_actdist_host (C ABI), pinned host buffers, population resident in HBM"}
+        if host_pop:
+            dt = timed(True)
+            e2e = {"value": world * n_pairs * args.steps / dt, "unit": UNIT,
+                   "h2d_bytes_per_step": int(n_pairs * 24 + coords_h.numel() * 4),
+                   "d2h_bytes_per_step": int(n_pairs * 32),
+                   "api": "igmk_upload_coords + igmk_actdist_host (C ABI), pinned host buffers: the population "
+                          "(%.0f MB) is staged again every step, as after an M-step" % (coords_h.numel() * 4 / 1e6)}
+        else:
+            e2e = e2e_pairs
+        sampler.mark_stop()      # the clock samples cover the timed regions
+
+    # ---- the other configs of BASELINE.json, same run, outside the timed regions
+    extra = {}
+    if not args.no_extras and not args.max_pairs and args.nstruct == 1000 and args.resolution == 200_000:
+        want = set(args.extras.split(","))
+        if "4" in want:
+            try:
+                r4 = extra_config4(eng, nbead, args.nstruct, rank, world, dev, dist, torch, coords_np, radius)
+                if rank == 0:
+                    extra["config4_contact"] = r4
+            except Exception as e:
+                extra["config4_contact"] = {"error": repr(e)}
+        if "3" in want:
+            try:
+                r3 = extra_config3(args, rank, world, dev, local_rank, dist, torch)
+                if rank == 0:
+                    extra["config3"] = r3
+            except Exception as e:
+                extra["config3"] = {"error": repr(e)}
+        if "5" in want and world == 1:
+            try:
+                extra["config5"] = extra_config5(args, dev, local_rank, torch)
+            except Exception as e:
+                extra["config5"] = {"error": repr(e)}
 
     if rank == 0:
         time.sleep(0.1)
@@ -434,38 +747,43 @@ def main():
         alg = algorithmic_bytes(ci, ii, jj, args.nstruct)
         k_ms = float(np.mean(kernel_ms))
         achieved = alg / (k_ms * 1e-3) / 1e9
+        kname = "actdist_list_warp_kernel + key-array redo launch" if args.nstruct <= 1024 else \
+            "actdist_list_block_kernel + key-array redo launch"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": "%s: synthetic %d-structure population at %d kb male diploid "
                             "(%d beads), Hi-C A-step (%s) over the sigma=%g candidate list, "
-                            "%d pairs per GPU" % (config_name(args), args.nstruct, args.resolution // 1000,
-                                                  nbead, args.mode, args.sigma, n_pairs),
+                            "%d pairs per GPU" % (config_name(args.resolution, args.nstruct), args.nstruct,
+                                                  args.resolution // 1000, nbead, args.mode, args.sigma, n_pairs),
                 "pairs_per_gpu": n_pairs, "nstruct": args.nstruct, "nbead": nbead,
                 "pair_structs_per_s": value * args.nstruct,
+                "population": "seeded NumPy generator (same coordinates as --impl reference)" if host_pop
+                              else "torch generator on the device",
                 "parallelism": "pairs sharded over %d GPU(s), coordinates replicated, %s" % (
-                    world, "results stored into every GPU's gather buffer from inside the kernel "
+                    world, "finished records stored into every GPU's gather buffer from inside the kernel "
                     "(NVLink peer stores) + one barrier" if pg is not None else
                     "one NCCL all-gather of results"),
                 "l2": "inputs larger than L2 (coordinates %.0f MB, pair list %.0f MB)" % (
                     nbead * 3 * eng.nstruct * 4 / 1e6, n_pairs * 24 / 1e6),
                 "parity_sample_ok": parity,
+                "gather_parity": gather_parity,
                 "list_form_redo_pairs": redo_pairs,
                 "sigma_sweep": sweep,
+                "extra": extra,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          "traffic": measured_traffic(args.nstruct, n_pairs, args.mode),
-                         "kernel": "actdist_warp_kernel" if args.nstruct <= 1024 else "actdist_block_kernel",
-                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
+                         "kernel": kname, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
                          "peak_source": peak_src},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
-        # what actually limits the kernel: the issue slots it uses,
-        # from the warp-instruction count of the committed ncu capture and the live kernel time
+        # what actually limits the kernel: the issue slots it uses and the
+        # L1 / shared-memory data pipe, from the committed ncu capture rescaled to the live time
         winst = measured_traffic(args.nstruct, n_pairs, args.mode, "warp_instructions_per_launch")
         sm_mhz = line["clocks"].get("sm_mhz") or 1965.0
         if winst:
@@ -475,53 +793,40 @@ def main():
                 "achieved_winst_per_s": winst / (k_ms * 1e-3),
                 "peak_winst_per_s": sms * 4 * sm_mhz * 1e6,
                 "frac": winst / (k_ms * 1e-3) / (sms * 4 * sm_mhz * 1e6),
-                "note": "issue slots used (4 schedulers per SM at the sampled SM clock); the kernel is latency-bound"}
-        # ... and the unit it keeps busiest: the L1 / shared-memory data pipe (LSU wavefronts,
-        # 128 bytes per clock per SM) - ncu figure of the committed capture, rescaled to the
-        # live kernel time
+                "note": "issue slots used (4 schedulers per SM at the sampled SM clock)"}
         l1pct = measured_traffic(args.nstruct, n_pairs, args.mode, "l1tex_lsu_data_pipe_pct")
         ms_ncu = measured_traffic(args.nstruct, n_pairs, args.mode, "kernel_ms_under_ncu")
         if l1pct and ms_ncu:
             line["roofline"]["l1tex"] = {
                 "lsu_data_pipe_frac": l1pct / 100.0 * ms_ncu / k_ms,
                 "lsu_data_pipe_frac_under_ncu": l1pct / 100.0, "kernel_ms_under_ncu": ms_ncu,
-                "note": "l1tex__data_pipe_lsu_wavefronts: coordinate loads, tile and key-array traffic"}
+                "note": "l1tex__data_pipe_lsu_wavefronts: coordinate loads, tile and list traffic"}
         if e2e is not None:
             line["e2e"] = e2e
+            line["e2e_pairs_only"] = e2e_pairs
         if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only
-            # bounded CPU sample (about --cpu-seconds of work on all host cores):
-            # needs host copies of the beads the sample touches
-            nb = 320000
-            hap_needed = np.unique(np.concatenate([ii[:nb * 8], jj[:nb * 8]]))
-            beads = np.unique(np.concatenate([ci[h] for h in hap_needed]))
-            remap = -np.ones(nbead, np.int64)
-            remap[beads] = np.arange(len(beads))
-            sub = coords_t[torch.from_numpy(beads).to(dev)].cpu().numpy()
+            # bounded CPU sample (about --cpu-seconds of work on all host cores): the reference's
+            # own get_actdist on the leading slice of the same list, same population
+            nb = min(n_pairs, 1_000_000)
+            beads, remap, sub = sub_population(coords_get, ci, nbead, np.concatenate([ii[:nb], jj[:nb]]))
 
             class _CI2:
                 def __getitem__(self, i):
                     return [int(remap[b]) for b in ci[i]]
-            line["cpu_baseline"] = cpu_baseline(sub, radii[beads], chrom_hap, _CI2(), ii[:nb * 8],
-                                                jj[:nb * 8], pw[:nb * 8], args.it_corr, args.mode,
-                                                args.cpu_seconds)
-            # second CPU figure and a much larger parity gate: the plain-C oracle (OpenMP,
-            # all host threads) over the same sample, compared with the GPU results of the
-            # last timed step pair by pair
+            try:
+                line["cpu_baseline"] = cpu_reference_rate(sub, radii[beads], chrom_hap, _CI2(), ii[:nb], jj[:nb],
+                                                          pw[:nb], args.it_corr, args.mode, args.cpu_seconds)
+            except Exception as e:                       # no copy of the reference on this box
+                line["cpu_baseline"] = {"unavailable": repr(e)}
+            # second CPU figure and a much larger parity gate: the plain-C oracle (OpenMP, all
+            # host threads) over the first 1 M pairs, compared with the GPU results of the last
+            # timed step pair by pair
             from oracle import c_oracle
             if c_oracle.available():
-                n_c = int(min(len(ii), nb * 8, 1_000_000))
-                t0 = time.perf_counter()
-                exp_c = c_oracle.run_pairs(ii[:n_c], jj[:n_c], pw[:n_c], np.zeros(n_c), sub, radii[beads],
-                                           chrom_hap, ci.ptr, remap[ci.beads].astype(np.int32),
-                                           args.it_corr, 2.0, 0 if args.mode == "LB" else 1)
-                dt_c = time.perf_counter() - t0
+                n_c = int(nb)
                 got_c = last[rank][:n_c].cpu().numpy().reshape(-1).view(_lib.PAIR_RESULT_DTYPE)
-                ok = exp_c["o"] >= 0
-                equal = bool(np.array_equal(got_c["d2_sel_bits"][ok], exp_c["d2_sel_bits"][ok])
-                             and np.array_equal(got_c["contact_count"], exp_c["contact_count"])
-                             and np.array_equal(got_c["o"], exp_c["o"])
-                             and np.array_equal(got_c["p"].view(np.uint64), exp_c["p"].view(np.uint64))
-                             and np.array_equal(got_c["nrec"], exp_c["nrec"]))
+                equal, dt_c = c_oracle_check(ii[:n_c], jj[:n_c], pw[:n_c], sub, radii[beads], chrom_hap, ci, remap,
+                                             args.it_corr, args.mode, got_c)
                 line["cpu_baseline"]["c_port"] = {
                     "value": n_c / dt_c, "unit": UNIT, "cores": os.cpu_count() or 1,
                     "sample": "first %d pairs, oracle/actdist_oracle.c with OpenMP; %.1f s" % (n_c, dt_c),
@@ -536,73 +841,87 @@ def main():
 
 
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (oracle
-    port of get_actdist; the reference itself is Python and needs alabtools/h5py
-    to run end to end) on the host cores, same config/metric; bounded sample per
-    step.  Under torchrun only rank 0 works."""
+    """--impl reference: the reference's own CPU implementation of the path - its
+    unmodified get_actdist (igm/steps/ActivationDistanceStep.py:336-485, imported from the
+    reference tree or from the copy `make -C oracle` left in oracle/_ref) - on the host
+    cores, SAME population (seeded NumPy generator) and SAME list as the GPU arm; each
+    step is a bounded leading slice of that list.  Under torchrun only rank 0 works.
+    The product library is not loaded by this arm."""
     if rank != 0:
         return
     from igm_b200 import synthetic
-    chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw = build_index_and_pairs(args, 0)
+    chrom_hap, chrom_bead, copy_bead, ci, ii, jj, pw, _ = build_index_and_pairs(
+        args.resolution, args.sigma, 0, args.max_pairs, native=False)
     nbead = len(chrom_bead)
     radius = float(synthetic.bead_radius(nbead))
-    cores = os.cpu_count() or 1
-    # bounded sample: pairs of the first rows of the list; only their beads are generated
-    n_sample = int(min(len(ii), 25000 * cores))
-    si, sj, spw = ii[:n_sample], jj[:n_sample], pw[:n_sample]
-    hap_needed = np.unique(np.concatenate([si, sj]))
-    beads = np.unique(np.concatenate([ci[h] for h in hap_needed]))
-    remap = -np.ones(nbead, np.int64)
-    remap[beads] = np.arange(len(beads))
-    rng = np.random.default_rng(SEED)
-    sub = synthetic.random_walk_coordinates(chrom_bead[beads], copy_bead[beads], args.nstruct,
-                                            radius, rng)
-
-    class _CI:
-        def __getitem__(self, i):
-            return [int(remap[b]) for b in ci[i]]
-    radii = np.full(len(beads), radius, np.float32)
-    per_step, per_ms = [], []
-    info = None
-    for k in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        info = cpu_baseline(sub, radii, chrom_hap, _CI(), si, sj, spw, args.it_corr, args.mode,
-                            max(2.0, args.cpu_seconds / max(1, args.steps)))
-        if k >= args.warmup:
-            per_step.append(info["value"])
-            per_ms.append((time.perf_counter() - t0) * 1e3)
-    value = float(np.mean(per_step))
-    # for context: the plain-C oracle (OpenMP) on the same sample
-    c_port = None
+    coords = host_population(chrom_bead, copy_bead, args.nstruct, radius)
+    radii = np.full(nbead, radius, np.float32)
+    steps = max(1, args.steps)
+    budget = max(1.0, min(args.cpu_seconds, 120.0 / (steps + args.warmup)))
+    kind = "reference"
     try:
-        from oracle import c_oracle
-        if c_oracle.available():
-            n_c = int(min(len(si), 400000))
-            t0 = time.perf_counter()
-            c_oracle.run_pairs(si[:n_c], sj[:n_c], spw[:n_c], np.zeros(n_c), sub, radii, chrom_hap, ci.ptr,
-                               remap[ci.beads].astype(np.int32), args.it_corr, 2.0,
-                               0 if args.mode == "LB" else 1)
-            c_port = {"value": n_c / (time.perf_counter() - t0), "unit": UNIT, "cores": cores,
-                      "sample": "first %d pairs, oracle/actdist_oracle.c with OpenMP" % n_c}
-    except Exception as e:          # the C oracle is optional here
-        c_port = {"unavailable": str(e)}
+        info = cpu_reference_rate(coords, radii, chrom_hap, ci, ii, jj, pw, args.it_corr, args.mode, budget,
+                                  steps=steps, warmup=args.warmup)
+    except Exception as e:
+        sys.stderr.write("reference copy unavailable (%r); timing the oracle port instead\n" % (e,))
+        info = port_rate(coords, radii, chrom_hap, ci, ii, jj, pw, args.it_corr, args.mode, budget, steps, args.warmup)
+        kind = "port"
+    value = info["value"]
+    loaded = sorted(set(l.split()[-1] for l in open("/proc/self/maps") if ".so" in l and ROOT in l)) \
+        if os.path.exists("/proc/self/maps") else []
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(per_ms)),
+        "steps": steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
         "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: synthetic %d-structure population at %d kb male diploid "
                                "(%d beads), Hi-C A-step (%s) over the sigma=%g candidate list; "
-                               "bounded CPU sample per step" % (config_name(args), args.nstruct,
-                                                                args.resolution // 1000,
-                                                                nbead, args.mode, args.sigma),
-                   "nstruct": args.nstruct, "nbead": nbead},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
-                         "sample": info["sample"], "c_port": c_port},
+                               "bounded CPU sample per step (leading slice of the same list, same "
+                               "population as the GPU arm)" % (config_name(args.resolution, args.nstruct),
+                                                               args.nstruct, args.resolution // 1000,
+                                                               nbead, args.mode, args.sigma),
+                   "nstruct": args.nstruct, "nbead": nbead, "pairs_in_list": int(len(ii)),
+                   "population": "seeded NumPy generator (same coordinates as the GPU arm)",
+                   "repo_native_libraries_loaded": [os.path.relpath(p, ROOT) for p in loaded]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": kind,
+                         "sample": info["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def _port_worker(sl):
+    from oracle import actdist_oracle as orc
+    ii, jj, pw, coords, radii, chrom_hap, ci, it_corr, mode = _G["p"]
+    a, b = sl
+    recs, _ = orc.run_pairs(ii[a:b], jj[a:b], pw[a:b], np.zeros(b - a), coords, radii, chrom_hap, ci, it_corr, 2.0, mode)
+    return len(recs)
+
+
+def port_rate(coords, radii, chrom_hap, ci, ii, jj, pw, it_corr, mode, budget_s, steps, warmup):
+    """Fallback of the reference arm when neither /root/reference nor oracle/_ref/igm exists:
+    the NumPy restatement (oracle/actdist_oracle.py), same pool / batch structure."""
+    import multiprocessing as mp
+    from oracle import actdist_oracle as orc
+    cores = os.cpu_count() or 1
+    _G["p"] = (ii, jj, pw, coords, radii, chrom_hap, ci, it_corr, orc.MODE_LB if mode == "LB" else orc.MODE_GP)
+    t0 = time.perf_counter()
+    _port_worker((0, min(200, len(ii))))
+    rate1 = min(200, len(ii)) / (time.perf_counter() - t0)
+    n = int(min(len(ii), max(1000, rate1 * cores * budget_s * 0.6)))
+    batches = [(a, min(n, a + 1000)) for a in range(0, n, 1000)]
+    rates, ms = [], []
+    with mp.get_context("fork").Pool(cores) as pool:
+        for k in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_port_worker, batches, chunksize=1)
+            dt = time.perf_counter() - t0
+            if k >= warmup:
+                rates.append(n / dt)
+                ms.append(dt * 1e3)
+    return {"value": float(np.mean(rates)), "cores": cores, "ms_per_step": float(np.mean(ms)),
+            "sample": "first %d candidate pairs, NumPy oracle port of get_actdist, fork pool of %d processes" % (n, cores)}
 
 
 if __name__ == "__main__":

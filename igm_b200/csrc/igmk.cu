@@ -67,6 +67,7 @@ struct igmk_ctx {
     std::vector<cudaEvent_t> ev_in, ev_k;
     long long host_slice_pairs = 1 << 19;             // IGMK_HOST_SLICE
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr};   // coordinate upload: copy done x2, kernel done x2
     float last_kernel_ms = 0.f;
     int group_threads = 0;       // IGMK_GROUP_THREADS
     int warps_per_cta = 0;       // IGMK_WARPS_PER_CTA
@@ -189,6 +190,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_redo);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_up) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -215,25 +217,42 @@ extern "C" int igmk_upload_coords_range(igmk_ctx* c, const float* xyz, int bead0
     if (bead0 < 0 || nb < 0 || bead0 + nb > c->nbead) return fail(IGMK_EINVAL, "igmk_upload_coords: bead range out of bounds");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t per_bead = (size_t)c->nstruct * 3 * sizeof(float);
-    // stage at most 256 MiB at a time
-    int step = (int)((256ull << 20) / per_bead);
-    if (step < 1) step = 1;
-    for (int b = 0; b < nb; b += step) {
-        const int n = (nb - b < step) ? nb - b : step;
-        const float* src = xyz + (size_t)b * c->nstruct * 3;
-        const float* dsrc = src;
-        if (!on_device) {
-            int rc = ensure(&c->d_stage, &c->stage_bytes, (size_t)n * per_bead);
-            if (rc) return rc;
-            CUDA_TRY(cudaMemcpyAsync(c->d_stage, src, (size_t)n * per_bead, cudaMemcpyHostToDevice, c->stream));
-            dsrc = (const float*)c->d_stage;
-        }
-        stage_coords_kernel<<<n, 256, 0, c->stream>>>(dsrc, c->d_coords + (size_t)(bead0 + b) * 3 * c->npad,
-                                                     c->nstruct, c->npad);
+    if (on_device) {
+        // already in HBM: one re-layout launch per 2^30 beads-worth of grid
+        stage_coords_kernel<<<nb, 256, 0, c->stream>>>(xyz, c->d_coords + (size_t)bead0 * 3 * c->npad, c->nstruct, c->npad);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->have_coords = true;
+        return IGMK_OK;
     }
+    // Host memory: two staging buffers of <= 64 MiB; the copy of chunk k + 1 (copy-in
+    // stream) overlaps the re-layout kernel of chunk k (compute stream).  Pinned host
+    // memory (igmk_host_alloc, torch pin_memory) makes the copies asynchronous.
+    int step = (int)((64ull << 20) / per_bead);
+    if (step < 1) step = 1;
+    if (step > nb) step = nb;
+    if (nb == 0) { c->have_coords = true; return IGMK_OK; }
+    int rc = ensure(&c->d_stage, &c->stage_bytes, 2 * (size_t)step * per_bead);
+    if (rc) return rc;
+    if (!c->ev_up[0]) {
+        for (int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming));
+    }
+    int k = 0;
+    for (int b = 0; b < nb; b += step, ++k) {
+        const int n = (nb - b < step) ? nb - b : step;
+        float* buf = (float*)((char*)c->d_stage + (size_t)(k & 1) * step * per_bead);
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_up[2 + (k & 1)], 0));     // the kernel that read this buffer
+        CUDA_TRY(cudaMemcpyAsync(buf, xyz + (size_t)b * c->nstruct * 3, (size_t)n * per_bead, cudaMemcpyHostToDevice, c->s_in));
+        CUDA_TRY(cudaEventRecord(c->ev_up[k & 1], c->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_up[k & 1], 0));
+        stage_coords_kernel<<<n, 256, 0, c->stream>>>(buf, c->d_coords + (size_t)(bead0 + b) * 3 * c->npad,
+                                                     c->nstruct, c->npad);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->ev_up[2 + (k & 1)], c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->have_coords = true;
     return IGMK_OK;
 }

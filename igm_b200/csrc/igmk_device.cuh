@@ -333,7 +333,19 @@ __device__ __forceinline__ void emit_result(const ActdistParams& P, int tid, lon
     if (P.n_peers == 0) {
         if (tid == 0) write_result(P.out + pair, d, d2_bits, count, o, p, extra);
     } else if (tid < P.n_peers) {
-        write_result(reinterpret_cast<igmk_pair_result*>(__ldg(P.peers + tid)) + pair, d, d2_bits, count, o, p, extra);
+        // records that travel to the peers are finished here (dist / prob: the 4-decimal text
+        // round trip), so no GPU has to re-finish the other ranks' slices after the gather
+        float dist = 0.f, prob = 0.f;
+        if (o >= 0) {
+            dist = round4_to_f32(sqrt((double)__uint_as_float(d2_bits)));   // float64 sqrt (:473)
+            prob = round4_to_f32(p);
+        }
+        const int nrec = (o >= 0 || d.always_rec) ? d.nrec : 0;
+        const long long pb = __double_as_longlong(p);
+        st_global_256(reinterpret_cast<igmk_pair_result*>(__ldg(P.peers + tid)) + pair,
+                      d2_bits, (uint32_t)count, (uint32_t)o, (uint32_t)nrec,
+                      (uint32_t)(pb & 0xffffffffll), (uint32_t)((unsigned long long)pb >> 32),
+                      __float_as_uint(dist), __float_as_uint(prob));
     }
 }
 

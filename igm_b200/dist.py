@@ -61,8 +61,8 @@ class PeerGather:
     Every rank owns `nbuf` buffers of shape (world, per, 32) uint8 in peer-mapped
     ("symmetric") device memory.  igmk_actdist_device_peers stores each raw pair
     result of rank r into slice [r] of the current buffer of EVERY rank from inside
-    the kernel, so by the time the kernel ends the all-gather has already happened;
-    what is left is one cross-rank barrier and the per-GPU finish pass (dist / prob).
+    the kernel - finished, dist / prob included - so by the time the kernel ends the
+    all-gather has already happened; what is left is one cross-rank barrier.
     Alternating between two buffers makes that single barrier per step sufficient:
     a rank can only start writing buffer b again after every rank has passed the
     barrier of the step that last read it.
@@ -97,15 +97,14 @@ class PeerGather:
 
     def step(self, eng, d_i, d_j, d_pw, d_pl, n_pairs: int, contact_range=2.0, it_corr=0, mode="LB",
              stream: int = 0):
-        """One sharded A-step: kernel with peer stores -> barrier -> finish.  Returns
+        """One sharded A-step: kernel with peer stores -> barrier.  Returns
         the (world, per, 32) uint8 tensor holding every rank's results (valid once the
         stream has been synchronised)."""
         b = self.k % len(self.bufs)
         self.k += 1
         eng.actdist_device_peers(d_i, d_j, d_pw, d_pl, self.peer_slices[b], self.world, n_pairs,
                                  contact_range, it_corr, mode, stream)
-        self.hdls[b].barrier()
-        eng.finish_results(self.bufs[b], self.world * self.per, stream)
+        self.hdls[b].barrier()           # the records arrive finished (dist / prob filled in by the kernel)
         return self.bufs[b]
 
 

@@ -116,8 +116,8 @@ int64_t igmk_last_redo_count(igmk_ctx* ctx);
  * kernel, so the all-gather overlaps the compute and no collective follows).
  * d_peer_slices: device array of n_peers addresses - where THIS rank's slice of
  * igmk_pair_result records starts in GPU p's gather buffer (peer-mapped memory,
- * e.g. torch symmetric memory).  dist / prob are NOT filled in: after a barrier
- * across ranks every GPU calls igmk_finish_results_device on its whole buffer. */
+ * e.g. torch symmetric memory).  The records arrive finished (dist / prob filled in by
+ * the kernel); what remains after the launch is one barrier across the ranks. */
 int igmk_actdist_device_peers(igmk_ctx* ctx, int64_t n_pairs,
                               const int32_t* d_i, const int32_t* d_j,
                               const double* d_pwish, const double* d_plast,
