@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libigmk.so")
 SOURCES = ["igmk.cu"]
-HEADERS = ["igmk_device.cuh", "igmk_actdist.cuh", "igmk_actdist_list.cuh", "igmk_contact.cuh", "igmk_restraint.cuh", "igmk_sprite.cuh",
+HEADERS = ["igmk_device.cuh", "igmk_actdist.cuh", "igmk_actdist_list.cuh", "igmk_actdist_slab.cuh", "igmk_contact.cuh", "igmk_restraint.cuh", "igmk_sprite.cuh",
            "igmk_rank.cuh", "../../include/igmk.h"]
 
 NVCC_FLAGS = [

@@ -19,6 +19,7 @@
 #include "../../include/igmk.h"
 #include "igmk_actdist.cuh"
 #include "igmk_actdist_list.cuh"
+#include "igmk_actdist_slab.cuh"
 #include "igmk_contact.cuh"
 #include "igmk_restraint.cuh"
 #include "igmk_sprite.cuh"
@@ -83,6 +84,8 @@ struct igmk_ctx {
                                  // residency: config 5 +4 %; config 2 -1 %)
     int list_form = 1;           // IGMK_LIST: 1 = list form first, key-array kernels for what it hands back; 0 = key arrays only
     float list_z = 1.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
+    int slab_form = 1;           // IGMK_SLAB: populations > 1024 structures run the list form slab by slab (0: one CTA per pair)
+    void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch
     int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
     float list_budget = 16.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
     void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
@@ -164,6 +167,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov) c->list_form = atoi(ov);
     ov = getenv("IGMK_LIST_Z");
     if (ov) c->list_z = (float)atof(ov);
+    ov = getenv("IGMK_SLAB");
+    if (ov) c->slab_form = atoi(ov);
     ov = getenv("IGMK_LIST_TILE_SLOTS");
     if (ov) c->list_tile_slots = atoi(ov);
     ov = getenv("IGMK_LIST_BUDGET");
@@ -188,6 +193,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_pairs);
     cudaFree(c->d_order);
     cudaFree(c->d_redo);
+    cudaFree(c->d_slab);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_up) if (e) cudaEventDestroy(e);
@@ -435,6 +441,52 @@ static int launch_list_block(igmk_ctx* c, ActdistParams P, int threads, cudaStre
     return IGMK_OK;
 }
 
+// Populations of more than 1024 structures: sample / fill / select kernels of
+// igmk_actdist_slab.cuh over batches of kSlabBatch pairs (processing order).
+static int launch_slab(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
+    int rc = list_prepare(c, P, st, 32);
+    if (rc) return rc;
+    P.list_budget = (float)kSlabCap / 1.35f;          // expected list length a pair may have
+    const int nseg = c->npad / kSeg;
+    SlabParams S;
+    S.nslab = (nseg + kSlabSegs - 1) / kSlabSegs;
+    const size_t off_cnt = (size_t)kSlabBatch * 4, off_lists = 2 * (size_t)kSlabBatch * 4;
+    rc = ensure(&c->d_slab, &c->slab_bytes, off_lists + (size_t)kSlabBatch * kSlabCap * 4);
+    if (rc) return rc;
+    S.T = (uint32_t*)c->d_slab;
+    S.cnt = (unsigned int*)((char*)c->d_slab + off_cnt);
+    S.lists = (uint32_t*)((char*)c->d_slab + off_lists);
+    int warps = kListWarps;
+    if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
+    const size_t list_bytes = (size_t)warps * 32 * kListBytes;
+    const size_t one_tile = (size_t)2 * kSlabSegs * kSegFloats * 4;
+    int slots = (c->tile_block > 0 && (long long)c->n_hap * S.nslab < (1 << 20)) ? c->list_tile_slots : 0;
+    if (slots > 2) slots = 2;
+    P.tile_slots = slots;
+    const size_t smem = list_bytes + (size_t)slots * one_tile;
+    CUDA_TRY(cudaFuncSetAttribute(slab_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (long long b0 = 0; b0 < P.n_pairs; b0 += kSlabBatch) {
+        S.slot0 = b0;
+        S.nslots = (int)((P.n_pairs - b0 < kSlabBatch) ? P.n_pairs - b0 : kSlabBatch);
+        int shift = 9;
+        if (c->tile_block > 0) { shift = 0; while ((2 << shift) <= c->tile_block) ++shift; }
+        // about eight tasks per CTA at least
+        while (shift > 5 && (long long)S.nslab * ((S.nslots + (1 << shift) - 1) >> shift) < 8LL * c->sm_count) --shift;
+        S.bshift = shift;
+        S.nblk = (S.nslots + (1 << shift) - 1) >> shift;
+        const int wgrid = (S.nslots + 7) / 8;
+        const int grid_w = (wgrid < 8 * c->sm_count) ? wgrid : 8 * c->sm_count;
+        slab_sample_kernel<<<grid_w, 256, 0, st>>>(P, S);
+        const long long ntask = (long long)S.nslab * S.nblk;
+        const int grid_f = (int)((ntask < c->sm_count) ? ntask : c->sm_count);
+        slab_fill_kernel<<<grid_f, 32 * warps, smem, st>>>(P, S);
+        slab_select_kernel<<<grid_w, 256, 0, st>>>(P, S);
+        g_launches += 3;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return IGMK_OK;
+}
+
 static int launch_simple(const igmk_ctx* c, const ActdistParams& P, cudaStream_t st) {
     const size_t smem = (size_t)4 * P.nstruct * sizeof(uint32_t);
     if (smem > 227 * 1024) return fail(IGMK_ELIMIT, "IGMK_ALGO_SIMPLE supports nstruct <= %d", 227 * 1024 / 16);
@@ -572,7 +624,8 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     // keep the key-array kernels alone (cross-check).
     if (c->list_form && c->group_threads == 0 && n_pairs <= 0x7fffffffLL) {
         const int T = group_threads_for(c);
-        int rc = (T == 32) ? launch_list_warp(c, P, st) : launch_list_block(c, P, (T + 31) / 32 * 32, st);
+        int rc = (T == 32) ? launch_list_warp(c, P, st)
+                           : (c->slab_form ? launch_slab(c, P, st) : launch_list_block(c, P, (T + 31) / 32 * 32, st));
         if (rc) return rc;
         ActdistParams R = P;
         R.redo_count = (unsigned int*)c->d_redo;

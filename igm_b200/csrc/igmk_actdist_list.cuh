@@ -129,11 +129,13 @@ __device__ __noinline__ SampleOut sample_threshold(uint4 kwa, uint4 kwb, int tid
 
 // Fill of one pair.  Returns 0 when the thread lists are complete for values <= T_bits,
 // 1 when the pair has to be redone by the key-array kernel.
-template <int SH, bool AS, bool BLOCK>
+// SAMPLE = false (slab pipeline, igmk_actdist_slab.cuh): T_bits is given, the row pointers
+// start at chunk c0 of the population and V counts the chunks of this slab only.
+template <int SH, bool AS, bool BLOCK, bool SAMPLE = true>
 __device__ __forceinline__ int fill_list(const ActdistParams& P, const Group<BLOCK>& g, const PairDesc& d,
                                          const PairPtrs& pp, int V, uint32_t as0, uint32_t as1,
                                          uint32_t lbase, uint32_t sred, int omax,
-                                         uint32_t& T_bits, int& mycnt, bool& ovf) {
+                                         uint32_t& T_bits, int& mycnt, bool& ovf, int c0 = 0) {
     constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
     const float qnan = __int_as_float(0x7fffffff);
     const u64 nz = P.negzero2;
@@ -147,14 +149,14 @@ __device__ __forceinline__ int fill_list(const ActdistParams& P, const Group<BLO
     uint32_t sa0 = as0 + (uint32_t)off0 * 4u, sa1 = as1 + (uint32_t)off0 * 4u;
     uint32_t lptr = lbase;
     const uint32_t llimit = lbase + (uint32_t)kListCap * 4u;
-    float T = 0.f;
+    float T = SAMPLE ? 0.f : __uint_as_float(T_bits);
     ovf = false;
     int status = 0;
     const u64 pol = (IGMK_JLOAD == LD_STREAM_L2KEEP || IGMK_JLOAD == LD_PLAIN_L2KEEP) ? l2_policy_evict_last() : 0ull;
 #pragma unroll 1
     for (int v = 0; v < V; ++v) {
-        const int c = tid + v * nthr;
-        if (v > 0 && c >= P.nchunks) break;            // padding chunks (c only grows)
+        const int c = c0 + tid + v * nthr;
+        if ((v > 0 || !SAMPLE) && c >= P.nchunks) break;   // padding chunks (c only grows)
         float s[4][NS];
         {
             // a padding chunk at v = 0 (tiny populations) still takes part in the sample;
@@ -176,7 +178,7 @@ __device__ __forceinline__ int fill_list(const ActdistParams& P, const Group<BLO
                     for (int k = 0; k < NS; ++k) s[q][k] = qnan;
                 }
         }
-        if (v == 0) {                                  // uniform over the group
+        if (SAMPLE && v == 0) {                        // uniform over the group
             uint32_t kw[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k)

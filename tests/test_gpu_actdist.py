@@ -268,6 +268,9 @@ def test_list_form_matches_key_arrays_warp(nstruct, monkeypatch):
 
 @pytest.mark.parametrize("nstruct", [1500, 4100, 10000])
 def test_list_form_matches_key_arrays_block(nstruct, monkeypatch):
+    """Populations of more than 1024 structures: the slab pipeline (sample / fill / select
+    kernels over slabs of 1024 structures), the one-CTA-per-pair list kernel (IGMK_SLAB=0)
+    and the key-array kernels (IGMK_LIST=0) give byte-identical results."""
     from igm_b200 import synthetic
     pop = synthetic.make_population(2_000_000, nstruct, seed=17 + nstruct, genome_scale=0.01)
     rng = np.random.default_rng(nstruct)
@@ -276,19 +279,21 @@ def test_list_form_matches_key_arrays_block(nstruct, monkeypatch):
     pw[::53] = rng.uniform(0.2, 1.0, len(pw[::53]))
     pl = np.zeros(len(ii))
     out = {}
-    for flag in ("1", "0"):
+    for flag, slab in (("1", "1"), ("1", "0"), ("0", "1")):
         monkeypatch.setenv("IGMK_LIST", flag)
+        monkeypatch.setenv("IGMK_SLAB", slab)
         with _engine(pop) as eng:
             for mode in ("lb", "gp"):
-                out[flag, mode] = eng.actdist(ii, jj, pw, pl, 2.0, 1, mode, 0)
+                out[flag, slab, mode] = eng.actdist(ii, jj, pw, pl, 2.0, 1, mode, 0)
                 if flag == "1":
                     assert 0 <= eng.last_redo_count() <= len(ii)
     for mode in ("lb", "gp"):
-        assert out["1", mode].tobytes() == out["0", mode].tobytes(), mode
+        assert out["1", "1", mode].tobytes() == out["0", "1", mode].tobytes(), mode
+        assert out["1", "0", mode].tobytes() == out["0", "1", mode].tobytes(), mode
     sel = np.sort(rng.choice(len(ii), 60, replace=False))
     _, dets = orc.run_pairs(ii[sel], jj[sel], pw[sel], pl[sel], pop.coordinates, pop.radii, pop.chrom_hap(),
                             pop.copy_index, 1, 2.0, MODES["lb"])
-    _check_against_details(out["1", "lb"][sel], dets)
+    _check_against_details(out["1", "1", "lb"][sel], dets)
 
 
 @pytest.mark.parametrize("kind", ["near_first", "far_first", "grid"])
