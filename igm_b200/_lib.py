@@ -40,6 +40,7 @@ EXPORTS = (
     "igmk_restraint_select_host", "igmk_sprite_rg2_host", "igmk_sprite_cluster_rg2_host",
     "igmk_rank_match_device", "igmk_rank_match_host",
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms", "igmk_last_redo_count",
+    "igmk_actdist_sel_index_device", "igmk_actdist_sel_index_host",
 )
 
 
@@ -98,6 +99,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.igmk_last_kernel_ms.argtypes = [vp]
     lib.igmk_last_kernel_ms.restype = C.c_float
     lib.igmk_last_redo_count.argtypes = [vp]
+    lib.igmk_actdist_sel_index_device.argtypes = [vp, C.c_int64, i32p, i32p, vp, C.c_int, i32p, vp]
+    lib.igmk_actdist_sel_index_host.argtypes = [vp, C.c_int64, i32p, i32p, vp, C.c_int, i32p]
     lib.igmk_last_redo_count.restype = C.c_int64
     for name in EXPORTS:
         fn = getattr(lib, name)

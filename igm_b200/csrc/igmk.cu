@@ -668,6 +668,54 @@ extern "C" int igmk_actdist_device_peers(igmk_ctx* c, int64_t n_pairs,
                           IGMK_ALGO_FAST, nullptr, d_peer_slices, n_peers, stream);
 }
 
+// sel_flat_idx of every pair: see sel_index_kernel.  d_results: the records
+// igmk_actdist_* produced for the same pair list.
+extern "C" int igmk_actdist_sel_index_device(igmk_ctx* c, int64_t n_pairs, const int32_t* d_i, const int32_t* d_j,
+                                             const igmk_pair_result* d_results, int mode, int32_t* d_sel_idx,
+                                             void* stream) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_actdist_sel_index: NULL context");
+    if (!c->have_coords || !c->have_index) return fail(IGMK_ESTATE, "igmk_actdist_sel_index: upload coordinates and index first");
+    if (mode != IGMK_MODE_LB && mode != IGMK_MODE_GP) return fail(IGMK_EINVAL, "igmk_actdist_sel_index: bad mode %d", mode);
+    if (n_pairs < 0) return fail(IGMK_EINVAL, "igmk_actdist_sel_index: negative n_pairs");
+    if (n_pairs == 0) return IGMK_OK;
+    if (!d_i || !d_j || !d_results || !d_sel_idx) return fail(IGMK_EINVAL, "igmk_actdist_sel_index: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ActdistParams P;
+    memset(&P, 0, sizeof P);
+    P.coords = c->d_coords; P.hap = c->d_hap; P.pi = d_i; P.pj = d_j;
+    P.n_pairs = n_pairs; P.nstruct = c->nstruct; P.npad = c->npad; P.nchunks = c->nchunks;
+    P.n_hap = c->n_hap; P.mode = mode; P.contact_range = 2.0f;
+    P.negzero2 = 0x8000000080000000ull;
+    const long long want = (n_pairs + 7) / 8, cap = 16LL * c->sm_count;
+    sel_index_kernel<<<(unsigned)((want < cap) ? want : cap), 256, 0, (cudaStream_t)stream>>>(P, d_results, d_sel_idx);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IGMK_OK;
+}
+
+extern "C" int igmk_actdist_sel_index_host(igmk_ctx* c, int64_t n_pairs, const int32_t* i, const int32_t* j,
+                                           const igmk_pair_result* results, int mode, int32_t* sel_idx) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_actdist_sel_index_host: NULL context");
+    if (n_pairs == 0) return IGMK_OK;
+    if (n_pairs < 0 || !i || !j || !results || !sel_idx) return fail(IGMK_EINVAL, "igmk_actdist_sel_index_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)n_pairs;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t off_j = up(n * 4), off_res = off_j + up(n * 4), off_out = off_res + up(n * sizeof(igmk_pair_result));
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, off_out + n * 4);
+    if (rc) return rc;
+    char* base = (char*)c->d_pairs;
+    CUDA_TRY(cudaMemcpyAsync(base, i, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_j, j, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(base + off_res, results, n * sizeof(igmk_pair_result), cudaMemcpyHostToDevice, c->stream));
+    rc = igmk_actdist_sel_index_device(c, n_pairs, (const int32_t*)base, (const int32_t*)(base + off_j),
+                                       (const igmk_pair_result*)(base + off_res), mode, (int32_t*)(base + off_out), c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(sel_idx, base + off_out, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return IGMK_OK;
+}
+
 extern "C" int igmk_finish_results_device(igmk_ctx* c, igmk_pair_result* d_results, int64_t n, void* stream) {
     if (!c) return fail(IGMK_EINVAL, "igmk_finish_results: NULL context");
     if (n < 0 || (n > 0 && !d_results)) return fail(IGMK_EINVAL, "igmk_finish_results: bad argument");

@@ -985,4 +985,68 @@ actdist_simple_kernel(const ActdistParams P) {
     }
 }
 
+// ------------------------------------------------------ selected-element index
+// sel_flat_idx of SURVEY.md 8b/8d: the index, in d_sq[0:npc].ravel() (row * N + structure),
+// of the element whose value is the selected order statistic - the LOWEST such index when
+// several elements tie (NumPy's sort is not stable, so the reference defines no particular
+// one).  d_sq is column-sorted at that point in BOTH modes (d_sq.sort(axis=0), :439), so the
+// row of a value is its rank among the copy-combination values of its structure.  One warp per
+// pair re-computes the pair's values and keeps the smallest matching index; -1 when the
+// pair has no record.  An optional second pass: the A-step itself never needs the index.
+template <int SH>
+__device__ __forceinline__ int sel_index_scan(const ActdistParams& P, const PairDesc& d, const PairPtrs& pp,
+                                              int lane, uint32_t want) {
+    constexpr int NS = (SH == SH_FULL4) ? 4 : (SH == SH_INTRA2 || SH == SH_GP4) ? 2 : 4;
+    int best = 0x7fffffff;
+    for (int c = lane; c < P.nchunks; c += 32) {
+        const size_t off = (size_t)(c >> 5) * kSegFloats + (size_t)(c & 31) * 4;
+        float s[4][NS];
+        {
+            const Row6 a0 = load_row6<LD_PLAIN>(pp.A0 + off), a1 = load_row6<LD_PLAIN>(pp.A1 + off);
+            const Row6 b0 = load_row6<LD_PLAIN>(pp.B0 + off), b1 = load_row6<LD_PLAIN>(pp.B1 + off);
+            chunk_values<SH, NS>(d, P.mode, a0, a1, b0, b1, P.negzero2, s);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int st = 4 * c + q;
+            if (st >= P.nstruct) continue;
+            int rank = 0;
+            bool hit = false;
+#pragma unroll
+            for (int k = 0; k < NS; ++k)
+                if (k < d.keep) {
+                    hit = hit || (__float_as_uint(s[q][k]) == want);
+                    rank += (s[q][k] < __uint_as_float(want)) ? 1 : 0;      // NaN (absent) never counts
+                }
+            if (hit) best = min(best, rank * P.nstruct + st);
+        }
+    }
+    return __reduce_min_sync(0xffffffffu, best);
+}
+
+__global__ void __launch_bounds__(256)
+sel_index_kernel(const ActdistParams P, const igmk_pair_result* __restrict__ res, int32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (long long pair = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pair < P.n_pairs;
+         pair += (long long)gridDim.x * wpb) {
+        const int o = res[pair].o;
+        int idx = -1;
+        if (o >= 0) {
+            const PairDesc d = make_pair_desc(P, __ldg(P.pi + pair), __ldg(P.pj + pair));
+            if (d.valid) {
+                const PairPtrs pp = pair_ptrs(P, d);
+                const uint32_t want = res[pair].d2_sel_bits;
+                switch (pair_shape(d, P.mode)) {
+                    case SH_FULL4:  idx = sel_index_scan<SH_FULL4>(P, d, pp, lane, want); break;
+                    case SH_INTRA2: idx = sel_index_scan<SH_INTRA2>(P, d, pp, lane, want); break;
+                    case SH_GP4:    idx = sel_index_scan<SH_GP4>(P, d, pp, lane, want); break;
+                    default:        idx = sel_index_scan<SH_GENERIC>(P, d, pp, lane, want); break;
+                }
+                if (idx == 0x7fffffff) idx = -1;
+            }
+        }
+        if (lane == 0) out[pair] = idx;
+    }
+}
+
 }  // namespace igmk

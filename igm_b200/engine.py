@@ -18,6 +18,77 @@ from ._lib import (ALGO_FAST, ALGO_SIMPLE, MODE_GP, MODE_LB, PAIR_RESULT_DTYPE, 
                    check, ptr)
 from .population import Population
 
+_pinned_cache = {}     # nbytes -> (address, ndarray view): page-locked staging buffers, kept per process
+
+
+def pinned_array(shape, dtype=np.float32, tag=None) -> np.ndarray:
+    """Page-locked host array (cudaHostAlloc through igmk_host_alloc) - asynchronous H2D
+    copies need it.  One buffer per size is kept for the life of the process (pinning
+    358 MB costs ~0.1 s; an A-step runs once per sigma iteration)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    key = (nbytes, tag)                                  # `tag` keeps concurrent users apart
+    ent = _pinned_cache.get(key)
+    if ent is None:
+        lib = _lib.load()
+        p = C.c_void_p()
+        check(lib.igmk_host_alloc(C.byref(p), max(nbytes, 1)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        ent = (p.value, np.frombuffer(buf, dtype=np.uint8, count=nbytes))
+        if len(_pinned_cache) >= 64:                     # bounded: drop the oldest buffer
+            old = next(iter(_pinned_cache))
+            lib.igmk_host_free(C.c_void_p(_pinned_cache.pop(old)[0]))
+        _pinned_cache[key] = ent
+    return ent[1].view(dtype).reshape(shape)
+
+
+class StagedHss:
+    """Host-side staging of a population file: coordinates in pinned memory + the index
+    tables ``get_actdist`` needs (igm/steps/ActivationDistanceStep.py:382-393)."""
+
+    def __init__(self, path: str, threads: int = 8):
+        import json
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        from . import hdf5
+        from .population import CopyIndex
+        with hdf5.open_h5(path) as f:
+            ds = f["coordinates"]
+            self.nbead, self.nstruct = int(ds.shape[0]), int(ds.shape[1])
+            ext = ds.raw_extents() if hasattr(ds, "raw_extents") else None
+            if ext is not None and str(ds.dtype) in ("float32", "<f4"):
+                crd = pinned_array((self.nbead, self.nstruct, 3), np.float32)
+                flat = crd.reshape(-1).view(np.uint8)
+                piece = 16 << 20
+                jobs = [(fo + a, min(piece, nb - a), do + a) for fo, nb, do in ext for a in range(0, nb, piece)]
+                fd = os.open(path, os.O_RDONLY)
+                try:
+                    def rd(job):
+                        fo, nb, do = job
+                        got = 0
+                        while got < nb:
+                            k = os.preadv(fd, [memoryview(flat[do + got:do + nb])], fo + got)
+                            if k <= 0:
+                                raise IOError("short read in %s" % path)
+                            got += k
+                    with ThreadPoolExecutor(max(1, min(threads, len(jobs)))) as ex:
+                        list(ex.map(rd, jobs))
+                finally:
+                    os.close(fd)
+            else:                                       # filtered / real h5py object: decode
+                crd = pinned_array((self.nbead, self.nstruct, 3), np.float32)
+                crd[...] = np.asarray(ds[:], dtype=np.float32)
+            self.coordinates = crd
+            self.radii = np.asarray(f["radii"][:], dtype=np.float32)
+            self.chrom = np.asarray(f["index"]["chrom"][:], dtype=np.int32)
+            ci = f["index"]["copy_index"][()]
+            if isinstance(ci, np.ndarray):
+                ci = ci.tobytes() if ci.dtype.kind in "SV" else ci.item()
+            if isinstance(ci, (bytes, np.bytes_)):
+                ci = bytes(ci).rstrip(b"\x00").decode("utf-8")
+            self.copy_index = CopyIndex.from_dict(json.loads(ci))
+
+
 _MODES = {"LB": MODE_LB, "GP": MODE_GP, MODE_LB: MODE_LB, MODE_GP: MODE_GP, "lb": MODE_LB, "gp": MODE_GP}
 
 
@@ -58,44 +129,24 @@ class ActdistEngine:
         self.close()
 
     @classmethod
-    def from_hss(cls, path: str, device: int = 0) -> "ActdistEngine":
-        """Engine for the population of a .hss file, coordinates streamed chunk by chunk
-        into HBM (igmk_upload_coords_range) instead of being materialised on the host:
-        replaces HssFile(...) + per-pair get_bead_crd chunk reads
-        (igm/steps/ActivationDistanceStep.py:202,415-416; igm/core/step.py:386-392)."""
-        import json
-        from . import hdf5
-        from .population import CopyIndex
-        with hdf5.open_h5(path) as f:
-            ds = f["coordinates"]
-            nbead, nstruct = int(ds.shape[0]), int(ds.shape[1])
-            eng = cls(nbead=nbead, nstruct=nstruct, device=device)
-            try:
-                if hasattr(ds, "iter_chunks"):
-                    for offs, chunk in ds.iter_chunks():
-                        if offs[1] != 0 or offs[2] != 0 or chunk.shape[1] != nstruct or chunk.shape[2] != 3:
-                            # chunking splits the structure axis: fall back to one full read
-                            eng.upload_coordinates(np.asarray(ds[:], dtype=np.float32))
-                            break
-                        eng.upload_coordinates(np.ascontiguousarray(chunk, dtype=np.float32), bead0=int(offs[0]))
-                else:                                   # real h5py
-                    step = max(1, (64 << 20) // (nstruct * 12))
-                    for b0 in range(0, nbead, step):
-                        eng.upload_coordinates(np.asarray(ds[b0:b0 + step], dtype=np.float32), bead0=b0)
-                radii = np.asarray(f["radii"][:], dtype=np.float32)
-                chrom = np.asarray(f["index"]["chrom"][:], dtype=np.int32)
-                ci = f["index"]["copy_index"][()]
-                if isinstance(ci, np.ndarray):
-                    ci = ci.tobytes() if ci.dtype.kind in "SV" else ci.item()
-                if isinstance(ci, (bytes, np.bytes_)):
-                    ci = bytes(ci).rstrip(b"\x00").decode("utf-8")
-                cidx = CopyIndex.from_dict(json.loads(ci))
-                eng.set_index(cidx.ptr, cidx.beads, np.ascontiguousarray(chrom[:len(cidx)]), radii)
-                eng.set_bead_chrom(chrom)
-                eng.copy_index, eng.chrom = cidx, chrom
-            except Exception:
-                eng.close()
-                raise
+    def from_hss(cls, path: str, device: int = 0, staged: "Optional[StagedHss]" = None) -> "ActdistEngine":
+        """Engine for the population of a .hss file: replaces HssFile(...) + per-pair
+        get_bead_crd chunk reads (igm/steps/ActivationDistanceStep.py:202,415-416;
+        igm/core/step.py:386-392).  The coordinates go file -> pinned host memory (parallel
+        pread of the stored extents, no decoding) -> HBM (double-buffered asynchronous copies
+        + re-layout kernel); ``staged`` shares one host copy between the engines of several
+        devices."""
+        st = staged if staged is not None else StagedHss(path)
+        eng = cls(nbead=st.nbead, nstruct=st.nstruct, device=device)
+        try:
+            eng.upload_coordinates(st.coordinates)
+            eng.set_index(st.copy_index.ptr, st.copy_index.beads,
+                          np.ascontiguousarray(st.chrom[:len(st.copy_index)]), st.radii)
+            eng.set_bead_chrom(st.chrom)
+            eng.copy_index, eng.chrom = st.copy_index, st.chrom
+        except Exception:
+            eng.close()
+            raise
         return eng
 
     # -- staging ---------------------------------------------------------
@@ -193,6 +244,16 @@ class ActdistEngine:
                                                   ptr(d_plast), float(np.float32(contact_range)),
                                                   int(it_corr), _MODES[mode], ptr(d_peer_slices),
                                                   int(n_peers), stream or None))
+
+    def sel_flat_idx(self, i, j, res, mode="LB") -> np.ndarray:
+        """Index of the selected element of every pair in ``d_sq[0:npc].ravel()``
+        (row * nstruct + structure; lowest index among ties; -1 without a record)."""
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        res = np.ascontiguousarray(res, dtype=PAIR_RESULT_DTYPE)
+        out = np.full(len(i), -1, dtype=np.int32)
+        check(self._lib.igmk_actdist_sel_index_host(self._ctx, len(i), ptr(i), ptr(j), ptr(res), _MODES[mode], ptr(out)))
+        return out
 
     def last_redo_count(self) -> int:
         """Pairs of the most recent A-step launch that the list-form kernel handed back

@@ -23,6 +23,7 @@ If ``h5py`` is importable, ``open_h5``/``write_h5`` prefer it.
 """
 from __future__ import annotations
 
+import os
 import struct
 import zlib
 from typing import Any, Dict, List, Optional, Tuple
@@ -186,6 +187,44 @@ class Dataset:
             return addr, dims[:-1]
         return None
 
+    def raw_extents(self):
+        """[(file_offset, nbytes, dest_byte_offset)] when the stored bytes ARE the array
+        (little-endian numeric type, no filter, and either a contiguous layout or chunks
+        that span all trailing dimensions, i.e. whole leading-axis slabs - what the
+        production .hss holds: pack_beads x nstruct x 3, igm/steps/ModelingStep.py:753-760);
+        None otherwise.  Lets a loader pread() the coordinates straight into pinned memory."""
+        dt = self._dt
+        if dt.cls == 9 or dt.np_dtype.kind not in "iuf" or dt.np_dtype.byteorder == ">" or self._filters:
+            return None
+        if not self.shape:
+            return None
+        esize = dt.size
+        rowb = esize * int(np.prod(self.shape[1:])) if len(self.shape) > 1 else esize
+        base = self._f._base
+        cl = self._chunk_layout()
+        if cl is None:
+            lay = self._layout
+            if lay[0] == 3 and lay[1] == 1:
+                addr, _sz = struct.unpack_from("<QQ", lay, 2)
+            elif lay[0] in (1, 2) and lay[2] == 1:
+                (addr,) = struct.unpack_from("<Q", lay, 8)
+            else:
+                return None
+            if addr == _UNDEF:
+                return None
+            return [(addr + base, rowb * self.shape[0], 0)]
+        btree, cdims = cl
+        if btree == _UNDEF or tuple(cdims[1:]) != tuple(self.shape[1:]):
+            return None
+        out = []
+        for csize, fmask, offs, addr in self._f._iter_chunks(btree, len(self.shape)):
+            if fmask or any(offs[1:]):
+                return None
+            rows = min(cdims[0], self.shape[0] - offs[0])
+            if rows > 0:
+                out.append((addr + base, rows * rowb, offs[0] * rowb))
+        return out
+
     def iter_chunks(self):
         """Yields (offsets, ndarray) for every stored chunk of a chunked dataset, clipped
         to the dataset extent (one pseudo-chunk at offset 0 for other layouts).  Lets a
@@ -348,13 +387,16 @@ class Group:
 
 
 class File(Group):
-    """Read-only view of a classic-format HDF5 file held in memory."""
+    """Read-only view of a classic-format HDF5 file (memory-mapped: opening a 3.6 GB .hss
+    touches only the metadata pages)."""
 
     def __init__(self, path: str, mode: str = "r"):
         if mode != "r":
             raise ValueError("igm_b200.hdf5.File is read-only; use write_h5() to write")
+        import mmap
         with open(path, "rb") as fh:
-            self._buf = fh.read()
+            size = os.fstat(fh.fileno()).st_size
+            self._buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ) if size else b""
         self.filename = path
         b = self._buf
         if b[:8] != _SIG:
@@ -381,7 +423,12 @@ class File(Group):
         self.close()
 
     def close(self):
-        pass
+        b, self._buf = self._buf, b""
+        try:
+            if hasattr(b, "close"):
+                b.close()
+        except (BufferError, ValueError):       # a view is still alive somewhere: let the GC do it
+            pass
 
     def _read(self, addr: int, n: int) -> bytes:
         a = addr + self._base
@@ -437,7 +484,9 @@ class File(Group):
 
         def name_at(off):
             s = hdata + off
-            e = b.index(b"\0", s)
+            e = b.find(b"\0", s)        # (mmap has find, not index)
+            if e < 0:
+                raise Hdf5FormatError("unterminated link name")
             return b[s:e].decode("utf-8")
 
         def walk(addr):

@@ -19,7 +19,10 @@ reproduced numerically on the device, bit for bit.
 
 Extra, optional keys (all under ``restraints/Hi-C``): ``gpu_mode`` ("LB" |
 "GP"), ``gpu_shards`` (number of tasks, default 1), ``gpu_device`` (first
-device id), ``write_text_tmp`` (also write the reference's ``%d.out.tmp``).
+device id), ``gpu_devices`` / ``gpu_max_devices`` (devices one task drives concurrently;
+default: all visible), ``write_text_tmp`` (also write the reference's ``%d.out.tmp``),
+``reference_task_files`` (``%d.in.npy`` in the reference's float64 (n, 4) layout instead of
+one typed row per pair), ``write_task_files`` (False: tasks run in this process only).
 """
 from __future__ import annotations
 
@@ -174,23 +177,113 @@ def unpack_records(parts):
 
 
 _engine_cache = {}
+_staged_cache = {}
+_matrix_cache = {}
+_handoff = {}          # in-file path -> (ii, jj, pw, pl): setup() -> task() inside one process
+
+# task input file: one row per candidate pair (the reference stores a float64 (n, 4) array)
+PAIR_DTYPE = np.dtype([("i", np.int32), ("j", np.int32), ("pwish", np.float64), ("plast", np.float64)])
+
+
+def _file_key(path):
+    st = os.stat(path)
+    return (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+
+
+def _load_matrix(path):
+    """Parsed .hcs, kept across the sigma iterations of a run (the matrix does not change;
+    the reference re-reads it in every setup, :124-126)."""
+    key = _file_key(path)
+    pm = _matrix_cache.get(key)
+    if pm is None:
+        _matrix_cache.clear()
+        pm = ProbMatrix.from_hcs(path)
+        _matrix_cache[key] = pm
+    return pm
+
+
+def _stage_population(hss_path):
+    from ..engine import StagedHss
+    return StagedHss(hss_path)
+
+
+def _get_engines(hss_path, devices):
+    """One engine per device for the population file (keyed by path, mtime, size): the
+    coordinates are read ONCE into pinned host memory and staged into every device's HBM
+    concurrently; engines of an older population are closed."""
+    from concurrent.futures import ThreadPoolExecutor
+    key = _file_key(hss_path)
+    for k in list(_engine_cache):
+        if k[:3] != key:
+            _engine_cache.pop(k).close()
+    for k in list(_staged_cache):
+        if k != key:
+            _staged_cache.pop(k)
+    missing = [d for d in devices if key + (d,) not in _engine_cache]
+    if missing:
+        st = _staged_cache.get(key)
+        if st is None:
+            st = _staged_cache[key] = _stage_population(hss_path)
+        if len(missing) == 1:
+            _engine_cache[key + (missing[0],)] = ActdistEngine.from_hss(hss_path, missing[0], staged=st)
+        else:
+            with ThreadPoolExecutor(len(missing)) as ex:
+                for d, eng in zip(missing, ex.map(lambda d: ActdistEngine.from_hss(hss_path, d, staged=st), missing)):
+                    _engine_cache[key + (d,)] = eng
+    return [_engine_cache[key + (d,)] for d in devices]
 
 
 def _get_engine(hss_path, device):
-    """One engine per (file, mtime, device) per process: coordinates are staged
-    into HBM once per A-step, not once per batch."""
-    st = os.stat(hss_path)
-    key = (os.path.abspath(hss_path), st.st_mtime_ns, st.st_size, device)
-    eng = _engine_cache.get(key)
-    if eng is None:
-        # a new population (or a rewritten file) replaces everything that was staged; engines
-        # of the SAME file on other devices stay (gpu_shards > 1: one shard per device)
-        for k in list(_engine_cache):
-            if k[:3] != key[:3] or k[3] == device:
-                _engine_cache.pop(k).close()
-        eng = ActdistEngine.from_hss(hss_path, device)     # chunk-wise staging, no host copy
-        _engine_cache[key] = eng
-    return eng
+    return _get_engines(hss_path, [device])[0]
+
+
+def visible_devices(dictHiC):
+    """Devices one task may drive: ``gpu_devices`` (list) or every visible GPU from
+    ``gpu_device`` on, at most ``gpu_max_devices``."""
+    if dictHiC.get("gpu_devices"):
+        return [int(d) for d in dictHiC["gpu_devices"]]
+    import torch  # device enumeration only
+    ndev = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    first = int(dictHiC.get("gpu_device", 0))
+    devs = list(range(first, max(ndev, first + 1)))
+    return devs[:int(dictHiC.get("gpu_max_devices", len(devs)))] or [first]
+
+
+def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr, mode):
+    """get_actdist for every pair, the list cut into contiguous shares, one per device, all
+    devices working at the same time (one host thread per device; the C library releases
+    the GIL).  The reference runs its batches concurrently on the workers of its controller
+    (igm/core/step.py:259-274, igm/parallel/ipyparallel_controller.py:66-109); with the
+    serial controller this is what gives igm-run all the GPUs of the box."""
+    from concurrent.futures import ThreadPoolExecutor
+    from ..engine import pinned_array
+    n = len(ii)
+    engines = _get_engines(hss_path, devices)
+    bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
+
+    def run(k):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        m = hi - lo
+        if m == 0:
+            return np.zeros(0, dtype=_lib.PAIR_RESULT_DTYPE)
+        tag = ("actdist", devices[k])
+        p_i = pinned_array((m,), np.int32, tag + ("i",)); p_i[:] = ii[lo:hi]
+        p_j = pinned_array((m,), np.int32, tag + ("j",)); p_j[:] = jj[lo:hi]
+        p_w = pinned_array((m,), np.float64, tag + ("w",)); p_w[:] = pw[lo:hi]
+        p_l = pinned_array((m,), np.float64, tag + ("l",)); p_l[:] = pl[lo:hi]
+        out = pinned_array((m,), _lib.PAIR_RESULT_DTYPE, tag + ("o",))
+        eng = engines[k]
+        _lib.check(eng._lib.igmk_actdist_host(eng._ctx, m, _lib.ptr(p_i), _lib.ptr(p_j), _lib.ptr(p_w), _lib.ptr(p_l),
+                                              float(np.float32(contact_range)), int(it_corr),
+                                              _lib.MODE_LB if str(mode).upper() == "LB" else _lib.MODE_GP, 0,
+                                              _lib.ptr(out)))
+        return out
+    if len(devices) == 1:
+        parts = [run(0)]
+    else:
+        with ThreadPoolExecutor(len(devices)) as ex:
+            parts = list(ex.map(run, range(len(devices))))
+    return engines[0], (parts[0] if len(parts) == 1 else np.concatenate(parts))
 
 
 class ActivationDistanceStep(Step):
@@ -226,7 +319,7 @@ class ActivationDistanceStep(Step):
         logger.info(inter_sigma)
         logger.info(intra_sigma)
 
-        pm = ProbMatrix.from_hcs(dictHiC["input_matrix"])
+        pm = _load_matrix(dictHiC["input_matrix"])
         n = pm.n
         last_actdist_file = self.cfg.get("runtime/Hi-C").get("actdist_file", None)
         n_shards = max(1, int(dictHiC.get("gpu_shards", 1)))
@@ -240,32 +333,56 @@ class ActivationDistanceStep(Step):
 
         ii, jj, pw = filter_candidates(pm, intra_sigma, inter_sigma)
         pl = lookup_plast(last_actdist_file, n, ii, jj)
-        params = np.stack([ii.astype(np.float64), jj.astype(np.float64), pw, pl], axis=1)
-        # contiguous, equal-count shards keep bead-i locality and output order
+        # contiguous, equal-count shards keep bead-i locality and output order.  The task input
+        # is one typed row per pair (the reference writes float64 (n, 4)); a task that runs in
+        # this process takes the arrays from memory instead of reading the file back
         bounds = np.linspace(0, len(ii), n_shards + 1).astype(np.int64)
+        _handoff.clear()
         for b in range(n_shards):
-            np.save(os.path.join(self.tmp_dir, "%d.in.npy" % b), params[bounds[b]:bounds[b + 1]])
+            lo, hi = bounds[b], bounds[b + 1]
+            fname = os.path.join(self.tmp_dir, "%d.in.npy" % b)
+            if dictHiC.get("reference_task_files", False):
+                # the reference's own layout: float64 (n, 4) = (i, j, pwish, plast) (:181-186)
+                np.save(fname, np.stack([ii[lo:hi].astype(np.float64), jj[lo:hi].astype(np.float64),
+                                         pw[lo:hi], pl[lo:hi]], axis=1))
+            elif dictHiC.get("write_task_files", True):
+                rows = np.empty(hi - lo, dtype=PAIR_DTYPE)
+                rows["i"], rows["j"], rows["pwish"], rows["plast"] = ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi]
+                np.save(fname, rows)
+            _handoff[fname] = (ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi])
         self.argument_list = range(n_shards)
 
     @staticmethod
     def task(batch_id, cfg, tmp_dir):
         dictHiC = cfg["restraints"]["Hi-C"]
         it_corr = cfg.get("runtime/Hi-C/iter_corr_knob")
-        params = np.load(os.path.join(tmp_dir, "%d.in.npy" % batch_id))
+        in_name = os.path.join(tmp_dir, "%d.in.npy" % batch_id)
         out_name = os.path.join(tmp_dir, "%d.out.npy" % batch_id)
-        if params.size == 0:
+        held = _handoff.pop(in_name, None)
+        if held is not None:
+            ii, jj, pw, pl = held
+        else:
+            params = np.load(in_name, mmap_mode="r")
+            if params.dtype.names:
+                ii, jj, pw, pl = params["i"], params["j"], params["pwish"], params["plast"]
+            elif params.size:                                # the reference's float64 (n, 4) layout
+                ii, jj, pw, pl = (params[:, 0].astype(np.int32), params[:, 1].astype(np.int32),
+                                  params[:, 2], params[:, 3])
+            else:
+                ii = np.zeros(0, np.int32)
+                jj, pw, pl = ii, np.zeros(0), np.zeros(0)
+        if len(ii) == 0:
             np.save(out_name, np.zeros((4, 0), dtype=np.uint32))
             return
-        import torch  # device enumeration only
-        ndev = torch.cuda.device_count() if torch.cuda.is_available() else 0
-        device = int(dictHiC.get("gpu_device", 0)) + (batch_id % max(1, ndev))
-        eng = _get_engine(cfg.get("optimization/structure_output"), device)
-        ii = params[:, 0].astype(np.int32)
-        jj = params[:, 1].astype(np.int32)
-        res = eng.actdist(ii, jj, params[:, 2], params[:, 3],
-                          contact_range=dictHiC.get("contact_range", 2.0),
-                          it_corr=1 if it_corr == 1 else 0,
-                          mode=dictHiC.get("gpu_mode", "LB"))
+        # one task drives every visible GPU at once; several tasks (gpu_shards > 1: workers of
+        # a parallel controller) take one device each
+        devices = visible_devices(dictHiC)
+        n_shards = max(1, int(dictHiC.get("gpu_shards", 1)))
+        if n_shards > 1:
+            devices = [devices[batch_id % len(devices)]]
+        eng, res = actdist_on_devices(cfg.get("optimization/structure_output"), devices, ii, jj, pw, pl,
+                                      dictHiC.get("contact_range", 2.0), 1 if it_corr == 1 else 0,
+                                      dictHiC.get("gpu_mode", "LB"))
         row, col, dist, prob = eng.expand_records(ii, jj, res)
         np.save(out_name, pack_records(row, col, dist, prob))
         if dictHiC.get("write_text_tmp", False):

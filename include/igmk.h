@@ -103,6 +103,20 @@ int igmk_actdist_host(igmk_ctx* ctx, int64_t n_pairs,
                       float contact_range, int it_corr, int mode, int algo,
                       igmk_pair_result* out);
 
+/* sel_flat_idx (the "selected structure index" of the A-step): for every pair the index, in
+ * d_sq[0:npc].ravel() = row * nstruct + structure (:439-448; d_sq is column-sorted there, so
+ * the row is the value's rank among the copy combinations of its structure), of the element
+ * that IS the selected
+ * order statistic - the lowest index when several elements tie (np.sort is not stable, so
+ * the reference defines no particular one); -1 for pairs without a record.  `results`: the
+ * records igmk_actdist_* returned for the same pairs and mode.  A separate pass because the
+ * A-step itself never needs the index. */
+int igmk_actdist_sel_index_device(igmk_ctx* ctx, int64_t n_pairs, const int32_t* d_i, const int32_t* d_j,
+                                  const igmk_pair_result* d_results, int mode, int32_t* d_sel_idx,
+                                  void* stream);
+int igmk_actdist_sel_index_host(igmk_ctx* ctx, int64_t n_pairs, const int32_t* i, const int32_t* j,
+                                const igmk_pair_result* results, int mode, int32_t* sel_idx);
+
 /* Diagnostic: how many pairs of the most recent igmk_actdist_* launch on this context the
  * list-form kernel handed back to the key-array kernels (large order index, many contacts,
  * or a population sample that misjudged the pair).  Synchronises the device. */

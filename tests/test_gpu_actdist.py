@@ -548,3 +548,39 @@ def test_swapped_and_duplicate_pairs():
             erow, ecol, edist, eprob = orc.records_to_arrays(recs)
             assert np.array_equal(row, erow) and np.array_equal(col, ecol)
             assert np.array_equal(dist, edist) and np.array_equal(prob, eprob)
+
+
+@pytest.mark.parametrize("nstruct", [100, 1000, 2500])
+def test_sel_flat_idx(nstruct):
+    """Selected structure index: d_sq[0:npc].ravel()[sel_flat_idx] is the
+    selected value, bit for bit, and the index is the lowest one holding that value."""
+    from igm_b200 import synthetic
+    pop = synthetic.make_population(2_000_000, nstruct, seed=900 + nstruct, genome_scale=0.02)
+    crd = pop.coordinates.copy()
+    crd[:, : nstruct // 3] = np.round(crd[:, : nstruct // 3] / 300.0) * 300.0      # ties among structures
+    from igm_b200.population import Population
+    pop = Population(crd, pop.radii, pop.chrom, pop.copy_index, pop.copy)
+    rng = np.random.default_rng(nstruct)
+    ii, jj = _sorted_pairs(rng, pop.n_hap, 260)
+    pw = rng.uniform(0.002, 1.0, len(ii)).astype(np.float32).astype(np.float64)
+    pw[::7] = 0.0                                            # no record -> -1
+    ch, ci = pop.chrom_hap(), pop.copy_index
+    with _engine(pop) as eng:
+        for mode in ("lb", "gp"):
+            res = eng.actdist(ii, jj, pw, None, 2.0, 0, mode, 0)
+            idx = eng.sel_flat_idx(ii, jj, res, mode)
+            for t in range(len(ii)):
+                if res["o"][t] < 0:
+                    assert idx[t] == -1
+                    continue
+                a, b = ci[int(ii[t])], ci[int(jj[t])]
+                if mode == "lb" and ch[ii[t]] == ch[jj[t]]:
+                    combos, npc = list(zip(a, b)), min(len(a), len(b))
+                else:
+                    combos = [(k, m) for k in a for m in b]
+                    npc = len(a) * len(b) if mode == "lb" else min(len(a), len(b))
+                d_sq = np.stack([np.sum(np.square(crd[k] - crd[m]), axis=1) for k, m in combos]).astype(np.float64)
+                d_sq.sort(axis=0)                                                  # :439
+                flat = d_sq[0:npc].ravel().astype(np.float32).view(np.uint32)
+                assert flat[idx[t]] == res["d2_sel_bits"][t], (mode, t)
+                assert idx[t] == np.flatnonzero(flat == res["d2_sel_bits"][t])[0], (mode, t)

@@ -88,3 +88,37 @@ def test_engine_from_hss_streams_chunks(tmp_path):
     with ActdistEngine(pop, 0) as a, ActdistEngine.from_hss(p, 0) as b:
         assert a.actdist(ii, jj, pw).tobytes() == b.actdist(ii, jj, pw).tobytes()
         assert np.array_equal(a.contact_counts_haploid(0, 9, 0, 9), b.contact_counts_haploid(0, 9, 0, 9))
+
+
+def test_task_drives_all_gpus_concurrently(tmp_path):
+    """One task, several devices (one host thread and one staged engine per device, the
+    population read once into pinned memory): the output file equals the single-device one.
+    Needs >= 2 GPUs on the box; skipped otherwise."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from igm_b200 import hdf5, synthetic
+    from igm_b200.steps.ActivationDistanceStep import ActivationDistanceStep
+    from igm_b200.steps._compat import Config
+    pop = synthetic.make_population(2_000_000, 400, seed=12, genome_scale=0.05)
+    hss = str(tmp_path / "pop.hss")
+    pop.save_hss(hss)
+    pm = synthetic.make_prob_matrix(pop.chrom_hap(), seed=3, inter_per_row=40.0)
+    hcs = str(tmp_path / "m.hcs")
+    pm.save_hcs(hcs)
+    outs = []
+    for devs in ([0], list(range(torch.cuda.device_count()))):
+        wd = tmp_path / ("run%d" % len(devs))
+        wd.mkdir()
+        cfg = Config({
+            "restraints": {"Hi-C": {"input_matrix": hcs, "intra_sigma_list": [0.01], "inter_sigma_list": [0.01],
+                                    "contact_range": 2.0, "tmp_dir": "actdist", "gpu_devices": devs}},
+            "optimization": {"structure_output": hss, "iter_corr_knob": 1},
+            "parameters": {"workdir": str(wd), "tmp_dir": str(wd / "tmp")},
+            "runtime": {"Hi-C": {}}})
+        ActivationDistanceStep(cfg).run()
+        with hdf5.open_h5(cfg["runtime"]["Hi-C"]["actdist_file"]) as f:
+            outs.append({k: f[k][()] for k in ("row", "col", "dist", "prob")})
+    assert len(outs[0]["row"]) > 1000
+    for k in ("row", "col", "dist", "prob"):
+        assert outs[0][k].tobytes() == outs[1][k].tobytes(), k

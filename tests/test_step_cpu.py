@@ -132,8 +132,15 @@ def test_step_bookkeeping_name_setup_reduce_skip(tmp_path):
     parts = [np.load(os.path.join(step.tmp_dir, "%d.in.npy" % b)) for b in range(3)]
     allp = np.concatenate(parts)
     ii, jj, pw = S.filter_candidates(pm, 0.2, 0.2)
-    assert allp.dtype == np.float64 and allp.shape == (len(ii), 4)     # (i, j, pwish, plast) as float64
-    assert np.array_equal(allp[:, 0], ii) and np.array_equal(allp[:, 2], pw)
+    assert allp.dtype == S.PAIR_DTYPE and allp.shape == (len(ii),)     # one typed row per pair
+    assert np.array_equal(allp["i"], ii) and np.array_equal(allp["pwish"], pw) and allp["j"].dtype == np.int32
+    # ... or the reference's own float64 (n, 4) layout (:181-186) on request
+    cfg_r = _cfg(tmp_path, hcs, "unused.hss", gpu_shards=3, reference_task_files=True, tmp_dir="actdist_ref")
+    step_r = S.ActivationDistanceStep(cfg_r)
+    step_r.setup()
+    allr = np.concatenate([np.load(os.path.join(step_r.tmp_dir, "%d.in.npy" % b)) for b in range(3)])
+    assert allr.dtype == np.float64 and allr.shape == (len(ii), 4)
+    assert np.array_equal(allr[:, 0], ii) and np.array_equal(allr[:, 2], pw)
     # reduce: concatenation, dtypes, swap-file naming (:260-298)
     rng = np.random.default_rng(0)
     exp = []
@@ -304,13 +311,21 @@ def test_engine_cache_keeps_one_engine_per_device(tmp_path, monkeypatch):
         def close(self):
             closed.append(self.tag)
 
-    monkeypatch.setattr(S, "ActdistEngine", type("E", (), {"from_hss": staticmethod(lambda p, d: FakeEngine(p, d))}))
+    monkeypatch.setattr(S, "ActdistEngine",
+                        type("E", (), {"from_hss": staticmethod(lambda p, d, staged=None: FakeEngine(p, d))}))
     monkeypatch.setattr(S, "_engine_cache", {})
+    monkeypatch.setattr(S, "_staged_cache", {})
+    staged = []
+    monkeypatch.setattr(S, "_stage_population", lambda p: staged.append(p) or object())
     a, b = str(tmp_path / "a.hss"), str(tmp_path / "b.hss")
     open(a, "wb").write(b"x" * 10)
     open(b, "wb").write(b"y" * 20)
     e0 = S._get_engine(a, 0)
     e1 = S._get_engine(a, 1)
     assert S._get_engine(a, 0) is e0 and S._get_engine(a, 1) is e1 and not closed
-    S._get_engine(b, 0)                                   # another population: both are released
-    assert sorted(closed) == [(a, 0), (a, 1)] and len(S._engine_cache) == 1
+    assert staged == [a]                                  # one host copy of the file for both devices
+    e23 = S._get_engines(a, [2, 3])                       # staged concurrently, same host copy
+    assert [e.tag for e in e23] == [(a, 2), (a, 3)] and staged == [a]
+    S._get_engine(b, 0)                                   # another population: all are released
+    assert sorted(closed) == [(a, 0), (a, 1), (a, 2), (a, 3)] and len(S._engine_cache) == 1
+    assert staged == [a, b] and len(S._staged_cache) == 1

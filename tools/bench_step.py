@@ -25,7 +25,13 @@ def main():
     from igm_b200.population import CopyIndex, Population
     from igm_b200.steps import ActivationDistanceStep
     from igm_b200.steps._compat import Config
-    nstruct = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    args = [a for a in sys.argv[1:]]
+    ngpu = 0
+    if "--gpus" in args:
+        k = args.index("--gpus")
+        ngpu = int(args[k + 1])
+        del args[k:k + 2]
+    nstruct = int(args[0]) if args else 1000
     tmp = tempfile.mkdtemp(prefix="igmk_step_")
     dev = torch.device("cuda:0")
     bins = synthetic.genome_bins(200_000)
@@ -42,11 +48,13 @@ def main():
     pm.save_hcs(hcs)
     t_files = time.perf_counter() - t0
     del pop, coords
-    out = {"nstruct": nstruct, "nbead": nbead, "write_inputs_s": t_files, "sigmas": []}
+    out = {"nstruct": nstruct, "nbead": nbead, "write_inputs_s": t_files, "sigmas": [],
+           "devices_per_task": ngpu or torch.cuda.device_count()}
     cfg = Config({"parameters": {"workdir": tmp, "tmp_dir": os.path.join(tmp, "tmp")},
                   "optimization": {"structure_output": hss, "iter_corr_knob": 1},
                   "restraints": {"Hi-C": {"input_matrix": hcs, "intra_sigma_list": list(SIGMAS),
-                                          "inter_sigma_list": list(SIGMAS), "contact_range": 2.0}},
+                                          "inter_sigma_list": list(SIGMAS), "contact_range": 2.0,
+                                          **({"gpu_max_devices": ngpu} if ngpu else {})}},
                   "runtime": {"Hi-C": {}, "opt_iter": 0}})
     for k in range(len(SIGMAS)):
         step = ActivationDistanceStep(cfg)
@@ -59,7 +67,8 @@ def main():
         t = time.perf_counter(); step.reduce(); ph["reduce_s"] = time.perf_counter() - t
         with hdf5.open_h5(cfg["runtime"]["Hi-C"]["actdist_file"]) as f:
             ph["records"] = int(len(f["row"]))
-        ph["pairs"] = int(sum(len(np.load(os.path.join(step.tmp_dir, "%d.in.npy" % a))) for a in step.argument_list))
+        ph["pairs"] = int(sum(len(np.load(os.path.join(step.tmp_dir, "%d.in.npy" % a), mmap_mode="r"))
+                              for a in step.argument_list))
         ph["sigma"] = cfg["runtime"]["Hi-C"]["intra_sigma"]
         ph["total_s"] = ph["setup_s"] + ph["task_s"] + ph["reduce_s"]
         ph["pairs_per_s_whole_step"] = ph["pairs"] / ph["total_s"]
