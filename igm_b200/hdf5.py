@@ -631,9 +631,15 @@ def _dtype_message(dt: np.dtype) -> bytes:
     raise ValueError("unsupported dtype for HDF5 writer: %r" % dt)
 
 
-def _dataspace_message(shape) -> bytes:
+def _dataspace_message(shape, maxdims: bool = False) -> bytes:
+    """Version-1 simple dataspace.  ``maxdims``: also store the maximum dimensions (= the
+    current ones), as libhdf5 does for every dataset h5py creates (flags bit 0) - the demo
+    files written by the real library show it (tests/test_hdf5_spec_cpu.py)."""
     shape = tuple(int(s) for s in shape)
-    return struct.pack("<BBBB4x", 1, len(shape), 0, 0) + b"".join(struct.pack("<Q", s) for s in shape)
+    dims = b"".join(struct.pack("<Q", s) for s in shape)
+    if maxdims and shape:
+        return struct.pack("<BBBB4x", 1, len(shape), 1, 0) + dims + dims
+    return struct.pack("<BBBB4x", 1, len(shape), 0, 0) + dims
 
 
 def _pad8(b: bytes) -> bytes:
@@ -699,10 +705,12 @@ class _Writer:
         raw = memoryview(arr.reshape(-1).view(np.uint8)) if arr.size else b""
         daddr = self.alloc(raw) if len(raw) else _UNDEF
         msgs = [
-            _message(0x01, _dataspace_message(arr.shape)),
+            _message(0x01, _dataspace_message(arr.shape, maxdims=True)),
             _message(0x03, _dtype_message(arr.dtype), flags=1),
-            # fill value v2: alloc time late(2)... use early alloc, write-time never, undefined
-            _message(0x05, struct.pack("<BBBB", 2, 1, 2, 0)),
+            # fill value, version 2: allocate late (2), write the fill value if set (2), defined
+            # (1) with size 0 = the library default - byte for byte what libhdf5 stores for a
+            # contiguous dataset created through h5py
+            _message(0x05, struct.pack("<BBBBI", 2, 2, 2, 1, 0), flags=1),
             _message(0x08, struct.pack("<BBQQ", 3, 1, daddr, len(raw))),
         ]
         for k, v in (attrs or {}).items():

@@ -122,3 +122,23 @@ def test_task_drives_all_gpus_concurrently(tmp_path):
     assert len(outs[0]["row"]) > 1000
     for k in ("row", "col", "dist", "prob"):
         assert outs[0][k].tobytes() == outs[1][k].tobytes(), k
+
+
+def test_dropin_runs_under_the_reference_step_run_on_the_gpu(tmp_path):
+    """tests/real_step_driver.py with the real kernels: the drop-in driven by the reference's
+    own Step.run / Config / SerialController / StepDB, records equal to the oracle's, second
+    run skipped from the restart log."""
+    import json
+    import subprocess
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("no copy of the reference package (oracle/_ref/igm)")
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "tests", "real_step_driver.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600, cwd=H.ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["records"] > 0 and d["records_equal_oracle"] and not d["fake_gpu"]
+    assert d["statuses"] == ["entry", "setup", "map", "mapped", "reduced", "cleanup", "completed"]
+    assert d["task_calls_first_run"] == 1 and d["task_calls_second_run"] == 0
+    assert d["second_run_actdist_file"] == d["actdist_file"]

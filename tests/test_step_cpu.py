@@ -329,3 +329,26 @@ def test_engine_cache_keeps_one_engine_per_device(tmp_path, monkeypatch):
     S._get_engine(b, 0)                                   # another population: all are released
     assert sorted(closed) == [(a, 0), (a, 1), (a, 2), (a, 3)] and len(S._engine_cache) == 1
     assert staged == [a, b] and len(S._staged_cache) == 1
+
+
+def test_dropin_runs_under_the_reference_step_run(tmp_path):
+    """The drop-in subclasses the reference's REAL igm.core.Step and is driven by its
+    Step.run (igm/core/step.py:226-322): sqlite restart log (job_tracking.py), statuses in the
+    reference's order, and a second run from a fresh configuration takes skip() and restores
+    runtime/Hi-C/actdist_file without calling task again.  Here the device call is replaced
+    by the NumPy oracle (no GPU); tests/test_gpu_step.py runs the same driver on the kernels."""
+    import json
+    import subprocess
+    import sys
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip("no copy of the reference package (run `make -C oracle`)")
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "tests", "real_step_driver.py"), str(tmp_path), "--fake-gpu"],
+                       capture_output=True, text=True, timeout=600, cwd=H.ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["records"] > 0 and d["records_equal_oracle"]
+    assert d["statuses"] == ["entry", "setup", "map", "mapped", "reduced", "cleanup", "completed"]
+    assert d["task_calls_first_run"] == 1 and d["task_calls_second_run"] == 0
+    assert d["second_run_actdist_file"] == d["actdist_file"] and os.path.exists(d["actdist_file"])
+    assert d["second_run_sigma"] == 0.05
