@@ -87,7 +87,7 @@ struct igmk_ctx {
     int slab_form = 1;           // IGMK_SLAB: populations > 1024 structures run the list form slab by slab (0: one CTA per pair)
     void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch
     int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
-    float list_budget = 16.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
+    float list_budget = 20.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
     void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
     unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
     bool redo_pending = false;
@@ -456,7 +456,7 @@ static int launch_slab(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     S.T = (uint32_t*)c->d_slab;
     S.cnt = (unsigned int*)((char*)c->d_slab + off_cnt);
     S.lists = (uint32_t*)((char*)c->d_slab + off_lists);
-    int warps = kListWarps;
+    int warps = kSlabWarps;
     if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
     const size_t list_bytes = (size_t)warps * 32 * kListBytes;
     const size_t one_tile = (size_t)2 * kSlabSegs * kSegFloats * 4;

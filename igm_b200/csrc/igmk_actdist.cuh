@@ -425,6 +425,19 @@ __device__ __forceinline__ uint32_t warp_select(uint32_t list, int n, int r, int
 // shared-memory round trip for that one pair) or simply streams them from L2 as
 // before.  Slot word = locus << 12 | state << 10 | users; every transition is a
 // single-word atomic, so there is no ABA window.
+// How a tile is filled (IGMK_TILE_BULK):
+//   0  the claiming warp copies the rows itself (LDG.128 + STS.128), then uses the tile;
+//   1  the claiming warp issues two bulk asynchronous copies and WAITS for them (measured
+//      12 % slower than 0: a 24 KB bulk copy takes longer than 48 warp-wide load / store
+//      rounds, and every warp of that locus streams from L2 meanwhile);
+//   2  asynchronous: the claiming warp issues the bulk copies (TMA engine, completion on the
+//      slot's mbarrier) and goes on at once, streaming its own pair from L2; the first warp
+//      that wants the locus after the bytes have landed (non-blocking mbarrier probe) flips
+//      the slot to READY.  Slot word = locus << 12 | state << 10 | generation << 6 | users;
+//      generation g (mod 16) completes phase g & 1 of the mbarrier.
+#ifndef IGMK_TILE_BULK
+#define IGMK_TILE_BULK 0
+#endif
 enum : uint32_t { TS_EMPTY = 0u, TS_LOADING = 1u, TS_READY = 2u };
 struct TileCtl {
     uint32_t base;        // shared address of slot 0 (0: tiles disabled)
@@ -441,8 +454,8 @@ struct __align__(8) TileShared {
     uint32_t par[2];
 };
 __device__ __forceinline__ void tile_init(TileShared* ts) {   // one thread, before a CTA barrier
-    ts->slot[0] = (0xfffffu << 12) | (0u << 10);
-    ts->slot[1] = (0xfffffu << 12) | (0u << 10);
+    ts->slot[0] = (0xfffffu << 12) | (0u << 10) | ((IGMK_TILE_BULK == 2) ? (15u << 6) : 0u);
+    ts->slot[1] = (0xfffffu << 12) | (0u << 10) | ((IGMK_TILE_BULK == 2) ? (15u << 6) : 0u);
     ts->par[0] = 0u; ts->par[1] = 0u;
     mbar_init((uint32_t)__cvta_generic_to_shared(&ts->bar[0]), 1u);
     mbar_init((uint32_t)__cvta_generic_to_shared(&ts->bar[1]), 1u);
@@ -463,6 +476,67 @@ __device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+#if IGMK_TILE_BULK == 2
+__device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCtl& tile, int i,
+                                            const PairDesc& d, const PairPtrs& pp, int lane) {
+    int found = -1;
+    if (lane == 0) {
+        const uint32_t want = (uint32_t)i;
+        bool same_busy = false;
+        for (int s = 0; s < tile.nslots && found < 0; ++s) {
+            const uint32_t addr = tile.words + 4u * (uint32_t)s;
+            uint32_t w = lds32_volatile(addr);
+            for (int tries = 0; tries < 4; ++tries) {
+                if ((w >> 12) != want) break;
+                const uint32_t st = (w >> 10) & 3u;
+                if (st == TS_READY) {
+                    const uint32_t old = atoms_cas(addr, w, w + 1u);
+                    if (old == w) { found = s; break; }
+                    w = old;
+                    continue;
+                }
+                if (st == TS_LOADING) {
+                    // have the bytes of this generation landed?  (non-blocking probe)
+                    if (mbar_test(tile.bars + 8u * (uint32_t)s, (w >> 6) & 1u)) {
+                        const uint32_t nw = (w & ~(3u << 10)) | (TS_READY << 10) | 1u;   // first user
+                        const uint32_t old = atoms_cas(addr, w, nw);
+                        if (old == w) { found = s; break; }
+                        w = old;
+                        continue;
+                    }
+                    same_busy = true;
+                }
+                break;
+            }
+        }
+        if (found < 0 && !same_busy) {
+            // claim an idle slot (empty, ready without users, or loaded and never used) and
+            // start the copy; this warp streams its own pair from L2
+            for (int s = 0; s < tile.nslots; ++s) {
+                const uint32_t addr = tile.words + 4u * (uint32_t)s;
+                const uint32_t w = lds32_volatile(addr);
+                const uint32_t st = (w >> 10) & 3u;
+                if ((w & 0x3fu) != 0u) continue;
+                if ((w >> 12) == want && st != TS_EMPTY) continue;
+                const uint32_t bar = tile.bars + 8u * (uint32_t)s;
+                if (st == TS_LOADING && !mbar_test(bar, (w >> 6) & 1u)) continue;
+                const uint32_t gen = (((w >> 6) & 15u) + 1u) & 15u;
+                const uint32_t nw = (want << 12) | (TS_LOADING << 10) | (gen << 6);
+                if (atoms_cas(addr, w, nw) != w) continue;
+                const uint32_t dst0 = tile.base + (uint32_t)s * tile.slot_bytes;
+                const uint32_t rowb = tile.slot_bytes >> 1;
+                mbar_expect_tx(bar, (d.a1 >= 0) ? 2u * rowb : rowb);
+                bulk_g2s(dst0, pp.A0, rowb, bar);
+                if (d.a1 >= 0) bulk_g2s(dst0 + rowb, pp.A1, rowb, bar);
+                break;
+            }
+        }
+    }
+    found = __shfl_sync(0xffffffffu, found, 0);
+    if (found >= 0) __threadfence_block();
+    return found;
+}
+#else
 __device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCtl& tile, int i,
                                             const PairDesc& d, const PairPtrs& pp, int lane) {
     int found = -1, claimed = -1;
@@ -509,9 +583,6 @@ __device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCt
         return found;
     }
     if (claimed < 0) return -1;
-#ifndef IGMK_TILE_BULK
-#define IGMK_TILE_BULK 0
-#endif
     const uint32_t dst0 = tile.base + (uint32_t)claimed * tile.slot_bytes;
     const uint32_t rowb = tile.slot_bytes >> 1;
 #if IGMK_TILE_BULK
@@ -557,6 +628,7 @@ __device__ __forceinline__ int tile_acquire(const ActdistParams& P, const TileCt
     __syncwarp();
     return claimed;
 }
+#endif
 __device__ __forceinline__ void tile_release(const TileCtl& tile, int slot, int lane) {
     __syncwarp();                            // every lane's tile reads are done
     if (lane == 0)

@@ -24,6 +24,10 @@
 
 namespace igmk {
 
+#ifndef IGMK_SWPB
+#define IGMK_SWPB 24              // warps per CTA of the slab fill kernel (78 registers, no spills; 20 / 22 / 24 warps: 23.0 / 23.7 / 24.1 M pairs/s at N = 10 000)
+#endif
+constexpr int kSlabWarps = IGMK_SWPB;
 constexpr int kSlabSegs = 8;                  // segments of 128 structures per slab
 constexpr int kSlabChunks = kSlabSegs * 32;   // float4 chunks per slab and bead row
 constexpr int kSlabCap = 8192;                // list words per pair in global memory
@@ -114,7 +118,7 @@ slab_sample_kernel(const ActdistParams P, const SlabParams S) {
 }
 
 // -------------------------------------------------------------------- B: fill
-__global__ void __launch_bounds__(32 * kListWarps, 1)
+__global__ void __launch_bounds__(32 * kSlabWarps, 1)
 slab_fill_kernel(const ActdistParams P, const SlabParams S) {
     extern __shared__ uint4 s_dyn[];              // [thread] lists | locus-i tiles
     __shared__ TileShared s_tile;

@@ -22,24 +22,31 @@ _pinned_cache = {}     # nbytes -> (address, ndarray view): page-locked staging 
 
 
 def pinned_array(shape, dtype=np.float32, tag=None) -> np.ndarray:
-    """Page-locked host array (cudaHostAlloc through igmk_host_alloc) - asynchronous H2D
-    copies need it.  One buffer per size is kept for the life of the process (pinning
-    358 MB costs ~0.1 s; an A-step runs once per sigma iteration)."""
+    """Page-locked host array (cudaHostAlloc through igmk_host_alloc) - asynchronous H2D /
+    D2H copies need it.  Buffers are kept for the life of the process, one per ``tag`` (a
+    tagged buffer only ever grows, by at least 1.5x, and serves every smaller request: the
+    candidate lists of a sigma sweep grow from step to step) or one per size (no tag):
+    page-locking runs at 1 - 3 GB/s, far too slow to repeat for every A-step."""
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
-    key = (nbytes, tag)                                  # `tag` keeps concurrent users apart
+    key = ("size", nbytes) if tag is None else ("tag", tag)
     ent = _pinned_cache.get(key)
-    if ent is None:
+    if ent is None or len(ent[1]) < nbytes:
         lib = _lib.load()
+        cap = max(nbytes, 1)
+        if ent is not None:
+            cap = max(cap, int(1.5 * len(ent[1])))
+            lib.igmk_host_free(C.c_void_p(ent[0]))
+            del _pinned_cache[key]
         p = C.c_void_p()
-        check(lib.igmk_host_alloc(C.byref(p), max(nbytes, 1)))
-        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
-        ent = (p.value, np.frombuffer(buf, dtype=np.uint8, count=nbytes))
+        check(lib.igmk_host_alloc(C.byref(p), cap))
+        buf = (C.c_char * cap).from_address(p.value)
+        ent = (p.value, np.frombuffer(buf, dtype=np.uint8, count=cap))
         if len(_pinned_cache) >= 64:                     # bounded: drop the oldest buffer
             old = next(iter(_pinned_cache))
             lib.igmk_host_free(C.c_void_p(_pinned_cache.pop(old)[0]))
         _pinned_cache[key] = ent
-    return ent[1].view(dtype).reshape(shape)
+    return ent[1][:nbytes].view(dtype).reshape(shape)
 
 
 class StagedHss:

@@ -180,6 +180,7 @@ _engine_cache = {}
 _staged_cache = {}
 _matrix_cache = {}
 _handoff = {}          # in-file path -> (ii, jj, pw, pl): setup() -> task() inside one process
+LAST_TIMING = {}       # seconds spent in the phases of the most recent setup / task / reduce (diagnostic)
 
 # task input file: one row per candidate pair (the reference stores a float64 (n, 4) array)
 PAIR_DTYPE = np.dtype([("i", np.int32), ("j", np.int32), ("pwish", np.float64), ("plast", np.float64)])
@@ -257,9 +258,13 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
     serial controller this is what gives igm-run all the GPUs of the box."""
     from concurrent.futures import ThreadPoolExecutor
     from ..engine import pinned_array
+    import time
     n = len(ii)
+    t0 = time.perf_counter()
     engines = _get_engines(hss_path, devices)
+    LAST_TIMING["task_engines_s"] = time.perf_counter() - t0
     bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
+    t0 = time.perf_counter()
 
     def run(k):
         lo, hi = int(bounds[k]), int(bounds[k + 1])
@@ -283,6 +288,7 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
     else:
         with ThreadPoolExecutor(len(devices)) as ex:
             parts = list(ex.map(run, range(len(devices))))
+    LAST_TIMING["task_device_s"] = time.perf_counter() - t0
     return engines[0], (parts[0] if len(parts) == 1 else np.concatenate(parts))
 
 
@@ -331,8 +337,14 @@ class ActivationDistanceStep(Step):
         self.keep_temporary_files = dictHiC.get("keep_temporary_files", False)
         os.makedirs(self.tmp_dir, exist_ok=True)
 
+        import time
+        t0 = time.perf_counter()
         ii, jj, pw = filter_candidates(pm, intra_sigma, inter_sigma)
+        LAST_TIMING["setup_filter_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         pl = lookup_plast(last_actdist_file, n, ii, jj)
+        LAST_TIMING["setup_plast_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         # contiguous, equal-count shards keep bead-i locality and output order.  The task input
         # is one typed row per pair (the reference writes float64 (n, 4)); a task that runs in
         # this process takes the arrays from memory instead of reading the file back
@@ -350,6 +362,7 @@ class ActivationDistanceStep(Step):
                 rows["i"], rows["j"], rows["pwish"], rows["plast"] = ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi]
                 np.save(fname, rows)
             _handoff[fname] = (ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi])
+        LAST_TIMING["setup_files_s"] = time.perf_counter() - t0
         self.argument_list = range(n_shards)
 
     @staticmethod
@@ -383,8 +396,13 @@ class ActivationDistanceStep(Step):
         eng, res = actdist_on_devices(cfg.get("optimization/structure_output"), devices, ii, jj, pw, pl,
                                       dictHiC.get("contact_range", 2.0), 1 if it_corr == 1 else 0,
                                       dictHiC.get("gpu_mode", "LB"))
+        import time
+        t0 = time.perf_counter()
         row, col, dist, prob = eng.expand_records(ii, jj, res)
+        LAST_TIMING["task_expand_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
         np.save(out_name, pack_records(row, col, dist, prob))
+        LAST_TIMING["task_save_s"] = time.perf_counter() - t0
         if dictHiC.get("write_text_tmp", False):
             # the reference's own wire format (:228-230), for byte-level comparison
             ad = np.repeat(np.sqrt(res["d2_sel_bits"].view(np.float32).astype(np.float64)), res["nrec"])

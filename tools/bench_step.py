@@ -70,6 +70,8 @@ def main():
         ph["pairs"] = int(sum(len(np.load(os.path.join(step.tmp_dir, "%d.in.npy" % a), mmap_mode="r"))
                               for a in step.argument_list))
         ph["sigma"] = cfg["runtime"]["Hi-C"]["intra_sigma"]
+        import igm_b200.steps  # noqa: F401
+        ph["detail"] = {k: round(v, 4) for k, v in sys.modules["igm_b200.steps.ActivationDistanceStep"].LAST_TIMING.items()}
         ph["total_s"] = ph["setup_s"] + ph["task_s"] + ph["reduce_s"]
         ph["pairs_per_s_whole_step"] = ph["pairs"] / ph["total_s"]
         out["sigmas"].append(ph)
