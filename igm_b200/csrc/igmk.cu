@@ -84,11 +84,13 @@ struct igmk_ctx {
                                  // residency: config 5 +4 %; config 2 -1 %)
     int list_form = 1;           // IGMK_LIST: 1 = list form first, key-array kernels for what it hands back; 0 = key arrays only
     float list_z = 1.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
+    int slab_batch = kSlabBatch; // IGMK_SLAB_BATCH: pairs per batch of the slab pipeline (lists of a batch should stay in L2)
     int slab_form = 1;           // IGMK_SLAB: populations > 1024 structures run the list form slab by slab (0: one CTA per pair)
     void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch
     int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
     float list_budget = 20.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
     void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
+    void* d_rec = nullptr; size_t rec_bytes = 0;        // PairRec per pair in processing order
     unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
     bool redo_pending = false;
     int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
@@ -169,6 +171,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov) c->list_z = (float)atof(ov);
     ov = getenv("IGMK_SLAB");
     if (ov) c->slab_form = atoi(ov);
+    ov = getenv("IGMK_SLAB_BATCH");
+    if (ov && atoi(ov) >= 1024) c->slab_batch = atoi(ov);
     ov = getenv("IGMK_LIST_TILE_SLOTS");
     if (ov) c->list_tile_slots = atoi(ov);
     ov = getenv("IGMK_LIST_BUDGET");
@@ -193,6 +197,7 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_pairs);
     cudaFree(c->d_order);
     cudaFree(c->d_redo);
+    cudaFree(c->d_rec);
     cudaFree(c->d_slab);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -390,6 +395,13 @@ static int list_prepare(igmk_ctx* c, ActdistParams& P, cudaStream_t st, int grou
     P.list_z = c->list_z;
     P.list_budget = c->list_budget * (float)group_threads;
     CUDA_TRY(cudaMemsetAsync(P.redo_count, 0, sizeof(unsigned int), st));
+    // pair descriptors in processing order
+    rc = ensure(&c->d_rec, &c->rec_bytes, (size_t)P.n_pairs * sizeof(PairRec));
+    if (rc) return rc;
+    P.rec = (const PairRec*)c->d_rec;
+    build_pairrec_kernel<<<(unsigned)((P.n_pairs + 255) / 256), 256, 0, st>>>(P, (PairRec*)c->d_rec);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
     return IGMK_OK;
 }
 
@@ -402,7 +414,7 @@ static int launch_list_warp(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
     const size_t list_bytes = (size_t)warps * 32 * kListBytes;
     const size_t one_tile = (size_t)24 * c->npad;
-    int slots = (c->tile_block > 0 && c->n_hap < (1 << 20)) ? c->list_tile_slots : 0;
+    int slots = (c->tile_block > 0 && c->nbead < (1 << 20)) ? c->list_tile_slots : 0;     // tile key: bead id
     if (slots > 2) slots = 2;
     while (slots > 0 && list_bytes + slots * one_tile > budget) --slots;
     P.tile_slots = slots;
@@ -450,8 +462,9 @@ static int launch_slab(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     const int nseg = c->npad / kSeg;
     SlabParams S;
     S.nslab = (nseg + kSlabSegs - 1) / kSlabSegs;
-    const size_t off_cnt = (size_t)kSlabBatch * 4, off_lists = 2 * (size_t)kSlabBatch * 4;
-    rc = ensure(&c->d_slab, &c->slab_bytes, off_lists + (size_t)kSlabBatch * kSlabCap * 4);
+    const long long batch = c->slab_batch;
+    const size_t off_cnt = (size_t)batch * 4, off_lists = 2 * (size_t)batch * 4;
+    rc = ensure(&c->d_slab, &c->slab_bytes, off_lists + (size_t)batch * kSlabCap * 4);
     if (rc) return rc;
     S.T = (uint32_t*)c->d_slab;
     S.cnt = (unsigned int*)((char*)c->d_slab + off_cnt);
@@ -460,14 +473,14 @@ static int launch_slab(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
     const size_t list_bytes = (size_t)warps * 32 * kListBytes;
     const size_t one_tile = (size_t)2 * kSlabSegs * kSegFloats * 4;
-    int slots = (c->tile_block > 0 && (long long)c->n_hap * S.nslab < (1 << 20)) ? c->list_tile_slots : 0;
+    int slots = (c->tile_block > 0 && (long long)c->nbead * S.nslab < (1 << 20)) ? c->list_tile_slots : 0;   // key: (bead, slab)
     if (slots > 2) slots = 2;
     P.tile_slots = slots;
     const size_t smem = list_bytes + (size_t)slots * one_tile;
     CUDA_TRY(cudaFuncSetAttribute(slab_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (long long b0 = 0; b0 < P.n_pairs; b0 += kSlabBatch) {
+    for (long long b0 = 0; b0 < P.n_pairs; b0 += batch) {
         S.slot0 = b0;
-        S.nslots = (int)((P.n_pairs - b0 < kSlabBatch) ? P.n_pairs - b0 : kSlabBatch);
+        S.nslots = (int)((P.n_pairs - b0 < batch) ? P.n_pairs - b0 : batch);
         int shift = 9;
         if (c->tile_block > 0) { shift = 0; while ((2 << shift) <= c->tile_block) ++shift; }
         // about eight tasks per CTA at least
@@ -603,6 +616,7 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
     P.tile_block = 0;
     P.tile_slots = 0;
     P.redo = nullptr; P.redo_count = nullptr; P.n_pairs_dev = nullptr; P.list_z = 0.f; P.list_budget = 0.f;
+    P.rec = nullptr;
     c->redo_pending = false;
 
     if (algo == IGMK_ALGO_SIMPLE) return launch_simple(c, P, st);

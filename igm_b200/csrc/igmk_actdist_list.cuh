@@ -45,6 +45,46 @@ constexpr int kListWarps = IGMK_LWPB;
 constexpr int kListBlockThreads = IGMK_LBT;
 static_assert(kListSlots % 8 == 4, "list stride must be 4 mod 8 words");
 
+// ---------------------------------------------------------------- pair descriptors
+__global__ void __launch_bounds__(256)
+build_pairrec_kernel(const ActdistParams P, PairRec* __restrict__ rec) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.n_pairs) return;
+    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
+    const PairDesc d = make_pair_desc(P, __ldg(P.pi + pair), __ldg(P.pj + pair));
+    PairRec r;
+    r.pair = (int32_t)pair;
+    r.a0 = d.a0; r.a1 = d.a1; r.b0 = d.b0; r.b1 = d.b1;
+    r.rcutsq = d.rcutsq;
+    r.bits = (uint32_t)d.keep | ((uint32_t)d.cmask << 4) | ((uint32_t)d.nrec << 8) | ((uint32_t)d.valid << 12);
+    r.omax = 0;
+    if (d.valid) {
+        // o <= o_max: p <= pwish for pwish <= 1 (the post-check of the select does not rely on it)
+        const int total = d.keep * P.nstruct;
+        const double x = __dmul_rn(__dmul_rn((double)d.keep, __ldg(P.pwish + pair)), (double)P.nstruct);
+        const double q = rint(x);
+        r.omax = (q >= (double)(total - 1)) ? (total - 1) : ((q > 0.0) ? (int)q : 0);
+    }
+    reinterpret_cast<uint4*>(rec + slot)[0] = make_uint4((uint32_t)r.pair, (uint32_t)r.a0, (uint32_t)r.a1, (uint32_t)r.b0);
+    reinterpret_cast<uint4*>(rec + slot)[1] = make_uint4((uint32_t)r.b1, __float_as_uint(r.rcutsq), r.bits, (uint32_t)r.omax);
+}
+
+__device__ __forceinline__ PairDesc load_pairrec(const PairRec* rec, long long slot, long long& pair, int& omax) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(rec + slot));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rec + slot) + 1);
+    PairDesc d;
+    pair = (long long)(int32_t)u.x;
+    d.a0 = (int)u.y; d.a1 = (int)u.z; d.b0 = (int)u.w; d.b1 = (int)v.x;
+    d.rcutsq = __uint_as_float(v.y);
+    d.keep = (int)(v.z & 15u);
+    d.cmask = (int)((v.z >> 4) & 15u);
+    d.nrec = (int)((v.z >> 8) & 15u);
+    d.valid = (int)((v.z >> 12) & 1u);
+    d.always_rec = 0;
+    omax = (int)v.w;
+    return d;
+}
+
 struct SampleOut { uint32_t T_bits; int ok; };
 
 // Threshold from the group's first chunks (the first `ns` structures): kw = the 16-bit keys
@@ -321,22 +361,15 @@ template <bool BLOCK>
 __device__ __forceinline__ void process_pair_list(const ActdistParams& P, Group<BLOCK>& g, int V,
                                                   long long slot, const TileCtl& tile,
                                                   uint32_t lbase, uint32_t sred) {
-    const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-    const int i = __ldg(P.pi + pair);
-    const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
+    long long pair;
+    int omax;
+    const PairDesc d = load_pairrec(P.rec, slot, pair, omax);
     if (!d.valid) {                        // uniform over the group
         emit_empty(P, g.tid, pair);
         return;
     }
     const PairPtrs pp = pair_ptrs(P, d);
-    // o <= o_max: p <= pwish for pwish <= 1 (the post-check in select_list does not rely on it)
-    int omax;
-    {
-        const int total = d.keep * P.nstruct;
-        const double x = __dmul_rn(__dmul_rn((double)d.keep, __ldg(P.pwish + pair)), (double)P.nstruct);
-        const double r = rint(x);
-        omax = (r >= (double)(total - 1)) ? (total - 1) : ((r > 0.0) ? (int)r : 0);
-    }
+    const int i = d.a0;                    // key of the locus-i tile: the bead of copy 0
     if (g.tid == 0) sts32(g.ctl, 0u);
     uint32_t T_bits = 0u;
     int mycnt = 0, status;

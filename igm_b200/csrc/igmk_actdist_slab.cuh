@@ -46,13 +46,6 @@ struct SlabParams {
     int bshift;
 };
 
-__device__ __forceinline__ int omax_of(const ActdistParams& P, const PairDesc& d, long long pair) {
-    const int total = d.keep * P.nstruct;
-    const double x = __dmul_rn(__dmul_rn((double)d.keep, __ldg(P.pwish + pair)), (double)P.nstruct);
-    const double r = rint(x);
-    return (r >= (double)(total - 1)) ? (total - 1) : ((r > 0.0) ? (int)r : 0);
-}
-
 // ------------------------------------------------------------------ A: sample
 template <int SH>
 __device__ __forceinline__ void first_chunk_keys(const ActdistParams& P, const PairDesc& d, const PairPtrs& pp,
@@ -86,10 +79,9 @@ slab_sample_kernel(const ActdistParams P, const SlabParams S) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < S.nslots; w += gridDim.x * wpb) {
-        const long long slot = S.slot0 + w;
-        const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-        const int i = __ldg(P.pi + pair);
-        const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
+        long long pair;
+        int omax;
+        const PairDesc d = load_pairrec(P.rec, S.slot0 + w, pair, omax);
         uint32_t T = kNoList;
         if (!d.valid) {
             emit_empty(P, lane, pair);
@@ -104,7 +96,7 @@ slab_sample_kernel(const ActdistParams P, const SlabParams S) {
             }
             const SampleOut so = sample_threshold<false>(make_uint4(kw[0], kw[1], kw[2], kw[3]),
                                                          make_uint4(kw[4], kw[5], kw[6], kw[7]), lane, 32, 0u,
-                                                         d.keep, P.nstruct, omax_of(P, d, pair),
+                                                         d.keep, P.nstruct, omax,
                                                          __float_as_uint(d.rcutsq), P.list_z, P.list_budget);
             if (so.ok && so.T_bits < 0x7f800000u) T = so.T_bits;
             else push_redo(P, lane, pair);
@@ -156,10 +148,10 @@ slab_fill_kernel(const ActdistParams P, const SlabParams S) {
         if (w >= S.nslots) continue;
         uint32_t T_bits = __ldg(S.T + w);
         if (T_bits == kNoList) continue;
-        const long long slot = S.slot0 + w;
-        const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
-        const int i = __ldg(P.pi + pair);
-        const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
+        long long pair;
+        int omax_unused;
+        const PairDesc d = load_pairrec(P.rec, S.slot0 + w, pair, omax_unused);
+        const int i = d.a0;                              // tile key: (bead of copy 0, slab)
         const int Vs = min(kSlabSegs, nseg - slab * kSlabSegs);
         const size_t soff = (size_t)slab * kSlabSegs * kSegFloats;
         PairPtrs pp;
@@ -211,17 +203,22 @@ slab_fill_kernel(const ActdistParams P, const SlabParams S) {
 }
 
 // ------------------------------------------------------------------ C: select
+// #{list <= piv} over a pair's list in global memory (L2); four independent loads per lane
+// and iteration keep enough requests in flight (the select is latency-bound)
 __device__ __forceinline__ int global_count_le(const uint32_t* list, int n, int lane, float piv) {
-    u64 acc = 0ull;
+    u64 acc0 = 0ull, acc1 = 0ull;
     int k = lane;
-    for (; k + 32 < n; k += 64) {
+    for (; k + 96 < n; k += 128) {
         const float x0 = __uint_as_float(__ldg(list + k)), x1 = __uint_as_float(__ldg(list + k + 32));
-        acc = f2add(acc, f2pack(f_le_one(x0, piv), f_le_one(x1, piv)));
+        const float x2 = __uint_as_float(__ldg(list + k + 64)), x3 = __uint_as_float(__ldg(list + k + 96));
+        acc0 = f2add(acc0, f2pack(f_le_one(x0, piv), f_le_one(x1, piv)));
+        acc1 = f2add(acc1, f2pack(f_le_one(x2, piv), f_le_one(x3, piv)));
     }
-    if (k < n) acc = f2add(acc, f2pack(f_le_one(__uint_as_float(__ldg(list + k)), piv), 0.f));
-    float lo, hi;
-    f2split(acc, lo, hi);
-    return __reduce_add_sync(0xffffffffu, (int)(lo + hi));
+    for (; k < n; k += 32) acc0 = f2add(acc0, f2pack(f_le_one(__uint_as_float(__ldg(list + k)), piv), 0.f));
+    float a, b, c, d;
+    f2split(acc0, a, b);
+    f2split(acc1, c, d);
+    return __reduce_add_sync(0xffffffffu, (int)((a + b) + (c + d)));
 }
 
 __global__ void __launch_bounds__(256)
@@ -234,8 +231,9 @@ slab_select_kernel(const ActdistParams P, const SlabParams S) {
     for (int w = blockIdx.x * wpb + wib; w < S.nslots; w += gridDim.x * wpb) {
         const uint32_t T_bits = __ldg(S.T + w);
         if (T_bits == kNoList) continue;                 // uniform over the warp
-        const long long slot = S.slot0 + w;
-        const long long pair = P.perm ? (long long)__ldg(P.perm + slot) : slot;
+        long long pair;
+        int omax_unused;
+        const PairDesc d = load_pairrec(P.rec, S.slot0 + w, pair, omax_unused);
         const unsigned int nraw = __ldg(S.cnt + w);
         if (nraw > (unsigned int)kSlabCap) {             // a list overflowed
             push_redo(P, lane, pair);
@@ -243,8 +241,6 @@ slab_select_kernel(const ActdistParams P, const SlabParams S) {
         }
         const int n = (int)nraw;
         const uint32_t* list = S.lists + (size_t)w * kSlabCap;
-        const int i = __ldg(P.pi + pair);
-        const PairDesc d = make_pair_desc(P, i, __ldg(P.pj + pair));
         const int rcb = (int)__float_as_uint(d.rcutsq), tb = (int)T_bits;
         const int cnt = (rcb >= tb) ? n : global_count_le(list, n, lane, d.rcutsq);
         double p;

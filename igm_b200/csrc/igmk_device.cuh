@@ -72,8 +72,21 @@ struct ActdistParams {
     int32_t* redo;
     unsigned int* redo_count;
     const unsigned int* n_pairs_dev;
+    const struct PairRec* rec;    // list form: one 32-byte descriptor per pair in processing order (build_pairrec_kernel)
     float list_z;             // safety margin of the sample threshold, in standard deviations
     float list_budget;        // expected list length beyond which a pair goes to the key-array kernel
+};
+
+// Everything the list-form kernels need to know about one pair before they touch a
+// coordinate, gathered once per launch in processing order (one coalesced 32-byte read per
+// pair instead of the chain  perm -> i, j, pwish -> two index entries).
+struct __align__(16) PairRec {
+    int32_t  pair;     // index in the caller's list
+    int32_t  a0, a1;   // beads of locus i (-1: absent)
+    int32_t  b0, b1;   // beads of locus j
+    float    rcutsq;
+    uint32_t bits;     // keep | cmask << 4 | nrec << 8 | valid << 12
+    int32_t  omax;     // upper bound of the order-statistic index (p <= pwish)
 };
 
 // Combination shapes of one pair (which of the four copy combinations
