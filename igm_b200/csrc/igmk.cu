@@ -84,6 +84,7 @@ struct igmk_ctx {
                                  // residency: config 5 +4 %; config 2 -1 %)
     int list_form = 1;           // IGMK_LIST: 1 = list form first, key-array kernels for what it hands back; 0 = key arrays only
     float list_z = 1.5f;         // IGMK_LIST_Z: margin of the sample threshold (standard deviations)
+    int jblock_slab = 1;         // IGMK_JBLOCK_SLAB: slab pipeline sizes J-blocks by one slab's rows (0: whole rows; +2 %)
     int slab_batch = kSlabBatch; // IGMK_SLAB_BATCH: pairs per batch of the slab pipeline (lists of a batch should stay in L2)
     int slab_form = 1;           // IGMK_SLAB: populations > 1024 structures run the list form slab by slab (0: one CTA per pair)
     void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch
@@ -171,6 +172,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov) c->list_z = (float)atof(ov);
     ov = getenv("IGMK_SLAB");
     if (ov) c->slab_form = atoi(ov);
+    ov = getenv("IGMK_JBLOCK_SLAB");
+    if (ov) c->jblock_slab = atoi(ov);
     ov = getenv("IGMK_SLAB_BATCH");
     if (ov && atoi(ov) >= 1024) c->slab_batch = atoi(ov);
     ov = getenv("IGMK_LIST_TILE_SLOTS");
@@ -535,7 +538,11 @@ static int order_pairs(igmk_ctx* c, int64_t n_pairs, const int32_t* d_j, cudaStr
                        const int32_t** perm_out) {
     *perm_out = nullptr;
     if (c->l2_budget <= 0 || n_pairs < c->order_min_pairs || n_pairs > 0x7fffffffLL) return IGMK_OK;
-    const long long per_locus = 2ll * 12 * c->npad;
+    // rows one locus contributes to the working set: whole rows, or - slab pipeline
+    // (IGMK_JBLOCK_SLAB=1) - the rows of one slab only: a slab's J-block then fills the L2 budget
+    long long per_locus = 2ll * 12 * c->npad;
+    if (c->jblock_slab && c->list_form && c->slab_form && c->group_threads == 0 && c->nchunks > 256)
+        per_locus = 2ll * 12 * 1024;
     long long lpb = c->l2_budget / per_locus;
     if (lpb < 1) lpb = 1;
     const int nblk = (int)((c->n_hap + lpb - 1) / lpb);
