@@ -41,6 +41,7 @@ EXPORTS = (
     "igmk_rank_match_device", "igmk_rank_match_host",
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms", "igmk_last_redo_count",
     "igmk_actdist_sel_index_device", "igmk_actdist_sel_index_host",
+    "igmk_actdist_host_population",
 )
 
 
@@ -67,6 +68,8 @@ def _declare(lib: C.CDLL) -> None:
                                         C.c_int, C.c_int, C.c_int, vp, vp]
     lib.igmk_actdist_host.argtypes = [vp, C.c_int64, i32p, i32p, f64p, f64p, C.c_float,
                                       C.c_int, C.c_int, C.c_int, vp]
+    lib.igmk_actdist_host_population.argtypes = [vp, f32p, C.c_int64, i32p, i32p, f64p, f64p, C.c_float,
+                                                 C.c_int, C.c_int, C.c_int, vp]
     lib.igmk_actdist_device_peers.argtypes = [vp, C.c_int64, i32p, i32p, f64p, f64p, C.c_float,
                                               C.c_int, C.c_int, vp, C.c_int, vp]
     lib.igmk_finish_results_device.argtypes = [vp, vp, C.c_int64, vp]

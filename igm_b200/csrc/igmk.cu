@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -65,6 +66,12 @@ struct igmk_ctx {
     void* d_pairs = nullptr; size_t pairs_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of igmk_actdist_host
+    cudaStream_t s_up = nullptr;                      // re-layout kernels of the pipelined population upload (highest priority)
+    // igmk_actdist_host_population: beads the loci >= l need, as suffix minima per bead region
+    // (region 0: first copies, region 1: second copies; merged into one when they interleave)
+    int up_nreg = 0, up_lo_reg[2] = {0, 0}, up_hi_reg[2] = {0, 0};
+    std::vector<int> up_lo[2];
+    int up_piece = 0;                                 // pieces uploaded by the operation in flight (staging buffer parity)
     std::vector<cudaEvent_t> ev_in, ev_k;
     long long host_slice_pairs = 1 << 19;             // IGMK_HOST_SLICE
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -143,6 +150,11 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int pr_lo = 0, pr_hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_up, cudaStreamNonBlocking, pr_hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e != cudaSuccess) {
@@ -209,14 +221,18 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_up) cudaStreamDestroy(c->s_up);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return IGMK_OK;
 }
 
 // (nb, nstruct, 3) bead-major AoS  ->  [bead][segment of 128 structures][xyz][128]
-__global__ void stage_coords_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                    int nstruct, int npad) {
+// 128 threads at <= 32 registers: a block fits into the 4096 registers the persistent list
+// kernel (640 threads x 96) leaves free on an SM, so the pipelined upload
+// (igmk_actdist_host_population) re-lays out pieces while the pair kernel runs.
+__global__ void __launch_bounds__(128, 16)
+stage_coords_kernel(const float* __restrict__ src, float* __restrict__ dst, int nstruct, int npad) {
     const size_t bead = blockIdx.x;
     const float* s = src + bead * (size_t)nstruct * 3;
     float* d = dst + bead * (size_t)npad * 3;
@@ -226,46 +242,69 @@ __global__ void stage_coords_kernel(const float* __restrict__ src, float* __rest
     }
 }
 
-extern "C" int igmk_upload_coords_range(igmk_ctx* c, const float* xyz, int bead0, int nb, int on_device) {
-    if (!c || !xyz) return fail(IGMK_EINVAL, "igmk_upload_coords: NULL argument");
-    if (bead0 < 0 || nb < 0 || bead0 + nb > c->nbead) return fail(IGMK_EINVAL, "igmk_upload_coords: bead range out of bounds");
-    CUDA_TRY(cudaSetDevice(c->device));
+// Beads per piece of a host upload: two staging buffers of <= 64 MiB each.
+static int upload_step(const igmk_ctx* c) {
     const size_t per_bead = (size_t)c->nstruct * 3 * sizeof(float);
-    if (on_device) {
-        // already in HBM: one re-layout launch per 2^30 beads-worth of grid
-        stage_coords_kernel<<<nb, 256, 0, c->stream>>>(xyz, c->d_coords + (size_t)bead0 * 3 * c->npad, c->nstruct, c->npad);
-        g_launches++;
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        c->have_coords = true;
-        return IGMK_OK;
-    }
-    // Host memory: two staging buffers of <= 64 MiB; the copy of chunk k + 1 (copy-in
-    // stream) overlaps the re-layout kernel of chunk k (compute stream).  Pinned host
-    // memory (igmk_host_alloc, torch pin_memory) makes the copies asynchronous.
-    int step = (int)((64ull << 20) / per_bead);
+    long long step = (long long)((64ull << 20) / per_bead);
     if (step < 1) step = 1;
-    if (step > nb) step = nb;
-    if (nb == 0) { c->have_coords = true; return IGMK_OK; }
-    int rc = ensure(&c->d_stage, &c->stage_bytes, 2 * (size_t)step * per_bead);
+    if (step > c->nbead) step = c->nbead;
+    return (int)step;
+}
+
+static int upload_begin(igmk_ctx* c) {
+    const size_t per_bead = (size_t)c->nstruct * 3 * sizeof(float);
+    int rc = ensure(&c->d_stage, &c->stage_bytes, 2 * (size_t)upload_step(c) * per_bead);
     if (rc) return rc;
     if (!c->ev_up[0]) {
         for (int k = 0; k < 4; ++k) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_up[k], cudaEventDisableTiming));
     }
-    int k = 0;
-    for (int b = 0; b < nb; b += step, ++k) {
-        const int n = (nb - b < step) ? nb - b : step;
+    c->up_piece = 0;
+    return IGMK_OK;
+}
+
+// Beads [bead0, bead0 + nb) -> HBM from the host array `xyz` (.hss layout, its first row is
+// bead0), asynchronously: the copy of piece k + 1 (copy-in stream) overlaps the re-layout kernel of
+// piece k (stream sk).  Pinned host memory (igmk_host_alloc, torch pin_memory) makes the
+// copies asynchronous.  After the call ev_up[2 + ((up_piece - 1) & 1)] marks "everything
+// uploaded so far is in place" (the re-layout kernels are ordered on sk).
+static int upload_pieces(igmk_ctx* c, const float* xyz, int bead0, int nb, cudaStream_t sk) {
+    const size_t per_bead = (size_t)c->nstruct * 3 * sizeof(float);
+    const int step = upload_step(c);
+    for (int b = 0; b < nb; b += step) {
+        const int n = (nb - b < step) ? nb - b : step, k = c->up_piece++;
         float* buf = (float*)((char*)c->d_stage + (size_t)(k & 1) * step * per_bead);
         if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->ev_up[2 + (k & 1)], 0));     // the kernel that read this buffer
         CUDA_TRY(cudaMemcpyAsync(buf, xyz + (size_t)b * c->nstruct * 3, (size_t)n * per_bead, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaEventRecord(c->ev_up[k & 1], c->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_up[k & 1], 0));
-        stage_coords_kernel<<<n, 256, 0, c->stream>>>(buf, c->d_coords + (size_t)(bead0 + b) * 3 * c->npad,
-                                                     c->nstruct, c->npad);
+        CUDA_TRY(cudaStreamWaitEvent(sk, c->ev_up[k & 1], 0));
+        stage_coords_kernel<<<n, 128, 0, sk>>>(buf, c->d_coords + (size_t)(bead0 + b) * 3 * c->npad, c->nstruct, c->npad);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(c->ev_up[2 + (k & 1)], c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_up[2 + (k & 1)], sk));
     }
+    return IGMK_OK;
+}
+
+extern "C" int igmk_upload_coords_range(igmk_ctx* c, const float* xyz, int bead0, int nb, int on_device) {
+    if (!c || !xyz) return fail(IGMK_EINVAL, "igmk_upload_coords: NULL argument");
+    if (bead0 < 0 || nb < 0 || bead0 + nb > c->nbead) return fail(IGMK_EINVAL, "igmk_upload_coords: bead range out of bounds");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (on_device) {
+        // already in HBM: one re-layout launch
+        if (nb > 0) {
+            stage_coords_kernel<<<nb, 128, 0, c->stream>>>(xyz, c->d_coords + (size_t)bead0 * 3 * c->npad, c->nstruct, c->npad);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        c->have_coords = true;
+        return IGMK_OK;
+    }
+    if (nb == 0) { c->have_coords = true; return IGMK_OK; }
+    int rc = upload_begin(c);
+    if (rc) return rc;
+    rc = upload_pieces(c, xyz, bead0, nb, c->stream);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->have_coords = true;
     return IGMK_OK;
@@ -299,6 +338,36 @@ extern "C" int igmk_set_index(igmk_ctx* c, int n_hap, const int32_t* copy_ptr,
     c->h_hap.swap(h);
     c->n_hap = n_hap;
     c->have_index = true;
+    // Pipelined population upload (igmk_actdist_host_population): the beads every locus >= l
+    // needs form, per copy, the range [suffix minimum, region end) - whatever the index looks
+    // like; a monotone index (the usual one) makes consecutive ranges disjoint.
+    {
+        const int kNone = 0x7fffffff;
+        int mn[2] = {kNone, kNone}, mx[2] = {-1, -1};
+        for (int r = 0; r < 2; ++r) c->up_lo[r].assign((size_t)n_hap + 1, kNone);
+        for (int l = n_hap - 1; l >= 0; --l) {
+            const int b[2] = {c->h_hap[l].b0, c->h_hap[l].b1};
+            for (int r = 0; r < 2; ++r) {
+                int v = c->up_lo[r][l + 1];
+                if (b[r] >= 0) {
+                    v = (b[r] < v) ? b[r] : v;
+                    mn[r] = (b[r] < mn[r]) ? b[r] : mn[r];
+                    mx[r] = (b[r] > mx[r]) ? b[r] : mx[r];
+                }
+                c->up_lo[r][l] = v;
+            }
+        }
+        const bool two = mx[1] >= 0 && (mx[0] < mn[1] || mx[1] < mn[0]);     // disjoint bead regions
+        if (two) {
+            c->up_nreg = 2;
+            for (int r = 0; r < 2; ++r) { c->up_lo_reg[r] = mn[r]; c->up_hi_reg[r] = mx[r] + 1; }
+        } else {
+            c->up_nreg = 1;
+            for (int l = 0; l <= n_hap; ++l) c->up_lo[0][l] = (c->up_lo[1][l] < c->up_lo[0][l]) ? c->up_lo[1][l] : c->up_lo[0][l];
+            c->up_lo_reg[0] = (mn[1] < mn[0]) ? mn[1] : mn[0];
+            c->up_hi_reg[0] = ((mx[1] > mx[0]) ? mx[1] : mx[0]) + 1;
+        }
+    }
     return IGMK_OK;
 }
 
@@ -802,15 +871,17 @@ extern "C" int igmk_damid_actdist_host(igmk_ctx* c, int64_t n_loci, const int32_
     return IGMK_OK;
 }
 
-extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
-                                 const int32_t* i, const int32_t* j,
-                                 const double* pwish, const double* plast,
-                                 float contact_range, int it_corr, int mode, int algo,
-                                 igmk_pair_result* out) {
-    if (!c) return fail(IGMK_EINVAL, "igmk_actdist_host: NULL context");
-    if (n_pairs == 0) return IGMK_OK;
-    if (n_pairs < 0 || !i || !j || !pwish || !plast || !out) return fail(IGMK_EINVAL, "igmk_actdist_host: bad argument");
-    CUDA_TRY(cudaSetDevice(c->device));
+// Host-buffer form of the A-step.  xyz == nullptr: the population is resident.  Otherwise
+// the population (.hss layout, host memory) is staged by the same call, overlapped with the
+// pair kernels: the pair list is worked off from its END in slices, and before slice k is
+// launched only the beads its loci (and all higher ones) need are uploaded - for a list
+// sorted by (i, j > i), as setup() writes it (ActivationDistanceStep.py:166-178), the last
+// slice needs the top 1 / nslices of the loci, and each earlier slice a little more.
+static int actdist_host_impl(igmk_ctx* c, const float* xyz, int64_t n_pairs,
+                             const int32_t* i, const int32_t* j,
+                             const double* pwish, const double* plast,
+                             float contact_range, int it_corr, int mode, int algo,
+                             igmk_pair_result* out) {
     const size_t n = (size_t)n_pairs;
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     const size_t off_j = up(n * 4), off_pw = off_j + up(n * 4), off_pl = off_pw + up(n * 8);
@@ -819,9 +890,9 @@ extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
     int rc = ensure(&c->d_pairs, &c->pairs_bytes, total);
     if (rc) return rc;
     char* base = (char*)c->d_pairs;
-    // Three-stage pipeline over slices of the pair list: inputs of slice k+1 go up
-    // (copy-in stream) and results of slice k-1 come down (copy-out stream) while
-    // the kernel works on slice k.  Overlap needs pinned host buffers
+    // Three-stage pipeline over slices of the pair list: inputs of the next slice go up
+    // (copy-in stream) and results of the previous one come down (copy-out stream) while
+    // the kernel works on the current slice.  Overlap needs pinned host buffers
     // (igmk_host_alloc); pageable ones still work, serialised by the driver.
     const size_t slice = (size_t)c->host_slice_pairs;
     const int nsl = (int)((n + slice - 1) / slice);
@@ -833,9 +904,35 @@ extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
             CUDA_TRY(cudaEventCreateWithFlags(&c->ev_k[t], cudaEventDisableTiming));
         }
     }
+    int cur[2] = {0, 0}, m_run = c->n_hap;
+    if (xyz) {
+        rc = upload_begin(c);
+        if (rc) return rc;
+        for (int r = 0; r < c->up_nreg; ++r) cur[r] = c->up_hi_reg[r];
+        c->have_coords = true;           // every launch below is ordered after the pieces it reads
+    }
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-    for (int k = 0; k < nsl; ++k) {
+    for (int t = 0; t < nsl; ++t) {
+        const int k = xyz ? nsl - 1 - t : t;
         const size_t lo = (size_t)k * slice, cnt = (n - lo < slice) ? n - lo : slice;
+        if (xyz) {
+            int m = m_run;
+            for (size_t q = lo; q < lo + cnt; ++q) {
+                const int a = i[q], b = j[q];
+                m = (a < m) ? a : m;
+                m = (b < m) ? b : m;
+            }
+            m_run = (m < 0) ? 0 : m;                   // (out-of-range pairs are flagged by the kernel)
+            for (int r = 0; r < c->up_nreg; ++r) {
+                const int want = c->up_lo[r][m_run];
+                if (want < cur[r]) {
+                    rc = upload_pieces(c, xyz + (size_t)want * c->nstruct * 3, want, cur[r] - want, c->s_up);
+                    if (rc) { cudaDeviceSynchronize(); c->have_coords = false; return rc; }
+                    cur[r] = want;
+                }
+            }
+            if (c->up_piece > 0) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_up[2 + ((c->up_piece - 1) & 1)], 0));
+        }
         CUDA_TRY(cudaMemcpyAsync(base + lo * 4, i + lo, cnt * 4, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaMemcpyAsync(base + off_j + lo * 4, j + lo, cnt * 4, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaMemcpyAsync(base + off_pw + lo * 8, pwish + lo, cnt * 8, cudaMemcpyHostToDevice, c->s_in));
@@ -846,16 +943,61 @@ extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
         rc = igmk_actdist_device(c, (int64_t)cnt, (const int32_t*)base + lo, (const int32_t*)(base + off_j) + lo,
                                  (const double*)(base + off_pw) + lo, (const double*)(base + off_pl) + lo,
                                  contact_range, it_corr, mode, algo, d_out, c->stream);
-        if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (rc) { cudaDeviceSynchronize(); if (xyz) c->have_coords = false; return rc; }
         CUDA_TRY(cudaEventRecord(c->ev_k[k], c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
         CUDA_TRY(cudaMemcpyAsync(out + lo, d_out, cnt * sizeof(igmk_pair_result), cudaMemcpyDeviceToHost, c->s_out));
     }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    if (xyz) {
+        // the beads no pair of the list touched: the context ends up fully staged
+        int iv[2][2], niv = c->up_nreg;
+        for (int r = 0; r < niv; ++r) { iv[r][0] = cur[r]; iv[r][1] = c->up_hi_reg[r]; }
+        if (niv == 2 && iv[1][0] < iv[0][0]) { std::swap(iv[0][0], iv[1][0]); std::swap(iv[0][1], iv[1][1]); }
+        int pos = 0;
+        for (int r = 0; r <= niv; ++r) {
+            const int end = (r < niv) ? iv[r][0] : c->nbead;
+            if (end > pos) {
+                rc = upload_pieces(c, xyz + (size_t)pos * c->nstruct * 3, pos, end - pos, c->s_up);
+                if (rc) { cudaDeviceSynchronize(); c->have_coords = false; return rc; }
+            }
+            if (r < niv) pos = (iv[r][1] > pos) ? iv[r][1] : pos;
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->s_up));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->s_out));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(&c->last_kernel_ms, c->ev0, c->ev1));
     return IGMK_OK;
+}
+
+extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
+                                 const int32_t* i, const int32_t* j,
+                                 const double* pwish, const double* plast,
+                                 float contact_range, int it_corr, int mode, int algo,
+                                 igmk_pair_result* out) {
+    if (!c) return fail(IGMK_EINVAL, "igmk_actdist_host: NULL context");
+    if (n_pairs == 0) return IGMK_OK;
+    if (n_pairs < 0 || !i || !j || !pwish || !plast || !out) return fail(IGMK_EINVAL, "igmk_actdist_host: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return actdist_host_impl(c, nullptr, n_pairs, i, j, pwish, plast, contact_range, it_corr, mode, algo, out);
+}
+
+extern "C" int igmk_actdist_host_population(igmk_ctx* c, const float* xyz, int64_t n_pairs,
+                                            const int32_t* i, const int32_t* j,
+                                            const double* pwish, const double* plast,
+                                            float contact_range, int it_corr, int mode, int algo,
+                                            igmk_pair_result* out) {
+    if (!c || !xyz) return fail(IGMK_EINVAL, "igmk_actdist_host_population: NULL argument");
+    if (!c->have_index) return fail(IGMK_ESTATE, "igmk_actdist_host_population: set the index first");
+    if (n_pairs < 0 || (n_pairs > 0 && (!i || !j || !pwish || !plast || !out)))
+        return fail(IGMK_EINVAL, "igmk_actdist_host_population: bad argument");
+    if (mode != IGMK_MODE_LB && mode != IGMK_MODE_GP) return fail(IGMK_EINVAL, "igmk_actdist_host_population: bad mode %d", mode);
+    if (algo != IGMK_ALGO_FAST && algo != IGMK_ALGO_SIMPLE) return fail(IGMK_EINVAL, "igmk_actdist_host_population: bad algo %d", algo);
+    if (n_pairs == 0) return igmk_upload_coords(c, xyz, 0);
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->have_coords = false;
+    return actdist_host_impl(c, xyz, n_pairs, i, j, pwish, plast, contact_range, it_corr, mode, algo, out);
 }
 
 extern "C" float igmk_last_kernel_ms(igmk_ctx* c) { return c ? c->last_kernel_ms : 0.f; }

@@ -231,6 +231,30 @@ class ActdistEngine:
                                           ptr(out)))
         return out
 
+    def actdist_with_population(self, xyz, i, j, pwish, plast=None, contact_range: float = 2.0,
+                                it_corr: int = 0, mode="LB", algo: int = ALGO_FAST, out=None) -> np.ndarray:
+        """``upload_coordinates(xyz)`` + ``actdist(...)`` as ONE pipelined device operation
+        (igmk_actdist_host_population): the population upload hides behind the pair kernels.
+        ``xyz``: host array (nbead, nstruct, 3) float32, ideally page-locked
+        (``pinned_array`` / ``StagedHss.coordinates``); the index must be set."""
+        mode = _MODES[mode]
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        if xyz.shape != (self.nbead, self.nstruct, 3):
+            raise ValueError("coordinates must be (%d, %d, 3), got %r" % (self.nbead, self.nstruct, xyz.shape))
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        pwish = np.ascontiguousarray(pwish, dtype=np.float64)
+        plast = np.zeros(len(i), np.float64) if plast is None else np.ascontiguousarray(plast, dtype=np.float64)
+        if not (len(i) == len(j) == len(pwish) == len(plast)):
+            raise ValueError("pair arrays must have equal length")
+        self._validate_pairs(i, j, mode)
+        if out is None:
+            out = np.zeros(len(i), dtype=PAIR_RESULT_DTYPE)
+        check(self._lib.igmk_actdist_host_population(self._ctx, ptr(xyz), len(i), ptr(i), ptr(j), ptr(pwish),
+                                                     ptr(plast), float(np.float32(contact_range)), int(it_corr),
+                                                     mode, int(algo), ptr(out)))
+        return out
+
     def actdist_device(self, d_i, d_j, d_pwish, d_plast, d_out, n_pairs: Optional[int] = None,
                        contact_range: float = 2.0, it_corr: int = 0, mode="LB",
                        algo: int = ALGO_FAST, stream: int = 0) -> None:

@@ -103,6 +103,23 @@ int igmk_actdist_host(igmk_ctx* ctx, int64_t n_pairs,
                       float contact_range, int it_corr, int mode, int algo,
                       igmk_pair_result* out);
 
+/* The whole device side of ActivationDistanceStep.task in one call: stage the population
+ * `xyz` (host memory, the .hss layout of igmk_upload_coords; every A-step follows an M-step
+ * that rewrote it, igm/steps/ModelingStep.py:730-782, read back through
+ * igm/core/step.py:386-392) AND run get_actdist over the pair list, with the upload hidden
+ * behind the pair kernels: slices of the list are taken from its end, and a slice is launched
+ * as soon as the beads of its loci and of all higher ones are in HBM (setup() writes the
+ * list sorted by i with j > i, ActivationDistanceStep.py:166-178, so the last slice needs
+ * only the top of the population).  Any list order and any copy index give the same results
+ * as igmk_upload_coords + igmk_actdist_host; they only overlap less.  The index must be set;
+ * afterwards the context holds the whole population.  Page-locked buffers make the copies
+ * asynchronous. */
+int igmk_actdist_host_population(igmk_ctx* ctx, const float* xyz, int64_t n_pairs,
+                                 const int32_t* i, const int32_t* j,
+                                 const double* pwish, const double* plast,
+                                 float contact_range, int it_corr, int mode, int algo,
+                                 igmk_pair_result* out);
+
 /* sel_flat_idx (the "selected structure index" of the A-step): for every pair the index, in
  * d_sq[0:npc].ravel() = row * nstruct + structure (:439-448; d_sq is column-sorted there, so
  * the row is the value's rank among the copy combinations of its structure), of the element
