@@ -51,7 +51,19 @@ static int fail(int code, const char* fmt, ...) {
                         cudaGetErrorString(_e), __FILE__, __LINE__);                \
     } while (0)
 
+// Per-launch scratch of the A-step.  Two sets: igmk_actdist_host* alternates them (and two
+// compute streams) between consecutive slices of the list, so the short kernels that end a
+// slice (redo, finish) run beside the next slice's list kernel instead of after a drained GPU.
+struct LaunchScratch {
+    void* d_order = nullptr; size_t order_bytes = 0;    // keys / values / cub temp of order_pairs()
+    void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
+    void* d_rec = nullptr; size_t rec_bytes = 0;        // PairRec per pair in processing order
+    void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch (slab pipeline)
+};
+
 struct igmk_ctx {
+    LaunchScratch scr[2];
+    int cur = 0;                                        // scratch set of the launch being issued
     int device = 0;
     int nbead = 0, nstruct = 0, npad = 0, nchunks = 0, n_hap = 0;
     int sm_count = 0;
@@ -65,6 +77,9 @@ struct igmk_ctx {
     void* d_stage = nullptr; size_t stage_bytes = 0;
     void* d_pairs = nullptr; size_t pairs_bytes = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                   // second compute stream (odd slices of igmk_actdist_host*)
+    cudaEvent_t ev_join = nullptr;
+    int host_overlap = 1;                             // IGMK_HOST_OVERLAP: consecutive slices on alternating streams (N <= 1024)
     cudaStream_t s_in = nullptr, s_out = nullptr;     // copy streams of igmk_actdist_host
     cudaStream_t s_up = nullptr;                      // re-layout kernels of the pipelined population upload (highest priority)
     // igmk_actdist_host_population: beads the loci >= l need, as suffix minima per bead region
@@ -74,6 +89,7 @@ struct igmk_ctx {
     int up_piece = 0;                                 // pieces uploaded by the operation in flight (staging buffer parity)
     std::vector<cudaEvent_t> ev_in, ev_k;
     long long host_slice_pairs = 1 << 19;             // IGMK_HOST_SLICE
+    int host_slice_ramp = 3;                          // IGMK_HOST_RAMP: slices ramp up from (and down to) slice >> ramp at the ends of a long list
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr};   // coordinate upload: copy done x2, kernel done x2
     float last_kernel_ms = 0.f;
@@ -81,7 +97,6 @@ struct igmk_ctx {
     int warps_per_cta = 0;       // IGMK_WARPS_PER_CTA
     long long l2_budget = 80ll << 20;   // IGMK_L2_BUDGET: bytes of locus-j rows one J-block may hold
     long long order_min_pairs = 65536;  // IGMK_ORDER_MIN: shorter lists keep the input order
-    void* d_order = nullptr; size_t order_bytes = 0;    // keys / values / cub temp of order_pairs()
     int tile_block = 512;        // IGMK_TILE_BLOCK (0: no shared-memory locus-i tile)
     int tile_slots = 1;          // IGMK_TILE_SLOTS (2 slots shrink L1 to 15 KB at N = 1000: slower)
     unsigned int* d_blockctr = nullptr;   // ring of 64 block counters (one per launch in flight)
@@ -94,11 +109,8 @@ struct igmk_ctx {
     int jblock_slab = 1;         // IGMK_JBLOCK_SLAB: slab pipeline sizes J-blocks by one slab's rows (0: whole rows; +2 %)
     int slab_batch = kSlabBatch; // IGMK_SLAB_BATCH: pairs per batch of the slab pipeline (lists of a batch should stay in L2)
     int slab_form = 1;           // IGMK_SLAB: populations > 1024 structures run the list form slab by slab (0: one CTA per pair)
-    void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch
     int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
     float list_budget = 20.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
-    void* d_redo = nullptr; size_t redo_bytes = 0;      // [256 B counter][n_pairs int32]
-    void* d_rec = nullptr; size_t rec_bytes = 0;        // PairRec per pair in processing order
     unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
     bool redo_pending = false;
     int block_stop = 32;         // IGMK_BLOCK_STOP: CTA groups leave the key bisection at <= this many candidates (larger: measured slower)
@@ -148,6 +160,8 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(&c->d_radii, (size_t)nbead * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_blockctr, 64 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
@@ -174,6 +188,10 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     if (ov) c->tile_block = atoi(ov);
     ov = getenv("IGMK_HOST_SLICE");
     if (ov && atoll(ov) > 0) c->host_slice_pairs = atoll(ov);
+    ov = getenv("IGMK_HOST_OVERLAP");
+    if (ov) c->host_overlap = atoi(ov);
+    ov = getenv("IGMK_HOST_RAMP");
+    if (ov) c->host_slice_ramp = atoi(ov);
     ov = getenv("IGMK_WARPS_PER_CTA");
     if (ov) c->warps_per_cta = atoi(ov);
     ov = getenv("IGMK_DYNAMIC_BLOCKS");
@@ -210,10 +228,12 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     cudaFree(c->d_hap);
     cudaFree(c->d_stage);
     cudaFree(c->d_pairs);
-    cudaFree(c->d_order);
-    cudaFree(c->d_redo);
-    cudaFree(c->d_rec);
-    cudaFree(c->d_slab);
+    for (LaunchScratch& sc : c->scr) {
+        cudaFree(sc.d_order);
+        cudaFree(sc.d_redo);
+        cudaFree(sc.d_rec);
+        cudaFree(sc.d_slab);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_up) if (e) cudaEventDestroy(e);
@@ -223,6 +243,8 @@ extern "C" int igmk_destroy(igmk_ctx* c) {
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->s_up) cudaStreamDestroy(c->s_up);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return IGMK_OK;
 }
@@ -459,19 +481,19 @@ static int launch_block(const igmk_ctx* c, const ActdistParams& Pin, int threads
 // First launch: igmk_actdist_list.cuh over the whole list; second launch: the key-array
 // kernels over the pairs the first one handed back (count and order live on the device).
 static int list_prepare(igmk_ctx* c, ActdistParams& P, cudaStream_t st, int group_threads) {
-    int rc = ensure(&c->d_redo, &c->redo_bytes, 256 + (size_t)P.n_pairs * sizeof(int32_t));
+    int rc = ensure(&c->scr[c->cur].d_redo, &c->scr[c->cur].redo_bytes, 256 + (size_t)P.n_pairs * sizeof(int32_t));
     if (rc) return rc;
-    P.redo_count = (unsigned int*)c->d_redo;
-    P.redo = (int32_t*)((char*)c->d_redo + 256);
+    P.redo_count = (unsigned int*)c->scr[c->cur].d_redo;
+    P.redo = (int32_t*)((char*)c->scr[c->cur].d_redo + 256);
     P.n_pairs_dev = nullptr;
     P.list_z = c->list_z;
     P.list_budget = c->list_budget * (float)group_threads;
     CUDA_TRY(cudaMemsetAsync(P.redo_count, 0, sizeof(unsigned int), st));
     // pair descriptors in processing order
-    rc = ensure(&c->d_rec, &c->rec_bytes, (size_t)P.n_pairs * sizeof(PairRec));
+    rc = ensure(&c->scr[c->cur].d_rec, &c->scr[c->cur].rec_bytes, (size_t)P.n_pairs * sizeof(PairRec));
     if (rc) return rc;
-    P.rec = (const PairRec*)c->d_rec;
-    build_pairrec_kernel<<<(unsigned)((P.n_pairs + 255) / 256), 256, 0, st>>>(P, (PairRec*)c->d_rec);
+    P.rec = (const PairRec*)c->scr[c->cur].d_rec;
+    build_pairrec_kernel<<<(unsigned)((P.n_pairs + 255) / 256), 256, 0, st>>>(P, (PairRec*)c->scr[c->cur].d_rec);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return IGMK_OK;
@@ -536,11 +558,11 @@ static int launch_slab(igmk_ctx* c, ActdistParams P, cudaStream_t st) {
     S.nslab = (nseg + kSlabSegs - 1) / kSlabSegs;
     const long long batch = c->slab_batch;
     const size_t off_cnt = (size_t)batch * 4, off_lists = 2 * (size_t)batch * 4;
-    rc = ensure(&c->d_slab, &c->slab_bytes, off_lists + (size_t)batch * kSlabCap * 4);
+    rc = ensure(&c->scr[c->cur].d_slab, &c->scr[c->cur].slab_bytes, off_lists + (size_t)batch * kSlabCap * 4);
     if (rc) return rc;
-    S.T = (uint32_t*)c->d_slab;
-    S.cnt = (unsigned int*)((char*)c->d_slab + off_cnt);
-    S.lists = (uint32_t*)((char*)c->d_slab + off_lists);
+    S.T = (uint32_t*)c->scr[c->cur].d_slab;
+    S.cnt = (unsigned int*)((char*)c->scr[c->cur].d_slab + off_cnt);
+    S.lists = (uint32_t*)((char*)c->scr[c->cur].d_slab + off_lists);
     int warps = kSlabWarps;
     if (c->warps_per_cta > 0 && warps > c->warps_per_cta) warps = c->warps_per_cta;
     const size_t list_bytes = (size_t)warps * 32 * kListBytes;
@@ -624,9 +646,9 @@ static int order_pairs(igmk_ctx* c, int64_t n_pairs, const int32_t* d_j, cudaStr
     cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                     (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, bits, st);
     const size_t total = 4 * up(n * 4) + up(temp);
-    int rc = ensure(&c->d_order, &c->order_bytes, total);
+    int rc = ensure(&c->scr[c->cur].d_order, &c->scr[c->cur].order_bytes, total);
     if (rc) return rc;
-    char* base = (char*)c->d_order;
+    char* base = (char*)c->scr[c->cur].d_order;
     uint32_t* k_in = (uint32_t*)base;
     uint32_t* k_out = (uint32_t*)(base + up(n * 4));
     int32_t* v_in = (int32_t*)(base + 2 * up(n * 4));
@@ -718,8 +740,8 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
                            : (c->slab_form ? launch_slab(c, P, st) : launch_list_block(c, P, (T + 31) / 32 * 32, st));
         if (rc) return rc;
         ActdistParams R = P;
-        R.redo_count = (unsigned int*)c->d_redo;
-        R.redo = (int32_t*)((char*)c->d_redo + 256);
+        R.redo_count = (unsigned int*)c->scr[c->cur].d_redo;
+        R.redo = (int32_t*)((char*)c->scr[c->cur].d_redo + 256);
         R.perm = R.redo;
         R.n_pairs_dev = R.redo_count;
         c->redo_pending = true;
@@ -732,10 +754,10 @@ static int actdist_launch(igmk_ctx* c, int64_t n_pairs,
 // context (diagnostic; synchronises the device).
 extern "C" int64_t igmk_last_redo_count(igmk_ctx* c) {
     if (!c) return -1;
-    if (!c->redo_pending || !c->d_redo) return 0;
+    if (!c->redo_pending || !c->scr[c->cur].d_redo) return 0;
     if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return -1;
     unsigned int v = 0;
-    if (cudaMemcpy(&v, c->d_redo, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, c->scr[c->cur].d_redo, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     c->last_redo = v;
     return (int64_t)v;
 }
@@ -894,8 +916,27 @@ static int actdist_host_impl(igmk_ctx* c, const float* xyz, int64_t n_pairs,
     // (copy-in stream) and results of the previous one come down (copy-out stream) while
     // the kernel works on the current slice.  Overlap needs pinned host buffers
     // (igmk_host_alloc); pageable ones still work, serialised by the driver.
+    // Slice sizes ramp up from slice >> ramp and down again (long lists only): the first slice's
+    // inputs (and, pipelined, the beads it needs) and the last slice's results are the only
+    // copies nothing hides.
     const size_t slice = (size_t)c->host_slice_pairs;
-    const int nsl = (int)((n + slice - 1) / slice);
+    std::vector<size_t> cut;                 // slice k = [cut[k], cut[k + 1])
+    cut.push_back(0);
+    const int ramp = (c->host_slice_ramp < 0) ? 0 : (c->host_slice_ramp > 4 ? 4 : c->host_slice_ramp);
+    if (ramp && n >= 6 * slice && slice >= 1024) {
+        const size_t small = slice >> ramp;
+        size_t pos = 0;
+        for (size_t sz = small; sz < slice; sz *= 2) { pos += sz; cut.push_back(pos); }
+        const size_t tail = slice - small;                           // = small + 2 small + ... + slice / 2
+        while (n - pos > tail + slice + slice / 2) { pos += slice; cut.push_back(pos); }
+        const size_t mid = n - pos - tail;                           // in (slice/2, 3 slice/2]
+        pos += mid; cut.push_back(pos);
+        for (size_t sz = slice / 2; sz >= small; sz /= 2) { pos += sz; cut.push_back(pos); }
+    } else {
+        for (size_t pos = slice; pos < n; pos += slice) cut.push_back(pos);
+        cut.push_back(n);
+    }
+    const int nsl = (int)cut.size() - 1;
     if ((int)c->ev_in.size() < nsl) {
         const size_t old = c->ev_in.size();
         c->ev_in.resize(nsl); c->ev_k.resize(nsl);
@@ -911,10 +952,17 @@ static int actdist_host_impl(igmk_ctx* c, const float* xyz, int64_t n_pairs,
         for (int r = 0; r < c->up_nreg; ++r) cur[r] = c->up_hi_reg[r];
         c->have_coords = true;           // every launch below is ordered after the pieces it reads
     }
+    // consecutive slices alternate between two compute streams and two scratch sets (warp
+    // list kernel only: the slab pipeline's batches want the L2 for themselves)
+    const bool alt = c->host_overlap && nsl > 1 && c->list_form && c->group_threads == 0 &&
+                     group_threads_for(c) == 32 && algo == IGMK_ALGO_FAST;
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    if (alt) CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev0, 0));
     for (int t = 0; t < nsl; ++t) {
         const int k = xyz ? nsl - 1 - t : t;
-        const size_t lo = (size_t)k * slice, cnt = (n - lo < slice) ? n - lo : slice;
+        c->cur = alt ? (t & 1) : 0;
+        cudaStream_t cs = c->cur ? c->stream2 : c->stream;
+        const size_t lo = cut[k], cnt = cut[k + 1] - cut[k];
         if (xyz) {
             int m = m_run;
             for (size_t q = lo; q < lo + cnt; ++q) {
@@ -927,26 +975,31 @@ static int actdist_host_impl(igmk_ctx* c, const float* xyz, int64_t n_pairs,
                 const int want = c->up_lo[r][m_run];
                 if (want < cur[r]) {
                     rc = upload_pieces(c, xyz + (size_t)want * c->nstruct * 3, want, cur[r] - want, c->s_up);
-                    if (rc) { cudaDeviceSynchronize(); c->have_coords = false; return rc; }
+                    if (rc) { cudaDeviceSynchronize(); c->cur = 0; c->have_coords = false; return rc; }
                     cur[r] = want;
                 }
             }
-            if (c->up_piece > 0) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_up[2 + ((c->up_piece - 1) & 1)], 0));
+            if (c->up_piece > 0) CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_up[2 + ((c->up_piece - 1) & 1)], 0));
         }
         CUDA_TRY(cudaMemcpyAsync(base + lo * 4, i + lo, cnt * 4, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaMemcpyAsync(base + off_j + lo * 4, j + lo, cnt * 4, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaMemcpyAsync(base + off_pw + lo * 8, pwish + lo, cnt * 8, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaMemcpyAsync(base + off_pl + lo * 8, plast + lo, cnt * 8, cudaMemcpyHostToDevice, c->s_in));
         CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_in[k], 0));
         igmk_pair_result* d_out = (igmk_pair_result*)(base + off_out) + lo;
         rc = igmk_actdist_device(c, (int64_t)cnt, (const int32_t*)base + lo, (const int32_t*)(base + off_j) + lo,
                                  (const double*)(base + off_pw) + lo, (const double*)(base + off_pl) + lo,
-                                 contact_range, it_corr, mode, algo, d_out, c->stream);
-        if (rc) { cudaDeviceSynchronize(); if (xyz) c->have_coords = false; return rc; }
-        CUDA_TRY(cudaEventRecord(c->ev_k[k], c->stream));
+                                 contact_range, it_corr, mode, algo, d_out, cs);
+        if (rc) { cudaDeviceSynchronize(); c->cur = 0; if (xyz) c->have_coords = false; return rc; }
+        CUDA_TRY(cudaEventRecord(c->ev_k[k], cs));
         CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
         CUDA_TRY(cudaMemcpyAsync(out + lo, d_out, cnt * sizeof(igmk_pair_result), cudaMemcpyDeviceToHost, c->s_out));
+    }
+    c->cur = 0;
+    if (alt) {
+        CUDA_TRY(cudaEventRecord(c->ev_join, c->stream2));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     if (xyz) {

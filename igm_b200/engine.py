@@ -112,6 +112,7 @@ class ActdistEngine:
         self.n_hap = 0
         self._ncopies = None
         self._chrom_hap = None
+        self._pending_xyz = None           # host coordinates not yet in HBM (from_hss(upload=False))
         if pop is not None:
             self.upload_coordinates(pop.coordinates)
             self.set_index(pop.copy_index.ptr, pop.copy_index.beads, pop.chrom_hap(), pop.radii)
@@ -136,17 +137,23 @@ class ActdistEngine:
         self.close()
 
     @classmethod
-    def from_hss(cls, path: str, device: int = 0, staged: "Optional[StagedHss]" = None) -> "ActdistEngine":
+    def from_hss(cls, path: str, device: int = 0, staged: "Optional[StagedHss]" = None,
+                 upload: bool = True) -> "ActdistEngine":
         """Engine for the population of a .hss file: replaces HssFile(...) + per-pair
         get_bead_crd chunk reads (igm/steps/ActivationDistanceStep.py:202,415-416;
         igm/core/step.py:386-392).  The coordinates go file -> pinned host memory (parallel
         pread of the stored extents, no decoding) -> HBM (double-buffered asynchronous copies
         + re-layout kernel); ``staged`` shares one host copy between the engines of several
-        devices."""
+        devices.  ``upload=False`` leaves the coordinates in host memory until the first
+        ``actdist_buffers`` call, which stages them inside the same pipelined device operation
+        (igmk_actdist_host_population); ``stage_pending`` uploads them on their own."""
         st = staged if staged is not None else StagedHss(path)
         eng = cls(nbead=st.nbead, nstruct=st.nstruct, device=device)
         try:
-            eng.upload_coordinates(st.coordinates)
+            if upload:
+                eng.upload_coordinates(st.coordinates)
+            else:
+                eng._pending_xyz = st.coordinates
             eng.set_index(st.copy_index.ptr, st.copy_index.beads,
                           np.ascontiguousarray(st.chrom[:len(st.copy_index)]), st.radii)
             eng.set_bead_chrom(st.chrom)
@@ -157,6 +164,27 @@ class ActdistEngine:
         return eng
 
     # -- staging ---------------------------------------------------------
+    def stage_pending(self) -> None:
+        """Upload the coordinates ``from_hss(upload=False)`` left in host memory."""
+        xyz, self._pending_xyz = self._pending_xyz, None
+        if xyz is not None:
+            self.upload_coordinates(xyz)
+
+    def actdist_buffers(self, n: int, b_i, b_j, b_pwish, b_plast, b_out, contact_range: float = 2.0,
+                        it_corr: int = 0, mode="LB", algo: int = ALGO_FAST) -> None:
+        """A-step on caller-owned (ideally page-locked) host buffers, no copies on the Python
+        side.  A population left pending by ``from_hss(upload=False)`` is staged by the same
+        call, its upload hidden behind the pair kernels."""
+        a = (int(n), ptr(b_i), ptr(b_j), ptr(b_pwish), ptr(b_plast), float(np.float32(contact_range)),
+             int(it_corr), _MODES[mode], int(algo), ptr(b_out))
+        xyz = self._pending_xyz
+        if xyz is not None and n > 0:
+            check(self._lib.igmk_actdist_host_population(self._ctx, ptr(xyz), *a))
+            self._pending_xyz = None
+        else:
+            self.stage_pending()
+            check(self._lib.igmk_actdist_host(self._ctx, *a))
+
     def upload_coordinates(self, xyz, bead0: int = 0) -> None:
         """xyz: (nb, nstruct, 3) float32, bead-major - NumPy array (host) or a
         CUDA torch tensor on this engine's device."""

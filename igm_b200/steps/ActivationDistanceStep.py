@@ -208,10 +208,13 @@ def _stage_population(hss_path):
     return StagedHss(hss_path)
 
 
-def _get_engines(hss_path, devices):
+def _get_engines(hss_path, devices, defer_upload=False):
     """One engine per device for the population file (keyed by path, mtime, size): the
     coordinates are read ONCE into pinned host memory and staged into every device's HBM
-    concurrently; engines of an older population are closed."""
+    concurrently; engines of an older population are closed.  ``defer_upload``: new engines
+    keep the coordinates in host memory for ``ActdistEngine.actdist_buffers`` to stage inside
+    its pipelined device call (every A-step follows an M-step that rewrote the file, so a new
+    population per step is the normal case)."""
     from concurrent.futures import ThreadPoolExecutor
     key = _file_key(hss_path)
     for k in list(_engine_cache):
@@ -225,13 +228,19 @@ def _get_engines(hss_path, devices):
         st = _staged_cache.get(key)
         if st is None:
             st = _staged_cache[key] = _stage_population(hss_path)
+        kw = {"upload": False} if defer_upload else {}
         if len(missing) == 1:
-            _engine_cache[key + (missing[0],)] = ActdistEngine.from_hss(hss_path, missing[0], staged=st)
+            _engine_cache[key + (missing[0],)] = ActdistEngine.from_hss(hss_path, missing[0], staged=st, **kw)
         else:
             with ThreadPoolExecutor(len(missing)) as ex:
-                for d, eng in zip(missing, ex.map(lambda d: ActdistEngine.from_hss(hss_path, d, staged=st), missing)):
+                for d, eng in zip(missing, ex.map(lambda d: ActdistEngine.from_hss(hss_path, d, staged=st, **kw), missing)):
                     _engine_cache[key + (d,)] = eng
-    return [_engine_cache[key + (d,)] for d in devices]
+    engines = [_engine_cache[key + (d,)] for d in devices]
+    if not defer_upload:
+        for eng in engines:
+            if getattr(eng, "_pending_xyz", None) is not None:
+                eng.stage_pending()
+    return engines
 
 
 def _get_engine(hss_path, device):
@@ -261,7 +270,7 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
     import time
     n = len(ii)
     t0 = time.perf_counter()
-    engines = _get_engines(hss_path, devices)
+    engines = _get_engines(hss_path, devices, defer_upload=True)
     LAST_TIMING["task_engines_s"] = time.perf_counter() - t0
     bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
     t0 = time.perf_counter()
@@ -270,18 +279,20 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
         lo, hi = int(bounds[k]), int(bounds[k + 1])
         m = hi - lo
         if m == 0:
+            engines[k].stage_pending()
             return np.zeros(0, dtype=_lib.PAIR_RESULT_DTYPE)
         tag = ("actdist", devices[k])
+        t1 = time.perf_counter()
         p_i = pinned_array((m,), np.int32, tag + ("i",)); p_i[:] = ii[lo:hi]
         p_j = pinned_array((m,), np.int32, tag + ("j",)); p_j[:] = jj[lo:hi]
         p_w = pinned_array((m,), np.float64, tag + ("w",)); p_w[:] = pw[lo:hi]
         p_l = pinned_array((m,), np.float64, tag + ("l",)); p_l[:] = pl[lo:hi]
         out = pinned_array((m,), _lib.PAIR_RESULT_DTYPE, tag + ("o",))
-        eng = engines[k]
-        _lib.check(eng._lib.igmk_actdist_host(eng._ctx, m, _lib.ptr(p_i), _lib.ptr(p_j), _lib.ptr(p_w), _lib.ptr(p_l),
-                                              float(np.float32(contact_range)), int(it_corr),
-                                              _lib.MODE_LB if str(mode).upper() == "LB" else _lib.MODE_GP, 0,
-                                              _lib.ptr(out)))
+        t2 = time.perf_counter()
+        engines[k].actdist_buffers(m, p_i, p_j, p_w, p_l, out, contact_range, it_corr, str(mode).upper())
+        if k == 0:
+            LAST_TIMING["task_pinned_buffers_s"] = t2 - t1
+            LAST_TIMING["task_library_call_s"] = time.perf_counter() - t2
         return out
     if len(devices) == 1:
         parts = [run(0)]

@@ -352,3 +352,36 @@ def test_dropin_runs_under_the_reference_step_run(tmp_path):
     assert d["task_calls_first_run"] == 1 and d["task_calls_second_run"] == 0
     assert d["second_run_actdist_file"] == d["actdist_file"] and os.path.exists(d["actdist_file"])
     assert d["second_run_sigma"] == 0.05
+
+
+def test_engine_cache_deferred_upload(tmp_path, monkeypatch):
+    """_get_engines(defer_upload=True) creates engines whose coordinates stay in host memory
+    (the A-step's own device call stages them); any other user of the cache gets them staged."""
+    log = []
+
+    class FakeEngine:
+        def __init__(self, path, device, upload):
+            self._pending_xyz = None if upload else "xyz"
+            log.append(("new", device, upload))
+
+        def stage_pending(self):
+            log.append(("stage", self._pending_xyz))
+            self._pending_xyz = None
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(S, "ActdistEngine", type("E", (), {
+        "from_hss": staticmethod(lambda p, d, staged=None, upload=True: FakeEngine(p, d, upload))}))
+    monkeypatch.setattr(S, "_engine_cache", {})
+    monkeypatch.setattr(S, "_staged_cache", {})
+    monkeypatch.setattr(S, "_stage_population", lambda p: object())
+    a = str(tmp_path / "a.hss")
+    open(a, "wb").write(b"x" * 10)
+    e = S._get_engines(a, [0], defer_upload=True)[0]
+    assert e._pending_xyz == "xyz" and log == [("new", 0, False)]
+    assert S._get_engines(a, [0], defer_upload=True)[0] is e and e._pending_xyz == "xyz"
+    assert S._get_engine(a, 0) is e and e._pending_xyz is None      # e.g. the SPRITE step: staged now
+    assert log[-1] == ("stage", "xyz")
+    S._get_engines(a, [1])
+    assert log[-1] == ("new", 1, True)
