@@ -61,6 +61,8 @@ struct LaunchScratch {
     void* d_slab = nullptr; size_t slab_bytes = 0;      // T | cnt | lists of one batch (slab pipeline)
 };
 
+constexpr int kPadRows = 64;
+
 struct igmk_ctx {
     LaunchScratch scr[2];
     int cur = 0;                                        // scratch set of the launch being issued
@@ -151,8 +153,9 @@ extern "C" int igmk_create(int device, int nbead, int nstruct, igmk_ctx** out) {
     c->npad = (nstruct + kSeg - 1) / kSeg * kSeg;
     c->nchunks = (nstruct + 3) / 4;
     c->sm_count = prop.multiProcessorCount;
-    // one extra all-zero row behind the population: the "origin bead" of the DamID path
-    const size_t bytes = (size_t)(nbead + 1) * 3 * c->npad * sizeof(float);
+    // one extra all-zero row behind the population: the "origin bead" of the DamID path; kPadRows
+    // more so that an in-place all-gather of equal bead shares (igmk_coords_device) fits
+    const size_t bytes = (size_t)(nbead + 1 + kPadRows) * 3 * c->npad * sizeof(float);
     e = cudaMalloc(&c->d_coords, bytes);
     if (e != cudaSuccess) { delete c; return fail(IGMK_ECUDA, "igmk_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
     // every further resource is checked; a failure releases what exists so far
@@ -329,6 +332,44 @@ extern "C" int igmk_upload_coords_range(igmk_ctx* c, const float* xyz, int bead0
     if (rc) { cudaDeviceSynchronize(); return rc; }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->have_coords = true;
+    return IGMK_OK;
+}
+
+// The staged population as device memory: rows of 3 * npad floats, nbead rows of beads, one
+// all-zero row, kPadRows spare rows.  For NVLink replication: every rank uploads its share of
+// the beads (igmk_upload_coords_range) and one all-gather over whole rows completes the copies.
+extern "C" int igmk_coords_device(igmk_ctx* c, float** d_coords, int64_t* n_rows, int64_t* row_floats) {
+    if (!c || !d_coords || !n_rows || !row_floats) return fail(IGMK_EINVAL, "igmk_coords_device: NULL argument");
+    *d_coords = c->d_coords;
+    *n_rows = (int64_t)c->nbead + 1 + kPadRows;
+    *row_floats = 3ll * c->npad;
+    return IGMK_OK;
+}
+
+// Beads [bead0, bead0 + nb) of `src` (another device of this process) -> the same rows of
+// `dst`, over NVLink when the devices are peers.  Synchronises dst's stream.
+extern "C" int igmk_copy_coords_peer(igmk_ctx* dst, igmk_ctx* src, int bead0, int nb) {
+    if (!dst || !src) return fail(IGMK_EINVAL, "igmk_copy_coords_peer: NULL context");
+    if (dst->nbead != src->nbead || dst->nstruct != src->nstruct) return fail(IGMK_EINVAL, "igmk_copy_coords_peer: populations differ in shape");
+    if (bead0 < 0 || nb < 0 || bead0 + nb > dst->nbead) return fail(IGMK_EINVAL, "igmk_copy_coords_peer: bead range out of bounds");
+    if (!src->have_coords) return fail(IGMK_ESTATE, "igmk_copy_coords_peer: the source holds no coordinates");
+    CUDA_TRY(cudaSetDevice(dst->device));
+    if (nb > 0) {
+        if (dst->device != src->device) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return fail(IGMK_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            }
+        }
+        const size_t row = (size_t)3 * dst->npad, off = (size_t)bead0 * row;
+        CUDA_TRY(cudaMemcpyPeerAsync(dst->d_coords + off, dst->device, src->d_coords + off, src->device,
+                                     (size_t)nb * row * sizeof(float), dst->stream));
+        CUDA_TRY(cudaStreamSynchronize(dst->stream));
+    }
+    dst->have_coords = true;
     return IGMK_OK;
 }
 

@@ -55,6 +55,36 @@ def run_sharded(compute_shard: Callable, n_pairs: int, rank: int, world: int, de
     return full, per, bounds
 
 
+def bead_shares(nbead: int, world: int) -> Tuple[int, List[Tuple[int, int]]]:
+    """Equal contiguous bead ranges, one per GPU (the last may be short or empty)."""
+    return shard_bounds(nbead, world)
+
+
+def replicate_population(eng, xyz_host, rank: int, world: int, group=None) -> None:
+    """"Coordinates replicated per GPU" without one PCIe upload per GPU: every rank uploads
+    only ITS share of the beads from host memory (1 / world of the host-side traffic), then
+    one all-gather of whole staged rows over NVLink / NVSwitch completes every GPU's copy
+    (in place in the engine's own buffer).  ``xyz_host``: (nbead, nstruct, 3) float32, the
+    .hss layout, ideally page-locked; every rank passes the same population."""
+    import torch.distributed as dist
+    per, shares = bead_shares(eng.nbead, world)
+    lo, hi = shares[rank]
+    if hi > lo:
+        eng.upload_coordinates(xyz_host[lo:hi], bead0=lo)
+    if world == 1:
+        return
+    buf = eng.coords_tensor()                           # (nbead + 1 + spare rows, 3 * npad)
+    if world * per > buf.shape[0]:
+        raise ValueError("too many ranks for the staged buffer's spare rows")
+    whole = buf[:world * per]
+    # rows past nbead are zero on every rank (never uploaded), so the tail of the last share
+    # gathers zeros over zeros: the all-zero origin row stays intact
+    mine = whole[rank * per:(rank + 1) * per]
+    if dist.get_backend(group) != "nccl":
+        mine = mine.clone()
+    dist.all_gather_into_tensor(whole.view(-1), mine.reshape(-1), group=group)
+
+
 class PeerGather:
     """Gather buffers the A-step kernel writes into directly over NVLink.
 

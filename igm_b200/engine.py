@@ -18,7 +18,10 @@ from ._lib import (ALGO_FAST, ALGO_SIMPLE, MODE_GP, MODE_LB, PAIR_RESULT_DTYPE, 
                    check, ptr)
 from .population import Population
 
-_pinned_cache = {}     # nbytes -> (address, ndarray view): page-locked staging buffers, kept per process
+import threading
+
+_pinned_cache = {}     # key -> (address, ndarray view): page-locked staging buffers, kept per process
+_pinned_lock = threading.Lock()   # one task drives several devices from several threads
 
 
 def pinned_array(shape, dtype=np.float32, tag=None) -> np.ndarray:
@@ -30,22 +33,25 @@ def pinned_array(shape, dtype=np.float32, tag=None) -> np.ndarray:
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
     key = ("size", nbytes) if tag is None else ("tag", tag)
-    ent = _pinned_cache.get(key)
-    if ent is None or len(ent[1]) < nbytes:
-        lib = _lib.load()
-        cap = max(nbytes, 1)
-        if ent is not None:
-            cap = max(cap, int(1.5 * len(ent[1])))
-            lib.igmk_host_free(C.c_void_p(ent[0]))
-            del _pinned_cache[key]
-        p = C.c_void_p()
-        check(lib.igmk_host_alloc(C.byref(p), cap))
-        buf = (C.c_char * cap).from_address(p.value)
-        ent = (p.value, np.frombuffer(buf, dtype=np.uint8, count=cap))
-        if len(_pinned_cache) >= 64:                     # bounded: drop the oldest buffer
-            old = next(iter(_pinned_cache))
-            lib.igmk_host_free(C.c_void_p(_pinned_cache.pop(old)[0]))
-        _pinned_cache[key] = ent
+    with _pinned_lock:
+        ent = _pinned_cache.get(key)
+        if ent is None or len(ent[1]) < nbytes:
+            lib = _lib.load()
+            cap = max(nbytes, 1)
+            if ent is not None:
+                cap = max(cap, int(1.5 * len(ent[1])))
+                lib.igmk_host_free(C.c_void_p(ent[0]))
+                del _pinned_cache[key]
+            p = C.c_void_p()
+            check(lib.igmk_host_alloc(C.byref(p), cap))
+            buf = (C.c_char * cap).from_address(p.value)
+            ent = (p.value, np.frombuffer(buf, dtype=np.uint8, count=cap))
+            # bounded: drop the oldest size-keyed buffer (a population of an earlier step);
+            # tagged buffers belong to a device's working set and stay
+            sized = [k for k in _pinned_cache if k[0] == "size"]
+            if len(sized) >= 8:
+                lib.igmk_host_free(C.c_void_p(_pinned_cache.pop(sized[0])[0]))
+            _pinned_cache[key] = ent
     return ent[1][:nbytes].view(dtype).reshape(shape)
 
 
@@ -204,6 +210,23 @@ class ActdistEngine:
         if len(shape) != 3 or shape[1] != self.nstruct or shape[2] != 3:
             raise ValueError("coordinates must be (nbead, %d, 3), got %r" % (self.nstruct, shape))
         check(self._lib.igmk_upload_coords_range(self._ctx, ptr(xyz), int(bead0), int(shape[0]), on_device))
+
+    def copy_coordinates_from(self, other: "ActdistEngine", bead0: int, nb: int) -> None:
+        """Rows [bead0, bead0 + nb) from another engine of this process (device to device,
+        NVLink between peers)."""
+        check(self._lib.igmk_copy_coords_peer(self._ctx, other._ctx, int(bead0), int(nb)))
+
+    def coords_tensor(self):
+        """The staged population as a torch tensor (rows, 3 * npad) float32 on this engine's
+        device, zero-copy (rows = nbead + 1 + 64 spare) - for the caller's collectives."""
+        import torch
+        p, rows, rf = C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self._lib.igmk_coords_device(self._ctx, C.byref(p), C.byref(rows), C.byref(rf)))
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (int(rows.value), int(rf.value)), "typestr": "<f4",
+                                        "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(_Buf(), device=torch.device("cuda", self.device))
 
     def set_index(self, copy_ptr, copy_beads, chrom_hap, radii) -> None:
         copy_ptr = np.ascontiguousarray(copy_ptr, dtype=np.int32)

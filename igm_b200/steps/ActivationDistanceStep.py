@@ -228,13 +228,34 @@ def _get_engines(hss_path, devices, defer_upload=False):
         st = _staged_cache.get(key)
         if st is None:
             st = _staged_cache[key] = _stage_population(hss_path)
-        kw = {"upload": False} if defer_upload else {}
         if len(missing) == 1:
+            kw = {"upload": False} if defer_upload else {}
             _engine_cache[key + (missing[0],)] = ActdistEngine.from_hss(hss_path, missing[0], staged=st, **kw)
         else:
+            # several devices: each uploads only its share of the beads from host memory, then
+            # pulls the other shares from its peers over NVLink - one population's worth of
+            # PCIe traffic in total instead of one per device
+            from ..dist import bead_shares
+            _, shares = bead_shares(st.nbead, len(missing))
             with ThreadPoolExecutor(len(missing)) as ex:
-                for d, eng in zip(missing, ex.map(lambda d: ActdistEngine.from_hss(hss_path, d, staged=st, **kw), missing)):
-                    _engine_cache[key + (d,)] = eng
+                new = list(ex.map(lambda d: ActdistEngine.from_hss(hss_path, d, staged=st, upload=False), missing))
+
+                def own(k):
+                    lo, hi = shares[k]
+                    new[k]._pending_xyz = None
+                    if hi > lo:
+                        new[k].upload_coordinates(st.coordinates[lo:hi], bead0=lo)
+
+                def pull(k):
+                    for step in range(1, len(new)):              # staggered: no two devices read one peer at once
+                        src = (k + step) % len(new)
+                        lo, hi = shares[src]
+                        if hi > lo:
+                            new[k].copy_coordinates_from(new[src], lo, hi - lo)
+                list(ex.map(own, range(len(new))))
+                list(ex.map(pull, range(len(new))))
+            for d, eng in zip(missing, new):
+                _engine_cache[key + (d,)] = eng
     engines = [_engine_cache[key + (d,)] for d in devices]
     if not defer_upload:
         for eng in engines:
@@ -274,33 +295,32 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
     LAST_TIMING["task_engines_s"] = time.perf_counter() - t0
     bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
     t0 = time.perf_counter()
+    # ONE page-locked copy of the list and of the results for all devices (page-locking is
+    # serialised by the kernel: per-device buffers made an 8-GPU task slower than a 1-GPU one);
+    # every device works on its contiguous share of them
+    p_i = pinned_array((n,), np.int32, ("actdist", "i")); p_i[:] = ii
+    p_j = pinned_array((n,), np.int32, ("actdist", "j")); p_j[:] = jj
+    p_w = pinned_array((n,), np.float64, ("actdist", "w")); p_w[:] = pw
+    p_l = pinned_array((n,), np.float64, ("actdist", "l")); p_l[:] = pl
+    out = pinned_array((n,), _lib.PAIR_RESULT_DTYPE, ("actdist", "o"))
+    LAST_TIMING["task_pinned_buffers_s"] = time.perf_counter() - t0
+    t1 = time.perf_counter()
 
     def run(k):
         lo, hi = int(bounds[k]), int(bounds[k + 1])
-        m = hi - lo
-        if m == 0:
+        if hi == lo:
             engines[k].stage_pending()
-            return np.zeros(0, dtype=_lib.PAIR_RESULT_DTYPE)
-        tag = ("actdist", devices[k])
-        t1 = time.perf_counter()
-        p_i = pinned_array((m,), np.int32, tag + ("i",)); p_i[:] = ii[lo:hi]
-        p_j = pinned_array((m,), np.int32, tag + ("j",)); p_j[:] = jj[lo:hi]
-        p_w = pinned_array((m,), np.float64, tag + ("w",)); p_w[:] = pw[lo:hi]
-        p_l = pinned_array((m,), np.float64, tag + ("l",)); p_l[:] = pl[lo:hi]
-        out = pinned_array((m,), _lib.PAIR_RESULT_DTYPE, tag + ("o",))
-        t2 = time.perf_counter()
-        engines[k].actdist_buffers(m, p_i, p_j, p_w, p_l, out, contact_range, it_corr, str(mode).upper())
-        if k == 0:
-            LAST_TIMING["task_pinned_buffers_s"] = t2 - t1
-            LAST_TIMING["task_library_call_s"] = time.perf_counter() - t2
-        return out
+            return
+        engines[k].actdist_buffers(hi - lo, p_i[lo:hi], p_j[lo:hi], p_w[lo:hi], p_l[lo:hi], out[lo:hi],
+                                   contact_range, it_corr, str(mode).upper())
     if len(devices) == 1:
-        parts = [run(0)]
+        run(0)
     else:
         with ThreadPoolExecutor(len(devices)) as ex:
-            parts = list(ex.map(run, range(len(devices))))
+            list(ex.map(run, range(len(devices))))
+    LAST_TIMING["task_library_call_s"] = time.perf_counter() - t1
     LAST_TIMING["task_device_s"] = time.perf_counter() - t0
-    return engines[0], (parts[0] if len(parts) == 1 else np.concatenate(parts))
+    return engines[0], out
 
 
 class ActivationDistanceStep(Step):

@@ -80,6 +80,14 @@ int igmk_upload_coords(igmk_ctx* ctx, const float* xyz, int on_device);
 /* Partial upload of beads [bead0, bead0 + nb): lets a loader stream HDF5
  * chunks (pack_beads x nstruct x 3, igm/steps/ModelingStep.py:753-760). */
 int igmk_upload_coords_range(igmk_ctx* ctx, const float* xyz, int bead0, int nb, int on_device);
+/* Replication over NVLink instead of one PCIe upload per GPU ("coordinates replicated",
+ * north_star): every GPU uploads only its share of the beads, then the shares are exchanged.
+ * igmk_coords_device exposes the staged rows (3 * npad floats each; nbead bead rows, one
+ * all-zero row, 64 spare rows so an in-place all-gather of equal shares fits) to the
+ * caller's collective (one process per GPU); igmk_copy_coords_peer copies rows between two
+ * contexts of one process (one task driving all GPUs, igm/core/step.py:259-274). */
+int igmk_coords_device(igmk_ctx* ctx, float** d_coords, int64_t* n_rows, int64_t* row_floats);
+int igmk_copy_coords_peer(igmk_ctx* dst, igmk_ctx* src, int bead0, int nb);
 
 /* Index tables (host pointers): copy_ptr[n_hap+1] / copy_beads = CSR of
  * hss.index.copy_index; chrom_hap[n_hap] = hss.index.chrom indexed by haploid

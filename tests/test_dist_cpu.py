@@ -66,3 +66,57 @@ def test_gloo_world2_allgather(n):
         assert p.exitcode == 0
     exp = _fake_results(0, n).tobytes()
     assert got[0] == exp and got[1] == exp
+
+
+class _FakeEngine:
+    """Stands in for ActdistEngine in replicate_population: rows of 6 floats per bead."""
+
+    def __init__(self, nbead):
+        self.nbead = nbead
+        self.buf = torch.zeros((nbead + 1 + 64, 6), dtype=torch.float32)
+
+    def upload_coordinates(self, xyz, bead0=0):
+        self.buf[bead0:bead0 + len(xyz)] = torch.from_numpy(np.ascontiguousarray(xyz)).reshape(len(xyz), 6)
+
+    def coords_tensor(self):
+        return self.buf
+
+
+def _replicate_worker(rank, world, port, nbead, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    xyz = np.arange(nbead * 6, dtype=np.float32).reshape(nbead, 2, 3) + 1.0
+    eng = _FakeEngine(nbead)
+    idist.replicate_population(eng, xyz, rank, world)
+    q.put((rank, eng.buf.numpy().tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nbead", [1, 2, 7, 10])
+def test_gloo_world2_replicate_population(nbead):
+    """Every rank uploads its share of the beads; one all-gather of whole rows completes both
+    copies; the all-zero row behind the population stays zero."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, 2, port, nbead, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp = np.zeros((nbead + 1 + 64, 6), np.float32)
+    exp[:nbead] = (np.arange(nbead * 6, dtype=np.float32) + 1.0).reshape(nbead, 6)
+    assert got[0] == exp.tobytes() and got[1] == exp.tobytes()
+
+
+def test_bead_shares():
+    for n in (1, 5, 29838):
+        for w in (1, 2, 8):
+            per, sh = idist.bead_shares(n, w)
+            assert sh[0][0] == 0 and sh[-1][1] == n and w * per <= n + 1 + 64

@@ -125,3 +125,30 @@ def test_pipelined_population_edge_cases():
         eng._uniform_ploidy = True
         with pytest.raises(IgmkError):
             eng.actdist_with_population(pop.coordinates, ii, jj, pw, pl)
+
+
+def test_population_shares_between_contexts():
+    """NVLink replication path on whatever devices the box has: engine B uploads half of the
+    beads and takes the other half from engine A (igmk_copy_coords_peer); the staged rows
+    (igmk_coords_device, zero-copy torch view) and the A-step results are identical.  With
+    >= 2 GPUs the two engines sit on different devices."""
+    import torch
+    from igm_b200 import synthetic
+    from igm_b200.engine import ActdistEngine
+    pop = synthetic.make_population(2_000_000, 200, seed=21, genome_scale=0.05)
+    rng, ii, jj, pw, pl = _inputs(pop, 4000, 2)
+    dev_b = 1 if torch.cuda.device_count() > 1 else 0
+    half = pop.nbead // 2
+    with ActdistEngine(pop, device=0) as a:
+        with ActdistEngine(nbead=pop.nbead, nstruct=pop.nstruct, device=dev_b) as b:
+            b.set_index(pop.copy_index.ptr, pop.copy_index.beads, pop.chrom_hap(), pop.radii)
+            b.upload_coordinates(pop.coordinates[:half], bead0=0)
+            b.copy_coordinates_from(a, half, pop.nbead - half)
+            ta, tb = a.coords_tensor(), b.coords_tensor()
+            assert ta.shape == (pop.nbead + 1 + 64, 3 * 256) and tb.shape == ta.shape
+            assert torch.equal(ta.cpu(), tb.cpu())
+            assert float(ta[pop.nbead:].abs().max()) == 0.0          # origin row + spare rows
+            assert b.actdist(ii, jj, pw, pl).tobytes() == a.actdist(ii, jj, pw, pl).tobytes()
+            from igm_b200._lib import IgmkError
+            with pytest.raises(IgmkError):
+                b.copy_coordinates_from(a, pop.nbead - 1, 2)

@@ -301,22 +301,31 @@ def test_hdf5_writer_roundtrip_property(tmp_path):
 def test_engine_cache_keeps_one_engine_per_device(tmp_path, monkeypatch):
     """_get_engine: shards of one A-step on different devices keep their staged populations;
     a rewritten or different .hss replaces all of them."""
-    made, closed = [], []
+    made, closed, moved = [], [], []
 
     class FakeEngine:
         def __init__(self, path, device):
             self.tag = (path, device)
+            self._pending_xyz = None
             made.append(self.tag)
+
+        def upload_coordinates(self, xyz, bead0=0):
+            moved.append(("h2d", self.tag[1], bead0, len(xyz)))
+
+        def copy_coordinates_from(self, other, bead0, nb):
+            moved.append(("p2p", self.tag[1], other.tag[1], bead0, nb))
 
         def close(self):
             closed.append(self.tag)
 
     monkeypatch.setattr(S, "ActdistEngine",
-                        type("E", (), {"from_hss": staticmethod(lambda p, d, staged=None: FakeEngine(p, d))}))
+                        type("E", (), {"from_hss": staticmethod(lambda p, d, staged=None, upload=True: FakeEngine(p, d))}))
     monkeypatch.setattr(S, "_engine_cache", {})
     monkeypatch.setattr(S, "_staged_cache", {})
     staged = []
-    monkeypatch.setattr(S, "_stage_population", lambda p: staged.append(p) or object())
+    import types
+    monkeypatch.setattr(S, "_stage_population", lambda p: staged.append(p) or types.SimpleNamespace(
+        nbead=11, coordinates=np.zeros((11, 2, 3), np.float32)))
     a, b = str(tmp_path / "a.hss"), str(tmp_path / "b.hss")
     open(a, "wb").write(b"x" * 10)
     open(b, "wb").write(b"y" * 20)
@@ -326,6 +335,8 @@ def test_engine_cache_keeps_one_engine_per_device(tmp_path, monkeypatch):
     assert staged == [a]                                  # one host copy of the file for both devices
     e23 = S._get_engines(a, [2, 3])                       # staged concurrently, same host copy
     assert [e.tag for e in e23] == [(a, 2), (a, 3)] and staged == [a]
+    # each new device uploads its share of the beads and pulls the other share from its peer
+    assert sorted(moved) == [("h2d", 2, 0, 6), ("h2d", 3, 6, 5), ("p2p", 2, 3, 6, 5), ("p2p", 3, 2, 0, 6)]
     S._get_engine(b, 0)                                   # another population: all are released
     assert sorted(closed) == [(a, 0), (a, 1), (a, 2), (a, 3)] and len(S._engine_cache) == 1
     assert staged == [a, b] and len(S._staged_cache) == 1
