@@ -55,6 +55,14 @@ def pinned_array(shape, dtype=np.float32, tag=None) -> np.ndarray:
     return ent[1][:nbytes].view(dtype).reshape(shape)
 
 
+def is_pinned_view(arr, tag) -> bool:
+    """True when ``arr`` is a view that starts at the base of the tagged page-locked buffer
+    (so a consumer can hand it to the device as it is instead of copying it there)."""
+    ent = _pinned_cache.get(("tag", tag))
+    return (ent is not None and isinstance(arr, np.ndarray) and arr.flags["C_CONTIGUOUS"]
+            and arr.ctypes.data == ent[0] and arr.nbytes <= len(ent[1]))
+
+
 class StagedHss:
     """Host-side staging of a population file: coordinates in pinned memory + the index
     tables ``get_actdist`` needs (igm/steps/ActivationDistanceStep.py:382-393)."""

@@ -41,7 +41,18 @@ actdist_shape = [("row", "int32"), ("col", "int32"), ("dist", "float32"), ("prob
 actdist_fmt_str = "%6d %6d %10.4f %.4f"
 
 
-def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np.float32, native=True):
+def _pair_buffer(n, dtype, name):
+    """Page-locked buffer of the A-step's pair list (tags shared with actdist_on_devices, which
+    then hands the arrays to the device without another copy); plain memory without a GPU."""
+    try:
+        from ..engine import pinned_array
+        return pinned_array((n,), dtype, ("actdist", name))
+    except _lib.IgmkError:
+        return np.empty(n, dtype)
+
+
+def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np.float32, native=True,
+                      pinned=False):
     """Candidate filter of the reference's setup loop (:166-178), vectorised.
 
     Stored non-zeros are visited in CSR row-major order (what ``coo_generator``
@@ -50,6 +61,8 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
     NumPy >= 2 happens in float32.  ``i == j`` entries are
     dropped (they never produce a record, :379-380).  Returns (i, j, pwish64).
     ``native=False`` (or a compare dtype other than float32) takes the NumPy form.
+    ``pinned``: the native form writes into the step's page-locked pair buffers (sized by the
+    matrix, so they are locked once per run) and returns views of them.
     """
     dt = np.dtype(compare_dtype)
     use_intra = intra_sigma is not False and intra_sigma is not None
@@ -61,7 +74,10 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
         # one pass over the CSR arrays in the C library (igmk_filter_candidates)
         lib = _lib.load()
         cap = int(len(pm.indices))
-        oi, oj, op = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float64)
+        if pinned:
+            oi, oj, op = _pair_buffer(cap, np.int32, "i"), _pair_buffer(cap, np.int32, "j"), _pair_buffer(cap, np.float64, "w")
+        else:
+            oi, oj, op = np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float64)
         k = lib.igmk_filter_candidates(pm.n, _lib.ptr(pm.indptr), _lib.ptr(pm.indices), _lib.ptr(pm.data),
                                        _lib.ptr(pm.chrom), int(use_intra),
                                        float(np.float32(intra_sigma)) if use_intra else 0.0, int(use_inter),
@@ -69,6 +85,8 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
                                        _lib.ptr(oi), _lib.ptr(oj), _lib.ptr(op), cap)
         if k < 0:
             raise RuntimeError("igmk_filter_candidates failed (%d)" % k)
+        if pinned:
+            return oi[:k], oj[:k], op[:k]
         return oi[:k].copy(), oj[:k].copy(), op[:k].copy()
     pw = pm.data.astype(dt, copy=False)
     # first cut on the probability alone (the smaller threshold), then the intra / inter
@@ -94,11 +112,15 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
             pm.data[idx].astype(np.float64))
 
 
-def lookup_plast(last_actdist_file, n, ii, jj, native=True):
+def lookup_plast(last_actdist_file, n, ii, jj, native=True, out=None):
     """``plast[i, j]`` of setup (:144-160,177): the previous iteration's stored
     ``prob`` of the record whose (row, col) are the haploid indices themselves
     (only records with row < n and col < n survive the mask, quirk q7)."""
-    out = np.zeros(len(ii), dtype=np.float64)
+    if out is None:
+        out = np.zeros(len(ii), dtype=np.float64)
+    else:
+        out = out[:len(ii)]
+        out[:] = 0.0
     if last_actdist_file is None:
         return out
     with hdf5.open_h5(last_actdist_file) as h5f:
@@ -287,7 +309,7 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
     (igm/core/step.py:259-274, igm/parallel/ipyparallel_controller.py:66-109); with the
     serial controller this is what gives igm-run all the GPUs of the box."""
     from concurrent.futures import ThreadPoolExecutor
-    from ..engine import pinned_array
+    from ..engine import is_pinned_view, pinned_array
     import time
     n = len(ii)
     t0 = time.perf_counter()
@@ -298,10 +320,15 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
     # ONE page-locked copy of the list and of the results for all devices (page-locking is
     # serialised by the kernel: per-device buffers made an 8-GPU task slower than a 1-GPU one);
     # every device works on its contiguous share of them
-    p_i = pinned_array((n,), np.int32, ("actdist", "i")); p_i[:] = ii
-    p_j = pinned_array((n,), np.int32, ("actdist", "j")); p_j[:] = jj
-    p_w = pinned_array((n,), np.float64, ("actdist", "w")); p_w[:] = pw
-    p_l = pinned_array((n,), np.float64, ("actdist", "l")); p_l[:] = pl
+    # (setup() in this process already wrote the list there: nothing to copy then)
+    def staged(arr, dtype, name):
+        if arr.dtype == dtype and is_pinned_view(arr, ("actdist", name)):
+            return arr
+        buf = pinned_array((n,), dtype, ("actdist", name))
+        buf[:] = arr
+        return buf
+    p_i, p_j = staged(ii, np.int32, "i"), staged(jj, np.int32, "j")
+    p_w, p_l = staged(pw, np.float64, "w"), staged(pl, np.float64, "l")
     out = pinned_array((n,), _lib.PAIR_RESULT_DTYPE, ("actdist", "o"))
     LAST_TIMING["task_pinned_buffers_s"] = time.perf_counter() - t0
     t1 = time.perf_counter()
@@ -370,10 +397,11 @@ class ActivationDistanceStep(Step):
 
         import time
         t0 = time.perf_counter()
-        ii, jj, pw = filter_candidates(pm, intra_sigma, inter_sigma)
+        ii, jj, pw = filter_candidates(pm, intra_sigma, inter_sigma, pinned=True)
         LAST_TIMING["setup_filter_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        pl = lookup_plast(last_actdist_file, n, ii, jj)
+        pl = lookup_plast(last_actdist_file, n, ii, jj, out=_pair_buffer(len(pm.indices), np.float64, "l"))
+        _pair_buffer(len(pm.indices), _lib.PAIR_RESULT_DTYPE, "o")     # the task's result buffer: locked once per run too
         LAST_TIMING["setup_plast_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         # contiguous, equal-count shards keep bead-i locality and output order.  The task input
