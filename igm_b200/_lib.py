@@ -42,6 +42,7 @@ EXPORTS = (
     "igmk_host_alloc", "igmk_host_free", "igmk_last_kernel_ms", "igmk_last_redo_count",
     "igmk_actdist_sel_index_device", "igmk_actdist_sel_index_host",
     "igmk_actdist_host_population", "igmk_coords_device", "igmk_copy_coords_peer",
+    "igmk_reserve_pairs",
 )
 
 
@@ -65,6 +66,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.igmk_upload_coords_range.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_int]
     lib.igmk_coords_device.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.igmk_copy_coords_peer.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.igmk_reserve_pairs.argtypes = [vp, C.c_int64]
     lib.igmk_set_index.argtypes = [vp, C.c_int, i32p, i32p, i32p, f32p]
     lib.igmk_actdist_device.argtypes = [vp, C.c_int64, i32p, i32p, f64p, f64p, C.c_float,
                                         C.c_int, C.c_int, C.c_int, vp, vp]

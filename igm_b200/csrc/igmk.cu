@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/igmk.h"
@@ -1065,6 +1066,32 @@ static int actdist_host_impl(igmk_ctx* c, const float* xyz, int64_t n_pairs,
     return IGMK_OK;
 }
 
+// Device buffers of the host entry points for lists of up to n_pairs pairs, allocated now
+// instead of growing (cudaFree + cudaMalloc, tens of milliseconds and a device-wide
+// synchronisation each) from one A-step's list to the next larger one.
+extern "C" int igmk_reserve_pairs(igmk_ctx* c, int64_t n_pairs) {
+    if (!c || n_pairs < 0) return fail(IGMK_EINVAL, "igmk_reserve_pairs: bad argument");
+    if (n_pairs == 0) return IGMK_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)n_pairs;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    int rc = ensure(&c->d_pairs, &c->pairs_bytes, 2 * up(n * 4) + 2 * up(n * 8) + n * sizeof(igmk_pair_result));
+    if (rc) return rc;
+    // per-launch scratch: the host pipeline launches slices of at most 3/2 host_slice_pairs
+    size_t m = (size_t)c->host_slice_pairs * 3 / 2;
+    if (m > n) m = n;
+    size_t temp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)m, 0, 16, c->stream);
+    for (int k = 0; k < 2; ++k) {
+        LaunchScratch& sc = c->scr[k];
+        if ((rc = ensure(&sc.d_order, &sc.order_bytes, 4 * up(m * 4) + up(temp) + 4096))) return rc;
+        if ((rc = ensure(&sc.d_redo, &sc.redo_bytes, 256 + m * sizeof(int32_t)))) return rc;
+        if ((rc = ensure(&sc.d_rec, &sc.rec_bytes, m * sizeof(PairRec)))) return rc;
+    }
+    return IGMK_OK;
+}
+
 extern "C" int igmk_actdist_host(igmk_ctx* c, int64_t n_pairs,
                                  const int32_t* i, const int32_t* j,
                                  const double* pwish, const double* plast,
@@ -1103,25 +1130,69 @@ extern "C" float igmk_last_kernel_ms(igmk_ctx* c) { return c ? c->last_kernel_ms
 // comparison in float32 as NumPy >= 2 evaluates `float32 >= python float`.  Pure host
 // code (no device needed).  Returns the number of candidates, or -1 - needed when
 // `capacity` is too small (nothing is written beyond capacity).
+// Host threads of the setup / task phases (IGMK_HOST_THREADS, default min(8, cores)): the
+// lists are tens of MB, one core leaves them at ~50 ms per pass.
+static int host_threads(int64_t work) {
+    static const int conf = [] {
+        const char* ov = getenv("IGMK_HOST_THREADS");
+        int t = ov ? atoi(ov) : (int)std::thread::hardware_concurrency();
+        if (!ov && t > 8) t = 8;
+        return t < 1 ? 1 : t;
+    }();
+    const int64_t by_work = work / 65536;
+    return (int)((by_work < 1) ? 1 : (by_work < conf ? by_work : conf));
+}
+template <class F>
+static void run_threads(int nt, F&& body) {
+    if (nt <= 1) { body(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) th.emplace_back([&body, t] { body(t); });
+    body(0);
+    for (auto& x : th) x.join();
+}
+
 extern "C" int64_t igmk_filter_candidates(int64_t n_rows, const int64_t* indptr, const int32_t* indices,
                                           const float* data, const int32_t* chrom,
                                           int use_intra, float intra_sigma, int use_inter, float inter_sigma,
                                           int32_t* out_i, int32_t* out_j, double* out_p, int64_t capacity) {
     if (n_rows < 0 || !indptr || (indptr[n_rows] > 0 && (!indices || !data || !chrom))) return -1;
-    int64_t k = 0;
-    for (int64_t r = 0; r < n_rows; ++r) {
-        const int cr = chrom[r];
-        for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
-            const int32_t c = indices[e];
-            const float p = data[e];
-            const bool intra = chrom[c] == cr;
-            const bool keep = (intra ? (use_intra && p >= intra_sigma) : (use_inter && p >= inter_sigma)) && c != (int32_t)r;
-            if (!keep) continue;
-            if (k < capacity) { out_i[k] = (int32_t)r; out_j[k] = c; out_p[k] = (double)p; }
-            ++k;
+    const int64_t nnz = indptr[n_rows];
+    const int nt = host_threads(nnz);
+    // row ranges of about equal stored entries; count, then write at the prefix offsets
+    std::vector<int64_t> r0((size_t)nt + 1, n_rows), cnt((size_t)nt + 1, 0);
+    r0[0] = 0;
+    for (int t = 1; t < nt; ++t)
+        r0[t] = std::lower_bound(indptr, indptr + n_rows, nnz / nt * t) - indptr;
+    auto keep_entry = [&](int64_t r, int cr, int64_t e) {
+        const int32_t c = indices[e];
+        const float p = data[e];
+        const bool intra = chrom[c] == cr;
+        return (intra ? (use_intra && p >= intra_sigma) : (use_inter && p >= inter_sigma)) && c != (int32_t)r;
+    };
+    run_threads(nt, [&](int t) {
+        int64_t k = 0;
+        for (int64_t r = r0[t]; r < r0[t + 1]; ++r) {
+            const int cr = chrom[r];
+            for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e) k += keep_entry(r, cr, e) ? 1 : 0;
         }
-    }
-    return (k <= capacity) ? k : -1 - k;
+        cnt[t + 1] = k;
+    });
+    for (int t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
+    const int64_t total = cnt[nt];
+    if (total > capacity) return -1 - total;
+    run_threads(nt, [&](int t) {
+        int64_t k = cnt[t];
+        for (int64_t r = r0[t]; r < r0[t + 1]; ++r) {
+            const int cr = chrom[r];
+            for (int64_t e = indptr[r]; e < indptr[r + 1]; ++e) {
+                if (!keep_entry(r, cr, e)) continue;
+                out_i[k] = (int32_t)r; out_j[k] = indices[e]; out_p[k] = (double)data[e];
+                ++k;
+            }
+        }
+    });
+    return total;
 }
 
 // plast[i, j] of setup (:144-160, :177) as a merge join: the stored records (row, col, prob)
@@ -1135,27 +1206,65 @@ extern "C" int igmk_join_plast(int64_t n_rec, const int32_t* row, const int32_t*
     if (n_rec < 0 || n_pairs < 0 || (n_rec > 0 && (!row || !col || !prob)) || (n_pairs > 0 && (!ii || !jj || !out)))
         return -1;
     auto key = [n](int32_t a, int32_t b) { return (int64_t)a * n + b; };
-    int64_t last = -1;
-    for (int64_t t = 0; t < n_pairs; ++t) {
-        const int64_t kq = key(ii[t], jj[t]);
-        if (kq <= last) return 0;
-        last = kq;
+    const int nt = host_threads(n_rec + n_pairs);
+    std::atomic<int> ordered{1};
+    // candidate side: strictly increasing (checked range by range, one element of overlap); zero the output
+    run_threads(nt, [&](int t) {
+        const int64_t lo = n_pairs * t / nt, hi = n_pairs * (t + 1) / nt;
+        int64_t last = (lo > 0) ? key(ii[lo - 1], jj[lo - 1]) : -1;
+        bool ok = true;
+        for (int64_t q = lo; q < hi; ++q) {
+            const int64_t kq = key(ii[q], jj[q]);
+            ok = ok && kq > last;
+            last = kq;
+            out[q] = 0.0;
+        }
+        if (!ok) ordered.store(0);
+    });
+    if (!ordered.load()) return 0;
+    // record side: the records with row < n and col < n strictly increasing inside every range ...
+    std::vector<int64_t> first((size_t)nt, -1), lastk((size_t)nt, -1);
+    run_threads(nt, [&](int t) {
+        const int64_t lo = n_rec * t / nt, hi = n_rec * (t + 1) / nt;
+        int64_t last = -1, fst = -1;
+        bool ok = true;
+        for (int64_t e = lo; e < hi; ++e) {
+            if (row[e] >= n || col[e] >= n) continue;
+            const int64_t kr = key(row[e], col[e]);
+            if (fst < 0) fst = kr;
+            ok = ok && kr > last;
+            last = kr;
+        }
+        first[t] = fst; lastk[t] = last;
+        if (!ok) ordered.store(0);
+    });
+    if (!ordered.load()) return 0;
+    {   // ... and across the ranges
+        int64_t last = -1;
+        for (int t = 0; t < nt; ++t) {
+            if (first[t] < 0) continue;
+            if (first[t] <= last) return 0;
+            last = lastk[t];
+        }
     }
-    last = -1;
-    for (int64_t e = 0; e < n_rec; ++e) {
-        if (row[e] >= n || col[e] >= n) continue;
-        const int64_t kr = key(row[e], col[e]);
-        if (kr <= last) return 0;
-        last = kr;
-    }
-    for (int64_t t = 0; t < n_pairs; ++t) out[t] = 0.0;
-    int64_t t = 0;
-    for (int64_t e = 0; e < n_rec && t < n_pairs; ++e) {
-        if (row[e] >= n || col[e] >= n) continue;
-        const int64_t kr = key(row[e], col[e]);
-        while (t < n_pairs && key(ii[t], jj[t]) < kr) ++t;
-        if (t < n_pairs && key(ii[t], jj[t]) == kr) out[t] = (double)prob[e];
-    }
+    // merge: every record range starts at the candidate its first key points to; the keys of
+    // different ranges are disjoint, so the ranges write different candidates
+    run_threads(nt, [&](int t) {
+        if (first[t] < 0) return;
+        const int64_t lo = n_rec * t / nt, hi = n_rec * (t + 1) / nt;
+        int64_t a = 0, b = n_pairs;                       // first candidate with key >= first[t]
+        while (a < b) {
+            const int64_t m = (a + b) >> 1;
+            if (key(ii[m], jj[m]) < first[t]) a = m + 1; else b = m;
+        }
+        int64_t q = a;
+        for (int64_t e = lo; e < hi && q < n_pairs; ++e) {
+            if (row[e] >= n || col[e] >= n) continue;
+            const int64_t kr = key(row[e], col[e]);
+            while (q < n_pairs && key(ii[q], jj[q]) < kr) ++q;
+            if (q < n_pairs && key(ii[q], jj[q]) == kr) out[q] = (double)prob[e];
+        }
+    });
     return 1;
 }
 
@@ -1168,26 +1277,51 @@ extern "C" int igmk_expand_records(igmk_ctx* c, int64_t n_pairs,
                                    int64_t capacity, int64_t* n_records) {
     if (!c || !c->have_index) return fail(IGMK_ESTATE, "igmk_expand_records: index not set");
     if (n_pairs < 0 || (n_pairs > 0 && (!pi || !pj || !res))) return fail(IGMK_EINVAL, "igmk_expand_records: bad argument");
-    int64_t k = 0;
-    for (int64_t t = 0; t < n_pairs; ++t) {
-        const igmk_pair_result& r = res[t];
-        if (r.nrec <= 0) continue;
-        const int i = pi[t], j = pj[t];
-        if (i < 0 || j < 0 || i >= c->n_hap || j >= c->n_hap) return fail(IGMK_EINVAL, "igmk_expand_records: pair %lld out of range", (long long)t);
-        const HapEntry& a = c->h_hap[i];
-        const HapEntry& b = c->h_hap[j];
-        if (k + r.nrec > capacity) return fail(IGMK_EINVAL, "igmk_expand_records: capacity %lld too small", (long long)capacity);
-        const int ab[2] = {a.b0, a.b1}, bb[2] = {b.b0, b.b1};
-        const int na = a.b1 >= 0 ? 2 : 1, nb = b.b1 >= 0 ? 2 : 1;
-        if (a.chrom == b.chrom) {
-            const int m = na < nb ? na : nb;                    // zip(ii, jj)
-            for (int u = 0; u < m; ++u) { row[k] = ab[u]; col[k] = bb[u]; dist[k] = r.dist; prob[k] = r.prob; ++k; }
-        } else {
-            for (int u = 0; u < na; ++u)                        // for i0 in ii for i1 in jj
-                for (int w = 0; w < nb; ++w) { row[k] = ab[u]; col[k] = bb[w]; dist[k] = r.dist; prob[k] = r.prob; ++k; }
+    const int nt = host_threads(n_pairs);
+    // records of a pair: the kernel's nrec, re-derived here from the index (and checked against
+    // it while writing); offsets by a prefix sum over pair ranges
+    std::vector<int64_t> off((size_t)nt + 1, 0), bad((size_t)nt, -1);
+    const int n_hap = c->n_hap;
+    run_threads(nt, [&](int t) {
+        const int64_t lo = n_pairs * t / nt, hi = n_pairs * (t + 1) / nt;
+        int64_t k = 0;
+        for (int64_t q = lo; q < hi; ++q) {
+            if (res[q].nrec <= 0) continue;
+            if (pi[q] < 0 || pj[q] < 0 || pi[q] >= n_hap || pj[q] >= n_hap) { if (bad[t] < 0) bad[t] = q; continue; }
+            k += res[q].nrec;
         }
+        off[t + 1] = k;
+    });
+    for (int t = 0; t < nt; ++t) {
+        if (bad[t] >= 0) return fail(IGMK_EINVAL, "igmk_expand_records: pair %lld out of range", (long long)bad[t]);
+        off[t + 1] += off[t];
     }
-    if (n_records) *n_records = k;
+    if (off[nt] > capacity) return fail(IGMK_EINVAL, "igmk_expand_records: capacity %lld too small", (long long)capacity);
+    std::atomic<int> mismatch{0};
+    run_threads(nt, [&](int t) {
+        const int64_t lo = n_pairs * t / nt, hi = n_pairs * (t + 1) / nt;
+        int64_t k = off[t];
+        for (int64_t q = lo; q < hi; ++q) {
+            const igmk_pair_result& r = res[q];
+            if (r.nrec <= 0) continue;
+            const HapEntry& a = c->h_hap[pi[q]];
+            const HapEntry& b = c->h_hap[pj[q]];
+            const int ab[2] = {a.b0, a.b1}, bb[2] = {b.b0, b.b1};
+            const int na = a.b1 >= 0 ? 2 : 1, nb = b.b1 >= 0 ? 2 : 1;
+            const int64_t k0 = k;
+            if (k + (a.chrom == b.chrom ? (na < nb ? na : nb) : na * nb) > off[t + 1]) { mismatch.store(1); return; }
+            if (a.chrom == b.chrom) {
+                const int m = na < nb ? na : nb;                    // zip(ii, jj)
+                for (int u = 0; u < m; ++u) { row[k] = ab[u]; col[k] = bb[u]; dist[k] = r.dist; prob[k] = r.prob; ++k; }
+            } else {
+                for (int u = 0; u < na; ++u)                        // for i0 in ii for i1 in jj
+                    for (int w = 0; w < nb; ++w) { row[k] = ab[u]; col[k] = bb[w]; dist[k] = r.dist; prob[k] = r.prob; ++k; }
+            }
+            if (k - k0 != r.nrec) { mismatch.store(1); return; }
+        }
+    });
+    if (mismatch.load()) return fail(IGMK_EINVAL, "igmk_expand_records: record counts do not match the index");
+    if (n_records) *n_records = off[nt];
     return IGMK_OK;
 }
 

@@ -184,6 +184,12 @@ class ActdistEngine:
         if xyz is not None:
             self.upload_coordinates(xyz)
 
+    def reserve_pairs(self, n_pairs: int) -> None:
+        """Size the device buffers of the host entry points for lists of up to ``n_pairs``."""
+        if n_pairs > getattr(self, "_reserved_pairs", 0):
+            check(self._lib.igmk_reserve_pairs(self._ctx, int(n_pairs)))
+            self._reserved_pairs = int(n_pairs)
+
     def actdist_buffers(self, n: int, b_i, b_j, b_pwish, b_plast, b_out, contact_range: float = 2.0,
                         it_corr: int = 0, mode="LB", algo: int = ALGO_FAST) -> None:
         """A-step on caller-owned (ideally page-locked) host buffers, no copies on the Python

@@ -22,7 +22,8 @@ Extra, optional keys (all under ``restraints/Hi-C``): ``gpu_mode`` ("LB" |
 device id), ``gpu_devices`` / ``gpu_max_devices`` (devices one task drives concurrently;
 default: all visible), ``write_text_tmp`` (also write the reference's ``%d.out.tmp``),
 ``reference_task_files`` (``%d.in.npy`` in the reference's float64 (n, 4) layout instead of
-one typed row per pair), ``write_task_files`` (False: tasks run in this process only).
+one typed row per pair), ``write_task_files`` (default: only when the controller is not the
+serial one - tasks of this process take their arrays from memory and leave their records there).
 """
 from __future__ import annotations
 
@@ -202,6 +203,8 @@ _engine_cache = {}
 _staged_cache = {}
 _matrix_cache = {}
 _handoff = {}          # in-file path -> (ii, jj, pw, pl): setup() -> task() inside one process
+_handoff_out = {}      # out-file path -> packed records: task() -> reduce() inside one process
+_max_pairs = {}        # tmp_dir -> stored entries of the matrix = the longest list any sigma can produce
 LAST_TIMING = {}       # seconds spent in the phases of the most recent setup / task / reduce (diagnostic)
 
 # task input file: one row per candidate pair (the reference stores a float64 (n, 4) array)
@@ -302,7 +305,7 @@ def visible_devices(dictHiC):
     return devs[:int(dictHiC.get("gpu_max_devices", len(devs)))] or [first]
 
 
-def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr, mode):
+def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr, mode, max_pairs=0):
     """get_actdist for every pair, the list cut into contiguous shares, one per device, all
     devices working at the same time (one host thread per device; the C library releases
     the GIL).  The reference runs its batches concurrently on the workers of its controller
@@ -335,6 +338,8 @@ def actdist_on_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr
 
     def run(k):
         lo, hi = int(bounds[k]), int(bounds[k + 1])
+        if max_pairs:                       # the longest list of the run: device buffers sized once
+            engines[k].reserve_pairs(-(-int(max_pairs) // len(devices)))
         if hi == lo:
             engines[k].stage_pending()
             return
@@ -409,6 +414,12 @@ class ActivationDistanceStep(Step):
         # this process takes the arrays from memory instead of reading the file back
         bounds = np.linspace(0, len(ii), n_shards + 1).astype(np.int64)
         _handoff.clear()
+        _handoff_out.clear()
+        # a serial controller runs the tasks inside this process (igm/parallel/parallel_controller.py):
+        # the arrays are handed over in memory and the task files are not needed
+        in_process = "Serial" in type(getattr(self, "controller", None)).__name__
+        write_files = (bool(dictHiC.get("write_task_files", not in_process)) or bool(self.keep_temporary_files)
+                       or bool(dictHiC.get("reference_task_files", False)) or bool(dictHiC.get("write_text_tmp", False)))
         for b in range(n_shards):
             lo, hi = bounds[b], bounds[b + 1]
             fname = os.path.join(self.tmp_dir, "%d.in.npy" % b)
@@ -416,13 +427,16 @@ class ActivationDistanceStep(Step):
                 # the reference's own layout: float64 (n, 4) = (i, j, pwish, plast) (:181-186)
                 np.save(fname, np.stack([ii[lo:hi].astype(np.float64), jj[lo:hi].astype(np.float64),
                                          pw[lo:hi], pl[lo:hi]], axis=1))
-            elif dictHiC.get("write_task_files", True):
+            elif write_files:
                 rows = np.empty(hi - lo, dtype=PAIR_DTYPE)
                 rows["i"], rows["j"], rows["pwish"], rows["plast"] = ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi]
                 np.save(fname, rows)
-            _handoff[fname] = (ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi])
+            _handoff[fname] = (ii[lo:hi], jj[lo:hi], pw[lo:hi], pl[lo:hi], write_files)
         LAST_TIMING["setup_files_s"] = time.perf_counter() - t0
         self.argument_list = range(n_shards)
+        self.n_candidate_pairs = int(len(ii))
+        _max_pairs.clear()
+        _max_pairs[self.tmp_dir] = int(len(pm.indices)) // n_shards + 1
 
     @staticmethod
     def task(batch_id, cfg, tmp_dir):
@@ -431,8 +445,9 @@ class ActivationDistanceStep(Step):
         in_name = os.path.join(tmp_dir, "%d.in.npy" % batch_id)
         out_name = os.path.join(tmp_dir, "%d.out.npy" % batch_id)
         held = _handoff.pop(in_name, None)
+        write_out = True
         if held is not None:
-            ii, jj, pw, pl = held
+            ii, jj, pw, pl, write_out = held
         else:
             params = np.load(in_name, mmap_mode="r")
             if params.dtype.names:
@@ -444,7 +459,10 @@ class ActivationDistanceStep(Step):
                 ii = np.zeros(0, np.int32)
                 jj, pw, pl = ii, np.zeros(0), np.zeros(0)
         if len(ii) == 0:
-            np.save(out_name, np.zeros((4, 0), dtype=np.uint32))
+            if write_out:
+                np.save(out_name, np.zeros((4, 0), dtype=np.uint32))
+            else:
+                _handoff_out[out_name] = np.zeros((4, 0), dtype=np.uint32)
             return
         # one task drives every visible GPU at once; several tasks (gpu_shards > 1: workers of
         # a parallel controller) take one device each
@@ -454,13 +472,16 @@ class ActivationDistanceStep(Step):
             devices = [devices[batch_id % len(devices)]]
         eng, res = actdist_on_devices(cfg.get("optimization/structure_output"), devices, ii, jj, pw, pl,
                                       dictHiC.get("contact_range", 2.0), 1 if it_corr == 1 else 0,
-                                      dictHiC.get("gpu_mode", "LB"))
+                                      dictHiC.get("gpu_mode", "LB"), max_pairs=_max_pairs.get(tmp_dir, 0))
         import time
         t0 = time.perf_counter()
         row, col, dist, prob = eng.expand_records(ii, jj, res)
         LAST_TIMING["task_expand_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        np.save(out_name, pack_records(row, col, dist, prob))
+        if write_out:
+            np.save(out_name, pack_records(row, col, dist, prob))
+        else:
+            _handoff_out[out_name] = (row, col, dist, prob)          # reduce() of this process takes them
         LAST_TIMING["task_save_s"] = time.perf_counter() - t0
         if dictHiC.get("write_text_tmp", False):
             # the reference's own wire format (:228-230), for byte-level comparison
@@ -473,8 +494,15 @@ class ActivationDistanceStep(Step):
     def reduce(self):
         actdist_file = os.path.join(self.tmp_dir, "actdist.hdf5")
         last_actdist_file = self.cfg["runtime"]["Hi-C"].get("actdist_file", None)
-        columns = unpack_records([np.load(os.path.join(self.tmp_dir, "%d.out.npy" % i))
-                                  for i in self.argument_list])
+        parts = []
+        for i in self.argument_list:
+            name = os.path.join(self.tmp_dir, "%d.out.npy" % i)
+            held = _handoff_out.pop(name, None)                      # a task of this process left them in memory
+            parts.append(held if held is not None else np.load(name))
+        if len(parts) == 1 and isinstance(parts[0], tuple):
+            columns = dict(zip(("row", "col", "dist", "prob"), parts[0]))
+        else:
+            columns = unpack_records([pack_records(*a) if isinstance(a, tuple) else a for a in parts])
 
         additional_data = []
         if "Hi-C" in self.cfg["runtime"]:

@@ -111,6 +111,11 @@ int igmk_actdist_host(igmk_ctx* ctx, int64_t n_pairs,
                       float contact_range, int it_corr, int mode, int algo,
                       igmk_pair_result* out);
 
+/* Optional: size the device buffers of the *_host entry points for lists of up to n_pairs
+ * pairs now (the sigma sweep's lists grow from step to step, :69-98; growing the buffers costs a
+ * device-wide synchronisation and tens of milliseconds each time). */
+int igmk_reserve_pairs(igmk_ctx* ctx, int64_t n_pairs);
+
 /* The whole device side of ActivationDistanceStep.task in one call: stage the population
  * `xyz` (host memory, the .hss layout of igmk_upload_coords; every A-step follows an M-step
  * that rewrote it, igm/steps/ModelingStep.py:730-782, read back through

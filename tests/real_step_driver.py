@@ -48,7 +48,7 @@ def main():
     pm.save_hcs(hcs)
     calls = {"task": 0}
     if fake:
-        def fake_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr, mode):
+        def fake_devices(hss_path, devices, ii, jj, pw, pl, contact_range, it_corr, mode, max_pairs=0):
             calls["task"] += 1
             recs, dets = orc.run_pairs(ii, jj, pw, pl, pop.coordinates, pop.radii, pop.chrom_hap(), pop.copy_index,
                                        it_corr, contact_range, orc.MODE_LB)

@@ -120,7 +120,7 @@ def test_step_bookkeeping_name_setup_reduce_skip(tmp_path):
     pm = _small_matrix(1)
     hcs = str(tmp_path / "m.hcs")
     pm.save_hcs(hcs)
-    cfg = _cfg(tmp_path, hcs, "unused.hss", gpu_shards=3)
+    cfg = _cfg(tmp_path, hcs, "unused.hss", gpu_shards=3, write_task_files=True)   # (a parallel controller's default)
     cfg["runtime"]["opt_iter"] = 2
     step = S.ActivationDistanceStep(cfg)
     # sigma lists are consumed exactly as the reference does (:69-98)
@@ -396,3 +396,39 @@ def test_engine_cache_deferred_upload(tmp_path, monkeypatch):
     assert log[-1] == ("stage", "xyz")
     S._get_engines(a, [1])
     assert log[-1] == ("new", 1, True)
+
+
+def test_threaded_host_phases_match_numpy_forms(tmp_path):
+    """Lists long enough for the C library to split the candidate filter and the plast join over
+    several host threads (> 65 536 entries per thread): same output as the NumPy forms."""
+    from igm_b200 import hdf5
+    rng = np.random.default_rng(5)
+    n, per = 3000, 170
+    cols = np.sort(np.stack([rng.choice(n, per, replace=False) for _ in range(n)]), axis=1)
+    indptr = np.arange(0, n * per + 1, per, dtype=np.int64)
+    data = rng.uniform(0, 0.05, n * per).astype(np.float32)
+    chrom = np.sort(rng.integers(0, 23, n)).astype(np.int32)
+    pm = S.ProbMatrix(indptr, cols.reshape(-1).astype(np.int32), data, chrom)
+    a = S.filter_candidates(pm, 0.01, 0.02, native=True)
+    b = S.filter_candidates(pm, 0.01, 0.02, native=False)
+    assert len(a[0]) > 200000
+    for x, y in zip(a, b):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    # previous-iteration file: every third candidate has a stored probability, plus records of
+    # second copies (row / col >= n) in between, which the join must skip
+    ii, jj, _ = a
+    keep = np.arange(len(ii)) % 3 == 0
+    row = np.repeat(ii[keep], 2)
+    col = np.repeat(jj[keep], 2)
+    row[1::2] += n
+    col[1::2] += n
+    prob = rng.uniform(0, 1, len(row)).astype(np.float32)
+    f = str(tmp_path / "prev.hdf5")
+    hdf5.write_h5(f, {"row": row.astype(np.int32), "col": col.astype(np.int32),
+                      "dist": np.zeros(len(row), np.float32), "prob": prob})
+    p1 = S.lookup_plast(f, n, ii, jj, native=True)
+    p0 = S.lookup_plast(f, n, ii, jj, native=False)
+    assert np.array_equal(p1, p0) and np.count_nonzero(p1) > 60000
+    # an unsorted candidate list makes the native join decline (the general path answers)
+    perm = rng.permutation(len(ii))
+    assert np.array_equal(S.lookup_plast(f, n, ii[perm], jj[perm], native=True), p0[perm])

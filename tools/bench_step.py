@@ -67,8 +67,7 @@ def main():
         t = time.perf_counter(); step.reduce(); ph["reduce_s"] = time.perf_counter() - t
         with hdf5.open_h5(cfg["runtime"]["Hi-C"]["actdist_file"]) as f:
             ph["records"] = int(len(f["row"]))
-        ph["pairs"] = int(sum(len(np.load(os.path.join(step.tmp_dir, "%d.in.npy" % a), mmap_mode="r"))
-                              for a in step.argument_list))
+        ph["pairs"] = int(step.n_candidate_pairs)
         ph["sigma"] = cfg["runtime"]["Hi-C"]["intra_sigma"]
         import igm_b200.steps  # noqa: F401
         ph["detail"] = {k: round(v, 4) for k, v in sys.modules["igm_b200.steps.ActivationDistanceStep"].LAST_TIMING.items()}
