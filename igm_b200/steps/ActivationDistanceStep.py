@@ -52,8 +52,22 @@ def _pair_buffer(n, dtype, name):
         return np.empty(n, dtype)
 
 
+def count_candidates(pm: ProbMatrix, intra_sigma, inter_sigma) -> int:
+    """Length of the list ``filter_candidates`` would return (one counting pass in the C library)."""
+    use_intra = intra_sigma is not False and intra_sigma is not None
+    use_inter = inter_sigma is not False and inter_sigma is not None
+    if not (use_intra or use_inter):
+        return 0
+    k = _lib.load().igmk_filter_candidates(pm.n, _lib.ptr(pm.indptr), _lib.ptr(pm.indices), _lib.ptr(pm.data),
+                                           _lib.ptr(pm.chrom), int(use_intra),
+                                           float(np.float32(intra_sigma)) if use_intra else 0.0, int(use_inter),
+                                           float(np.float32(inter_sigma)) if use_inter else 0.0,
+                                           None, None, None, 0)
+    return int(-1 - k) if k < 0 else int(k)
+
+
 def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np.float32, native=True,
-                      pinned=False):
+                      pinned=False, capacity=None):
     """Candidate filter of the reference's setup loop (:166-178), vectorised.
 
     Stored non-zeros are visited in CSR row-major order (what ``coo_generator``
@@ -74,7 +88,7 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
     if dt == np.float32 and native:
         # one pass over the CSR arrays in the C library (igmk_filter_candidates)
         lib = _lib.load()
-        cap = int(len(pm.indices))
+        cap = int(len(pm.indices)) if capacity is None else int(capacity)
         if pinned:
             oi, oj, op = _pair_buffer(cap, np.int32, "i"), _pair_buffer(cap, np.int32, "j"), _pair_buffer(cap, np.float64, "w")
         else:
@@ -84,6 +98,8 @@ def filter_candidates(pm: ProbMatrix, intra_sigma, inter_sigma, compare_dtype=np
                                        float(np.float32(intra_sigma)) if use_intra else 0.0, int(use_inter),
                                        float(np.float32(inter_sigma)) if use_inter else 0.0,
                                        _lib.ptr(oi), _lib.ptr(oj), _lib.ptr(op), cap)
+        if k < 0 and capacity is not None:           # a capacity hint that was too small
+            return filter_candidates(pm, intra_sigma, inter_sigma, compare_dtype, native, pinned, None)
         if k < 0:
             raise RuntimeError("igmk_filter_candidates failed (%d)" % k)
         if pinned:
@@ -402,11 +418,18 @@ class ActivationDistanceStep(Step):
 
         import time
         t0 = time.perf_counter()
-        ii, jj, pw = filter_candidates(pm, intra_sigma, inter_sigma, pinned=True)
+        # the longest list this run can still produce (the smallest sigmas of the remaining
+        # schedule, :69-98): the page-locked buffers and the device buffers are sized for it once
+        def smallest(cur, rest):
+            vals = [v for v in [cur] + list(rest or []) if v is not False and v is not None]
+            return min(vals) if vals else cur
+        cap = count_candidates(pm, smallest(intra_sigma, self.cfg.get("runtime/Hi-C/intra_sigma_list", [])),
+                               smallest(inter_sigma, self.cfg.get("runtime/Hi-C/inter_sigma_list", [])))
+        ii, jj, pw = filter_candidates(pm, intra_sigma, inter_sigma, pinned=True, capacity=cap)
         LAST_TIMING["setup_filter_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        pl = lookup_plast(last_actdist_file, n, ii, jj, out=_pair_buffer(len(pm.indices), np.float64, "l"))
-        _pair_buffer(len(pm.indices), _lib.PAIR_RESULT_DTYPE, "o")     # the task's result buffer: locked once per run too
+        pl = lookup_plast(last_actdist_file, n, ii, jj, out=_pair_buffer(cap, np.float64, "l"))
+        _pair_buffer(cap, _lib.PAIR_RESULT_DTYPE, "o")     # the task's result buffer: locked once per run too
         LAST_TIMING["setup_plast_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         # contiguous, equal-count shards keep bead-i locality and output order.  The task input
@@ -436,7 +459,7 @@ class ActivationDistanceStep(Step):
         self.argument_list = range(n_shards)
         self.n_candidate_pairs = int(len(ii))
         _max_pairs.clear()
-        _max_pairs[self.tmp_dir] = int(len(pm.indices)) // n_shards + 1
+        _max_pairs[self.tmp_dir] = cap // n_shards + 1
 
     @staticmethod
     def task(batch_id, cfg, tmp_dir):
