@@ -522,6 +522,38 @@ def test_peer_store_entry_point_single_gpu(nstruct):
     assert got[0].tobytes() == ref.tobytes() and got[1].tobytes() == ref.tobytes()
 
 
+@pytest.mark.parametrize("n_peers", [1, 3, 8, 11])
+@pytest.mark.parametrize("n", [5, 1000, 60001])
+def test_peer_store_many_buffers(n_peers, n):
+    """Multi-GPU emit (finished records stored into every gather buffer from inside K1) with 1 to
+    11 buffers, all on this GPU: every buffer equals the ordinary path - short and long lists,
+    pairs the list form hands to the key-array kernel, invalid pairs in between."""
+    import torch
+    from igm_b200 import synthetic, _lib
+    from igm_b200.engine import ActdistEngine
+    pop = synthetic.make_population(2_000_000, 700, seed=5, genome_scale=0.03)
+    rng = np.random.default_rng(n + n_peers)
+    ii = rng.integers(0, pop.n_hap - 1, n).astype(np.int32)
+    jj = (ii + 1 + rng.integers(0, 40, n)).clip(max=pop.n_hap - 1).astype(np.int32)
+    nc, ch = pop.copy_index.ncopies(), pop.chrom_hap()
+    bad = ((ch[ii] == ch[jj]) & (nc[ii] != nc[jj]))
+    jj[bad] = ii[bad]                                         # i == j: empty result slot
+    pw = np.exp(rng.uniform(np.log(0.004), np.log(0.2), n))
+    pw[::17] = 0.9                                            # heavy pairs: handed to the key-array kernel
+    dev = torch.device("cuda:0")
+    with ActdistEngine(pop, 0) as eng:
+        ref = eng.actdist(ii, jj, pw, None, 2.0, 1, "LB")
+        d_i, d_j = torch.from_numpy(ii).to(dev), torch.from_numpy(jj).to(dev)
+        d_pw, d_pl = torch.from_numpy(pw).to(dev), torch.zeros(n, dtype=torch.float64, device=dev)
+        bufs = torch.full((n_peers, n, 32), 0xEE, dtype=torch.uint8, device=dev)
+        peers = torch.tensor([bufs[k].data_ptr() for k in range(n_peers)], dtype=torch.int64, device=dev)
+        eng.actdist_device_peers(d_i, d_j, d_pw, d_pl, peers, n_peers, n, 2.0, 1, "LB")
+        torch.cuda.synchronize()
+        got = bufs.cpu().numpy().reshape(n_peers, -1).view(_lib.PAIR_RESULT_DTYPE)
+    for k in range(n_peers):
+        assert got[k].tobytes() == ref.tobytes(), k
+
+
 def test_swapped_and_duplicate_pairs():
     """i > j pairs, duplicates and unsorted order behave like independent get_actdist calls."""
     from igm_b200 import synthetic
