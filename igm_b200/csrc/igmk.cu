@@ -112,7 +112,8 @@ struct igmk_ctx {
     int jblock_slab = 1;         // IGMK_JBLOCK_SLAB: slab pipeline sizes J-blocks by one slab's rows (0: whole rows; +2 %)
     int slab_batch = kSlabBatch; // IGMK_SLAB_BATCH: pairs per batch of the slab pipeline (lists of a batch should stay in L2)
     int slab_form = 1;           // IGMK_SLAB: populations > 1024 structures run the list form slab by slab (0: one CTA per pair)
-    int list_tile_slots = 2;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel
+    int list_tile_slots = 1;     // IGMK_LIST_TILE_SLOTS: locus-i tiles per CTA of the list-form warp kernel (2: -1.5 % on config 2,
+                                 // no change on config 5; the second slot's 24 KB are worth more as L1)
     float list_budget = 20.f;    // IGMK_LIST_BUDGET: expected list entries per thread beyond which a pair goes to the key arrays
     unsigned int last_redo = 0;  // pairs the list form handed back in the most recent launch (igmk_last_redo_count)
     bool redo_pending = false;
