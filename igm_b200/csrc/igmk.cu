@@ -1346,7 +1346,11 @@ static int contact_launch(igmk_ctx* c, int haploid, int row0, int nrows, int col
     P.hap = c->d_hap; P.haploid = haploid;
     dim3 grid((ncols + kCtTile - 1) / kCtTile, (nrows + kCtTile - 1) / kCtTile);
     if (haploid) contact_tile_hap_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
-    else         contact_tile_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
+    else {
+        if (kCtDynBytes > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(contact_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtDynBytes));
+        contact_tile_kernel<<<grid, kCtThreads, kCtDynBytes, (cudaStream_t)stream>>>(P);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return IGMK_OK;

@@ -111,11 +111,30 @@ __device__ __forceinline__ void contact_accumulate_packed(const float* sa, const
     }
 }
 
-// Bead-level tile: tile indices are bead ids.
+// Bead-level tile: tile indices are bead ids.  The coordinate chunks are double-buffered:
+// chunk c + 1 travels global -> shared memory by per-thread asynchronous 16-byte copies
+// (cp.async / LDGSTS, zero fill for beads outside the tile) while chunk c is being computed on,
+// so a CTA waits for L2 only once, in front of its first chunk.
+#ifndef IGMK_CT_ASYNC
+#define IGMK_CT_ASYNC 1
+#endif
+constexpr int kCtBufFloats = kCtTile * kCtRow;               // one side, one buffer
+constexpr size_t kCtDynBytes = IGMK_CT_ASYNC ? (size_t)4 * kCtBufFloats * sizeof(float) : 0;   // [2 buffers][a | b]
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(src), "r"(n) : "memory");
+}
+
 __global__ void __launch_bounds__(kCtThreads, IGMK_CT_MINB)
 contact_tile_kernel(const ContactParams P) {
+#if IGMK_CT_ASYNC
+    extern __shared__ __align__(16) float s_dyn_ct[];      // [2][a: kCtBufFloats | b: kCtBufFloats]
+#else
     __shared__ __align__(16) float s_a[kCtTile * kCtRow];
     __shared__ __align__(16) float s_b[kCtTile * kCtRow];
+#endif
     __shared__ uint32_t s_cnt[kCtTile * kCtTile];
     __shared__ float s_rc[kCtTile * kCtRcRow];
 
@@ -143,6 +162,60 @@ contact_tile_kernel(const ContactParams P) {
         for (int bb = 0; bb < kCtBB; ++bb) cnt2[aa][bb] = 0ull;
 
     const size_t row = (size_t)3 * P.npad;
+#if IGMK_CT_ASYNC
+    // this thread's three 16-byte pieces of a chunk: (bead, component, 4 structures)
+    auto issue = [&](int s0, int buf) {
+        float* sa = s_dyn_ct + (size_t)buf * 2 * kCtBufFloats;
+        float* sb = sa + kCtBufFloats;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int f = t + kCtThreads * k;          // 0 .. 767
+            const int bead = f / 24, rem = f - bead * 24;
+            const int comp = rem >> 3, v4 = rem & 7;
+            const int a = a_base + bead, b = b_base + bead;
+            const size_t so = coord_off(s0 + 4 * v4) + (size_t)comp * kSeg;
+            const int dst = bead * kCtRow + comp * kCtStruct + 4 * v4;
+            cp_async16_zfill(sa + dst, (a < a_end) ? P.coords + (size_t)a * row + so : P.coords, a < a_end);
+            cp_async16_zfill(sb + dst, (b < b_end) ? P.coords + (size_t)b * row + so : P.coords, b < b_end);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nchunk = (P.nstruct + kCtStruct - 1) / kCtStruct;
+    issue(0, 0);
+    for (int c = 0; c < nchunk; ++c) {
+        const int s0 = c * kCtStruct;
+        float* sa = s_dyn_ct + (size_t)(c & 1) * 2 * kCtBufFloats;
+        const float* sb = sa + kCtBufFloats;
+        if (c + 1 < nchunk) {
+            issue(s0 + kCtStruct, (c + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            // structures past the end of the population: NaN on the row side, so their d2 is
+            // NaN and never counts (the padding in HBM is zero); each thread patches the
+            // pieces it copied itself
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int f = t + kCtThreads * k;
+                const int bead = f / 24, rem = f - bead * 24;
+                const int comp = rem >> 3, v4 = rem & 7;
+                const int sv = s0 + 4 * v4;
+                if (sv + 3 >= P.nstruct) {
+                    const float qn = __int_as_float(0x7fffffff);
+                    float* q = sa + bead * kCtRow + comp * kCtStruct + 4 * v4;
+                    if (sv >= P.nstruct) q[0] = qn;
+                    if (sv + 1 >= P.nstruct) q[1] = qn;
+                    if (sv + 2 >= P.nstruct) q[2] = qn;
+                    q[3] = qn;
+                }
+            }
+        }
+        __syncthreads();
+        if (P.strict) contact_accumulate_packed<true>(sa, sb, ta, tb, slice, P.negzero2, s_rc, cnt2);
+        else          contact_accumulate_packed<false>(sa, sb, ta, tb, slice, P.negzero2, s_rc, cnt2);
+        __syncthreads();                                   // buffer (c & 1) is refilled by the next iteration's issue
+    }
+#else
     for (int s0 = 0; s0 < P.nstruct; s0 += kCtStruct) {
         __syncthreads();
         // stage 32 beads x 3 components x 32 structures of each side
@@ -175,6 +248,7 @@ contact_tile_kernel(const ContactParams P) {
         if (P.strict) contact_accumulate_packed<true>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
         else          contact_accumulate_packed<false>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
     }
+#endif
 
     // combine the 4 structure slices
 #pragma unroll
@@ -197,7 +271,6 @@ contact_tile_kernel(const ContactParams P) {
             P.counts[(size_t)(a - P.row0) * P.ncols + (b - P.col0)] = s_cnt[e];
     }
 }
-
 
 // Haploid variant: tile indices are haploid loci and the counts of all copy combinations of a locus pair are summed
 // (Contactmatrix.sumCopies() after buildContactMap, HicEvaluationStep.py:109-111):
