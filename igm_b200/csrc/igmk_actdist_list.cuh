@@ -31,7 +31,9 @@ namespace igmk {
 #define IGMK_LSLOTS 44            // list words per thread; = 4 (mod 8): conflict-free 128-bit reads
 #endif
 #ifndef IGMK_LWPB
-#define IGMK_LWPB 20              // warps per CTA of the warp-group kernel
+#define IGMK_LWPB 24              // warps per CTA of the warp-group kernel: 6 per scheduler at 80 registers; with ONE
+                                  // locus-i tile slot 24 warps' lists (132 KB) + tile (24 KB) stay below the 164 KB
+                                  // shared-memory carve-out step (20 warps: 297, 24 warps: 312 M pairs/s on config 2)
 #endif
 #ifndef IGMK_LBT
 #define IGMK_LBT 320              // threads per CTA of the CTA-group kernel
