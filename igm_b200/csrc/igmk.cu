@@ -1345,7 +1345,11 @@ static int contact_launch(igmk_ctx* c, int haploid, int row0, int nrows, int col
     P.negzero2 = 0x8000000080000000ull;
     P.hap = c->d_hap; P.haploid = haploid;
     dim3 grid((ncols + kCtTile - 1) / kCtTile, (nrows + kCtTile - 1) / kCtTile);
-    if (haploid) contact_tile_hap_kernel<<<grid, kCtThreads, 0, (cudaStream_t)stream>>>(P);
+    if (haploid) {
+        if (kCtDynBytes > 48 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(contact_tile_hap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtDynBytes));
+        contact_tile_hap_kernel<<<grid, kCtThreads, kCtDynBytes, (cudaStream_t)stream>>>(P);
+    }
     else {
         if (kCtDynBytes > 48 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(contact_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtDynBytes));

@@ -278,8 +278,12 @@ contact_tile_kernel(const ContactParams P) {
 __global__ void __launch_bounds__(kCtThreads, IGMK_CT_MINB)
 contact_tile_hap_kernel(const ContactParams P) {
     constexpr bool HAP = true;
+#if IGMK_CT_ASYNC
+    extern __shared__ __align__(16) float s_dyn_ct[];      // [2][a: kCtBufFloats | b: kCtBufFloats]
+#else
     __shared__ __align__(16) float s_a[kCtTile * kCtRow];
     __shared__ __align__(16) float s_b[kCtTile * kCtRow];
+#endif
     __shared__ uint32_t s_cnt[kCtTile * kCtTile];
     __shared__ float s_rc[kCtTile * kCtRcRow];
     __shared__ int s_ida[2][kCtTile], s_idb[2][kCtTile];     // bead id per copy, -1: absent
@@ -329,6 +333,63 @@ contact_tile_hap_kernel(const ContactParams P) {
             const float r = __fmul_rn(P.contact_range, __fadd_rn(ra, rb));
             s_rc[(e >> 5) * kCtRcRow + (e & 31)] = __fmul_rn(r, r);
         }
+#if IGMK_CT_ASYNC
+        // double-buffered staging as in contact_tile_kernel; absent beads (outside the tile /
+        // haploid locus without a second copy) are zero-filled by the copy and overwritten with
+        // NaN behind the wait, like the structures past the end of the population
+        auto issue = [&](int s0, int buf) {
+            float* sa = s_dyn_ct + (size_t)buf * 2 * kCtBufFloats;
+            float* sb = sa + kCtBufFloats;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int f = t + kCtThreads * k;          // 0 .. 767
+                const int bead = f / 24, rem = f - bead * 24;
+                const int comp = rem >> 3, v4 = rem & 7;
+                const int a = s_ida[ca][bead], b = s_idb[cb][bead];
+                const size_t so = coord_off(s0 + 4 * v4) + (size_t)comp * kSeg;
+                const int dst = bead * kCtRow + comp * kCtStruct + 4 * v4;
+                cp_async16_zfill(sa + dst, (a >= 0) ? P.coords + (size_t)a * row + so : P.coords, a >= 0);
+                cp_async16_zfill(sb + dst, (b >= 0) ? P.coords + (size_t)b * row + so : P.coords, b >= 0);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        const int nchunk = (P.nstruct + kCtStruct - 1) / kCtStruct;
+        __syncthreads();                                   // (ids visible before the first issue)
+        issue(0, 0);
+        for (int c = 0; c < nchunk; ++c) {
+            const int s0 = c * kCtStruct;
+            float* sa = s_dyn_ct + (size_t)(c & 1) * 2 * kCtBufFloats;
+            float* sb = sa + kCtBufFloats;
+            if (c + 1 < nchunk) {
+                issue(s0 + kCtStruct, (c + 1) & 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                  // each thread patches the pieces it copied itself
+                const int f = t + kCtThreads * k;
+                const int bead = f / 24, rem = f - bead * 24;
+                const int comp = rem >> 3, v4 = rem & 7;
+                const int dst = bead * kCtRow + comp * kCtStruct + 4 * v4;
+                const int sv = s0 + 4 * v4;
+                if (s_ida[ca][bead] < 0) {
+                    *reinterpret_cast<float4*>(sa + dst) = make_float4(qn, qn, qn, qn);
+                } else if (sv + 3 >= P.nstruct) {
+                    if (sv >= P.nstruct) sa[dst] = qn;
+                    if (sv + 1 >= P.nstruct) sa[dst + 1] = qn;
+                    if (sv + 2 >= P.nstruct) sa[dst + 2] = qn;
+                    sa[dst + 3] = qn;
+                }
+                if (s_idb[cb][bead] < 0) *reinterpret_cast<float4*>(sb + dst) = make_float4(qn, qn, qn, qn);
+            }
+            __syncthreads();
+            if (P.strict) contact_accumulate_packed<true>(sa, sb, ta, tb, slice, P.negzero2, s_rc, cnt2);
+            else          contact_accumulate_packed<false>(sa, sb, ta, tb, slice, P.negzero2, s_rc, cnt2);
+            __syncthreads();                               // buffer (c & 1) is refilled by the next issue; s_rc by the next combination
+        }
+    }
+#else
         for (int s0 = 0; s0 < P.nstruct; s0 += kCtStruct) {
             __syncthreads();
             // stage 32 beads x 3 components x 32 structures of each side
@@ -369,6 +430,8 @@ contact_tile_hap_kernel(const ContactParams P) {
             else          contact_accumulate_packed<false>(s_a, s_b, ta, tb, slice, P.negzero2, s_rc, cnt2);
         }
     }
+
+#endif
 
     // combine the 4 structure slices
 #pragma unroll
